@@ -1,0 +1,156 @@
+/* p2gpu.h — C ABI of libp2gpu.so, the B200 (sm_100a) backend for the hot path of plonky2's
+ * CircuitData::prove as driven by the 0xPARC/plonky2-aes gadget crates.
+ *
+ * What it replaces.  The reference enters the path through one call, `data.prove(pw)`
+ * (/root/reference/aes-gcm/examples/aes_gcm_128.rs:52, aes-gcm/src/circuit_gcm.rs:781,
+ * aes-gcm/src/circuit_aes.rs:404-725, feistel/src/circuit.rs:151, ecgfp5/src/circuit.rs:97,
+ * poseidon-cipher/src/circuit.rs:188), which lands in the un-vendored dependency
+ * plonky2 @ 109d517 (/root/reference/Cargo.toml:12).  A maintainer patches that crate
+ * ([patch] on Cargo.toml:12) so that plonk::prover::prove_with_partition_witness calls
+ * p2g_prove(); INTEGRATION.md shows the Rust `extern "C"` block and the patch.
+ *
+ * Conventions: every function returns 0 on success or a negative P2G_E_* code; field elements
+ * are canonical little-endian u64 (< p = 2^64 - 2^32 + 1); the caller owns every host buffer;
+ * the library owns all device memory behind opaque handles; one ctx per device, used from one
+ * host thread at a time.  Nothing here falls back to the CPU: without a CUDA device
+ * p2g_ctx_create fails with P2G_E_CUDA.
+ */
+#ifndef P2GPU_H
+#define P2GPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2G_OK 0
+#define P2G_E_CUDA (-1)    /* CUDA runtime error; text via p2g_last_error */
+#define P2G_E_BADARG (-2)
+#define P2G_E_UNSAT (-3)   /* witness does not satisfy the circuit (quotient not a polynomial);
+                              mirrors prove() returning Err, /root/reference/aes-gcm/src/circuit_aes.rs:403-405 */
+#define P2G_E_POW (-4)
+#define P2G_E_NOMEM (-5)
+
+typedef struct p2g_ctx p2g_ctx;
+typedef struct p2g_batch p2g_batch;     /* device-resident PolynomialBatch (fri/oracle.rs) */
+typedef struct p2g_circuit p2g_circuit; /* device-resident prover data of one CircuitData */
+
+int32_t p2g_version(void);
+int32_t p2g_ctx_create(int32_t device, p2g_ctx** out);
+void p2g_ctx_destroy(p2g_ctx* ctx);
+const char* p2g_last_error(p2g_ctx* ctx);
+int32_t p2g_ctx_sync(p2g_ctx* ctx);
+/* the CUDA stream (cudaStream_t) every call on this ctx is ordered on — for event timing */
+void* p2g_ctx_stream(p2g_ctx* ctx);
+
+/* ---- PolynomialBatch::from_values / from_coeffs  (fri/oracle.rs) ------------------------------
+ * cols: ncols polynomials of n = 2^log_n words each, column-major ([ncols][n]).
+ * `*_host` read host memory (H2D inside the call); `*_dev` read device memory already in HBM.
+ * cap_out (host, 4 * 2^cap_height words) receives the Merkle cap; may be NULL. */
+int32_t p2g_commit_from_values(p2g_ctx* ctx, const uint64_t* cols_host, uint32_t ncols, uint32_t log_n,
+                               uint32_t rate_bits, uint32_t cap_height, p2g_batch** out, uint64_t* cap_out);
+int32_t p2g_commit_from_coeffs(p2g_ctx* ctx, const uint64_t* cols_host, uint32_t ncols, uint32_t log_n,
+                               uint32_t rate_bits, uint32_t cap_height, p2g_batch** out, uint64_t* cap_out);
+int32_t p2g_commit_from_values_dev(p2g_ctx* ctx, const uint64_t* cols_dev, uint32_t ncols, uint32_t log_n,
+                                   uint32_t rate_bits, uint32_t cap_height, p2g_batch** out, uint64_t* cap_out);
+int32_t p2g_commit_from_coeffs_dev(p2g_ctx* ctx, const uint64_t* cols_dev, uint32_t ncols, uint32_t log_n,
+                                   uint32_t rate_bits, uint32_t cap_height, p2g_batch** out, uint64_t* cap_out);
+int32_t p2g_batch_free(p2g_ctx* ctx, p2g_batch* b);
+/* read-back (parity tests, query phase). */
+int32_t p2g_batch_get_coeffs(p2g_ctx* ctx, const p2g_batch* b, uint64_t* out /*[ncols][n]*/);
+/* LDE values, column-major, bit-reversed index order: out[c*N + j] = f_c(7 * w_N^bitrev(j)) */
+int32_t p2g_batch_get_lde(p2g_ctx* ctx, const p2g_batch* b, uint64_t* out /*[ncols][N]*/);
+/* digests of tree level `level` (0 = leaf digests); level == path_len returns the cap */
+int32_t p2g_batch_get_level(p2g_ctx* ctx, const p2g_batch* b, uint32_t level, uint64_t* out);
+/* MerkleTree::get(leaf) + MerkleTree::prove(leaf): row (ncols words) and siblings (path_len*4) */
+int32_t p2g_batch_open_leaf(p2g_ctx* ctx, const p2g_batch* b, uint64_t leaf_index, uint64_t* row_out,
+                            uint64_t* siblings_out);
+
+/* ---- stand-alone MerkleTree::new over row-major leaves (hash/merkle_tree.rs) ------------------ */
+int32_t p2g_merkle_cap(p2g_ctx* ctx, const uint64_t* leaves_host, uint32_t log_leaves, uint32_t leaf_len,
+                       uint32_t cap_height, uint64_t* cap_out, uint64_t* leaf_digests_out /* may be NULL */);
+/* hash_n_to_m_no_pad on `count` independent inputs of `len` words each (row-major) -> 4 words each */
+int32_t p2g_hash_no_pad_many(p2g_ctx* ctx, const uint64_t* in_host, uint32_t count, uint32_t len, uint64_t* out_host);
+
+/* ---- circuit description: what CircuitBuilder::build leaves in ProverOnlyCircuitData +
+ *      CommonCircuitData (plonk/circuit_data.rs) and the quotient kernel needs ------------------ */
+enum { P2G_GATE_NOOP = 0, P2G_GATE_CONSTANT = 1, P2G_GATE_PUBLIC_INPUT = 2, P2G_GATE_ARITHMETIC = 3,
+       P2G_GATE_LOOKUP = 4, P2G_GATE_LOOKUP_TABLE = 5, P2G_GATE_POSEIDON = 6 };
+typedef struct {
+    int32_t kind;
+    int32_t selector_index;
+    int32_t group_start, group_end;
+    int32_t num_constraints;
+    int32_t param0;
+} p2g_gate;
+typedef struct {
+    int32_t degree_bits;
+    int32_t num_wires, num_routed_wires, num_constants;
+    int32_t num_challenges, quotient_degree_factor;
+    int32_t rate_bits, cap_height, pow_bits, num_query_rounds;
+    int32_t num_reduction_arity_bits; int32_t reduction_arity_bits[16];
+    int32_t num_selectors, num_lookup_selectors;
+    int32_t num_gates; const p2g_gate* gates;
+    int32_t num_gate_constraints;
+    int32_t num_partial_products;
+    int32_t num_luts;
+    const int32_t* lut_lens;
+    const uint16_t* lut_data;      /* (inp,out) pairs, all LUTs concatenated */
+    const int32_t* lookup_rows;    /* [num_luts][3]: last_lu_gate, last_lut_gate, first_lut_gate */
+    int32_t num_public_inputs;
+    const uint64_t* k_is;          /* [num_routed_wires] */
+    const uint64_t* constants_sigmas; /* [(selectors+lookup selectors+constants+routed)][n] values, host */
+    uint64_t circuit_digest[4];
+} p2g_circuit_desc;
+
+int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, p2g_circuit** out,
+                         uint64_t* constants_sigmas_cap_out /* may be NULL */);
+int32_t p2g_circuit_free(p2g_ctx* ctx, p2g_circuit* c);
+/* number of u64 words of a serialised proof for this circuit */
+size_t p2g_proof_words(const p2g_circuit* c);
+
+/* ---- the whole hot path: prove_with_partition_witness (plonk/prover.rs) ----------------------
+ * wires: [num_wires][n] host, column-major full witness; public_inputs: num_public_inputs words.
+ * proof_out: flat u64 proof (layout in DESIGN.md, identical to the oracle's). */
+int32_t p2g_prove(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host, const uint64_t* public_inputs,
+                  uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
+/* same with the witness already in HBM */
+int32_t p2g_prove_dev(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_dev, const uint64_t* public_inputs,
+                      uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
+
+/* stage read-backs for parity tests (valid after a p2g_prove on this ctx) */
+typedef struct {
+    uint64_t betas[4], gammas[4], deltas[16], alphas[4];
+    uint64_t zeta[2], fri_alpha[2], fri_betas[32];
+    uint64_t pow_witness;
+    uint64_t query_indices[64];
+} p2g_transcript;
+int32_t p2g_last_transcript(p2g_ctx* ctx, p2g_transcript* out);
+int32_t p2g_last_zs_values(p2g_ctx* ctx, uint64_t* out /*[num_zs_cols][n]*/);
+int32_t p2g_last_quotient_chunks(p2g_ctx* ctx, uint64_t* out /*[num_challenges*qdf][n]*/);
+
+/* per-stage device times of the last p2g_prove, milliseconds (CUDA events on the ctx stream) */
+typedef struct {
+    float h2d, wires_commit, zs_build, zs_commit, quotient, quotient_commit, openings, fri_combine,
+          fri_commit, pow, queries, total;
+} p2g_timings;
+int32_t p2g_last_timings(p2g_ctx* ctx, p2g_timings* out);
+int32_t p2g_set_timing(p2g_ctx* ctx, int32_t enabled);
+
+/* ---- individual hot-path stages, exposed for parity tests and kernel benchmarks -------------- */
+/* fri_proof_of_work (fri/prover.rs): lowest nonce whose response has >= pow_bits leading zeros.
+ * state: the 12-word duplex state with buffered inputs already overwritten; pos: slot of the nonce. */
+int32_t p2g_pow_grind(p2g_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t pow_bits, uint64_t* nonce_out);
+/* one FRI commit-phase fold (arity 2^arity_bits) of N ext values in bit-reversed order on the
+ * coset shift*<w_N>: out[k] = P'(x_k^arity) for the reference's coefficient-domain fold. */
+int32_t p2g_fri_fold(p2g_ctx* ctx, const uint64_t* values_host /*[N][2]*/, uint32_t log_n_values, uint32_t arity_bits,
+                     uint64_t shift, const uint64_t beta[2], uint64_t* out_host /*[N>>arity][2]*/);
+/* chained Poseidon permutations without memory traffic: the INT-pipe peak used as roofline
+ * denominator for the Merkle kernels.  Returns permutations per second. */
+int32_t p2g_poseidon_peak(p2g_ctx* ctx, uint32_t iters, double* perms_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,234 @@
+// C ABI of libp2gpu.so, part 1: context, PolynomialBatch commitment, Merkle/hash helpers.
+// See include/p2gpu.h for the reference interfaces each entry point replaces.
+#include "ctx.h"
+#include "poseidon.cuh"
+#include <string.h>
+#include <stdio.h>
+
+extern "C" int32_t p2g_version(void) { return 1; }
+
+extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
+    if (!out) return P2G_E_BADARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return P2G_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return P2G_E_CUDA;
+    p2g_ctx* ctx = new p2g_ctx();
+    ctx->device = device; ctx->timing = false; ctx->keep_debug = false;
+    memset(&ctx->timings, 0, sizeof(ctx->timings));
+    memset(&ctx->transcript, 0, sizeof(ctx->transcript));
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    ctx->pinned_words = 1 << 20;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinned_words * sizeof(gl_t)) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
+    *out = ctx;
+    return P2G_OK;
+}
+extern "C" void p2g_ctx_destroy(p2g_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    for (auto& kv : ctx->plans) ntt_plan_free(&kv.second);
+    cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+extern "C" const char* p2g_last_error(p2g_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" int32_t p2g_ctx_sync(p2g_ctx* ctx) { CU(cudaStreamSynchronize(ctx->st)); return P2G_OK; }
+extern "C" void* p2g_ctx_stream(p2g_ctx* ctx) { return (void*)ctx->st; }
+
+int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan** out) {
+    auto key = std::make_tuple(kind, log_n, kind == NTT_KIND_LDE ? rate_bits : 0);
+    auto it = ctx->plans.find(key);
+    if (it == ctx->plans.end()) {
+        NttPlan p;
+        if (ntt_plan_build(&p, kind, log_n, rate_bits, ctx->st) != 0) { ctx->err = "ntt_plan_build failed"; return P2G_E_CUDA; }
+        it = ctx->plans.emplace(key, p).first;
+    }
+    *out = &it->second;
+    return P2G_OK;
+}
+int ctx_alloc(p2g_ctx* ctx, gl_t** p, size_t words) {
+    CU(cudaMallocAsync((void**)p, (words ? words : 1) * sizeof(gl_t), ctx->st));
+    return P2G_OK;
+}
+void ctx_free(p2g_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->st); }
+
+int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+               uint32_t cap_height, bool from_values, p2g_batch** out, bool sync_cap) {
+    if (!ncols || log_n > 22 || log_n + rate_bits > 26 || cap_height > log_n + rate_bits) return P2G_E_BADARG;
+    p2g_batch* b = new p2g_batch();
+    b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->coeffs = b->lde = b->digests = b->cap = nullptr;
+    const size_t n = b->n(), N = b->N();
+    int rc;
+    if ((rc = ctx_alloc(ctx, &b->coeffs, (size_t)ncols * n))) return rc;
+    if ((rc = ctx_alloc(ctx, &b->lde, (size_t)ncols * N))) return rc;
+    if ((rc = ctx_alloc(ctx, &b->digests, merkle_digest_words(b->log_N(), cap_height)))) return rc;
+    if ((rc = ctx_alloc(ctx, &b->cap, (size_t)4 << cap_height))) return rc;
+    const NttPlan *inv, *lde;
+    if (from_values) {
+        if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, log_n, 0, &inv))) return rc;
+        if (ntt_launch(inv, cols_dev, n, b->coeffs, n, ncols, 1, ctx->st)) { ctx->err = "intt launch"; return P2G_E_CUDA; }
+    } else {
+        CU(cudaMemcpyAsync(b->coeffs, cols_dev, (size_t)ncols * n * sizeof(gl_t), cudaMemcpyDeviceToDevice, ctx->st));
+    }
+    if ((rc = ctx_get_plan(ctx, NTT_KIND_LDE, log_n, rate_bits, &lde))) return rc;
+    if (ntt_launch(lde, b->coeffs, n, b->lde, N, ncols, 0, ctx->st)) { ctx->err = "lde launch"; return P2G_E_CUDA; }
+    if (merkle_build(b->lde, 1, N, ncols, b->log_N(), cap_height, b->digests, b->cap, ctx->st)) { ctx->err = "merkle launch"; return P2G_E_CUDA; }
+    b->cap_host.resize((size_t)4 << cap_height);
+    if (sync_cap) {
+        CU(cudaMemcpyAsync(ctx->pinned, b->cap, b->cap_host.size() * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        memcpy(b->cap_host.data(), ctx->pinned, b->cap_host.size() * sizeof(gl_t));
+    }
+    *out = b;
+    return P2G_OK;
+}
+
+static int32_t commit_any(p2g_ctx* ctx, const uint64_t* cols, bool host, bool from_values, uint32_t ncols, uint32_t log_n,
+                          uint32_t rate_bits, uint32_t cap_height, p2g_batch** out, uint64_t* cap_out) {
+    if (!ctx || !cols || !out) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    gl_t* tmp = nullptr;
+    const gl_t* src = cols;
+    int rc;
+    if (host) {
+        size_t words = (size_t)ncols << log_n;
+        if ((rc = ctx_alloc(ctx, &tmp, words))) return rc;
+        CU(cudaMemcpyAsync(tmp, cols, words * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+        src = tmp;
+    }
+    rc = commit_dev(ctx, src, ncols, log_n, rate_bits, cap_height, from_values, out, true);
+    if (tmp) ctx_free(ctx, tmp);
+    if (rc) return rc;
+    if (cap_out) memcpy(cap_out, (*out)->cap_host.data(), (*out)->cap_host.size() * sizeof(gl_t));
+    return P2G_OK;
+}
+extern "C" int32_t p2g_commit_from_values(p2g_ctx* ctx, const uint64_t* c, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+                                          uint32_t cap_height, p2g_batch** out, uint64_t* cap_out) {
+    return commit_any(ctx, c, true, true, ncols, log_n, rate_bits, cap_height, out, cap_out);
+}
+extern "C" int32_t p2g_commit_from_coeffs(p2g_ctx* ctx, const uint64_t* c, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+                                          uint32_t cap_height, p2g_batch** out, uint64_t* cap_out) {
+    return commit_any(ctx, c, true, false, ncols, log_n, rate_bits, cap_height, out, cap_out);
+}
+extern "C" int32_t p2g_commit_from_values_dev(p2g_ctx* ctx, const uint64_t* c, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+                                              uint32_t cap_height, p2g_batch** out, uint64_t* cap_out) {
+    return commit_any(ctx, c, false, true, ncols, log_n, rate_bits, cap_height, out, cap_out);
+}
+extern "C" int32_t p2g_commit_from_coeffs_dev(p2g_ctx* ctx, const uint64_t* c, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+                                              uint32_t cap_height, p2g_batch** out, uint64_t* cap_out) {
+    return commit_any(ctx, c, false, false, ncols, log_n, rate_bits, cap_height, out, cap_out);
+}
+extern "C" int32_t p2g_batch_free(p2g_ctx* ctx, p2g_batch* b) {
+    if (!ctx || !b) return P2G_E_BADARG;
+    ctx_free(ctx, b->coeffs); ctx_free(ctx, b->lde); ctx_free(ctx, b->digests); ctx_free(ctx, b->cap);
+    delete b;
+    return P2G_OK;
+}
+extern "C" int32_t p2g_batch_get_coeffs(p2g_ctx* ctx, const p2g_batch* b, uint64_t* out) {
+    CU(cudaMemcpyAsync(out, b->coeffs, (size_t)b->ncols * b->n() * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return P2G_OK;
+}
+extern "C" int32_t p2g_batch_get_lde(p2g_ctx* ctx, const p2g_batch* b, uint64_t* out) {
+    CU(cudaMemcpyAsync(out, b->lde, (size_t)b->ncols * b->N() * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return P2G_OK;
+}
+extern "C" int32_t p2g_batch_get_level(p2g_ctx* ctx, const p2g_batch* b, uint32_t level, uint64_t* out) {
+    uint32_t L = b->path_len();
+    if (level > L) return P2G_E_BADARG;
+    const gl_t* src = level == L ? b->cap : b->digests + merkle_level_offset(b->log_N(), level);
+    size_t words = (size_t)4 << (b->log_N() - level);
+    CU(cudaMemcpyAsync(out, src, words * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return P2G_OK;
+}
+extern "C" int32_t p2g_batch_open_leaf(p2g_ctx* ctx, const p2g_batch* b, uint64_t leaf, uint64_t* row_out, uint64_t* sib_out) {
+    if (leaf >= b->N()) return P2G_E_BADARG;
+    CU(cudaMemcpy2DAsync(row_out, sizeof(gl_t), b->lde + leaf, b->N() * sizeof(gl_t), sizeof(gl_t), b->ncols,
+                         cudaMemcpyDeviceToHost, ctx->st));
+    uint64_t idx = leaf;
+    for (uint32_t k = 0; k < b->path_len(); k++) {
+        const gl_t* lvl = b->digests + merkle_level_offset(b->log_N(), k);
+        CU(cudaMemcpyAsync(sib_out + 4 * k, lvl + 4 * (idx ^ 1), 4 * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+        idx >>= 1;
+    }
+    CU(cudaStreamSynchronize(ctx->st));
+    return P2G_OK;
+}
+
+extern "C" int32_t p2g_merkle_cap(p2g_ctx* ctx, const uint64_t* leaves_host, uint32_t log_leaves, uint32_t leaf_len,
+                                  uint32_t cap_height, uint64_t* cap_out, uint64_t* leaf_digests_out) {
+    if (!ctx || !leaves_host || !cap_out || cap_height > log_leaves) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    size_t words = (size_t)leaf_len << log_leaves;
+    gl_t *d_leaves, *d_dig, *d_cap; int rc;
+    if ((rc = ctx_alloc(ctx, &d_leaves, words))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_dig, merkle_digest_words(log_leaves, cap_height)))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_cap, (size_t)4 << cap_height))) return rc;
+    CU(cudaMemcpyAsync(d_leaves, leaves_host, words * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+    if (merkle_build(d_leaves, 0, 0, leaf_len, log_leaves, cap_height, d_dig, d_cap, ctx->st)) { ctx->err = "merkle launch"; return P2G_E_CUDA; }
+    CU(cudaMemcpyAsync(cap_out, d_cap, ((size_t)4 << cap_height) * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    if (leaf_digests_out) {
+        const gl_t* src = log_leaves == cap_height ? d_cap : d_dig;
+        CU(cudaMemcpyAsync(leaf_digests_out, src, ((size_t)4 << log_leaves) * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx_free(ctx, d_leaves); ctx_free(ctx, d_dig); ctx_free(ctx, d_cap);
+    return P2G_OK;
+}
+
+__global__ void hash_no_pad_many_kernel(const gl_t* __restrict__ in, uint32_t count, uint32_t len, gl_t* __restrict__ out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    gl_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (uint32_t c0 = 0; c0 < len; c0 += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (c0 + i < len) s[i] = in[(size_t)j * len + c0 + i];
+        poseidon_permute(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[4 * (size_t)j + i] = s[i];
+}
+extern "C" int32_t p2g_hash_no_pad_many(p2g_ctx* ctx, const uint64_t* in_host, uint32_t count, uint32_t len, uint64_t* out_host) {
+    if (!ctx || !in_host || !out_host || !count) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    gl_t *d_in, *d_out; int rc;
+    if ((rc = ctx_alloc(ctx, &d_in, (size_t)count * len))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_out, (size_t)count * 4))) return rc;
+    CU(cudaMemcpyAsync(d_in, in_host, (size_t)count * len * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+    hash_no_pad_many_kernel<<<(count + 127) / 128, 128, 0, ctx->st>>>(d_in, count, len, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_host, d_out, (size_t)count * 4 * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx_free(ctx, d_in); ctx_free(ctx, d_out);
+    return P2G_OK;
+}
+
+extern "C" int32_t p2g_poseidon_peak(p2g_ctx* ctx, uint32_t iters, double* perms_per_sec) {
+    if (!ctx || !perms_per_sec || !iters) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t nthreads = 148 * 2048;   // every SM full of resident warps
+    gl_t* d_out; int rc;
+    if ((rc = ctx_alloc(ctx, &d_out, nthreads))) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    poseidon_bench_launch(d_out, nthreads, 2, ctx->st);   // warm-up
+    CU(cudaEventRecord(e0, ctx->st));
+    if (poseidon_bench_launch(d_out, nthreads, iters, ctx->st)) { ctx->err = "poseidon bench launch"; return P2G_E_CUDA; }
+    CU(cudaEventRecord(e1, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    *perms_per_sec = (double)nthreads * iters / (ms * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx_free(ctx, d_out);
+    return P2G_OK;
+}

@@ -1,0 +1,41 @@
+// Internal declarations shared by the translation units of libp2gpu.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "gl64.cuh"
+
+#define P2G_MAX_LOG_M 14   // largest sub-transform held in shared memory (2^14 * 8 B = 128 KB)
+
+// ---- NTT (ntt.cu) -------------------------------------------------------------------------
+// A plan = device tables for one transform shape.  The transform of size n = R * M runs as
+// R * variants thread blocks per column: block (variant, q) folds the first log2(R) DIF stages,
+// the coset/inverse scaling and the variant shift into one table multiply
+//     y_q[t] = sum_k x[t + k*M] * T[variant][q][k][t]
+// and then runs a size-M decimation-in-frequency transform entirely in shared memory.
+enum { NTT_KIND_LDE = 0, NTT_KIND_INV = 1 };
+struct NttPlan {
+    int kind, log_n, log_m, log_r, log_variants;
+    gl_t* T;    // [variants][R][R][M]
+    gl_t* tw;   // w_M^k (forward) or w_M^-k (inverse), k < M/2
+};
+int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream_t st);
+void ntt_plan_free(NttPlan* plan);
+// out_mode 0: block (variant,q) writes M contiguous words at out[col*out_stride + bitrev(variant)*n + q*M]
+//             (bit-reversed order: the layout MerkleTree leaves and the quotient kernel use)
+// out_mode 1: natural order, out[col*out_stride + f] (variants must be 1)
+int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out, size_t out_stride,
+               int ncols, int out_mode, cudaStream_t st);
+
+// ---- Merkle (merkle.cu) -------------------------------------------------------------------
+// Leaves are read either column-major (element c of leaf j at data[c*col_stride + j]) or
+// row-major (data[j*leaf_len + c]).  digests: levels 0..L-1 concatenated, then the cap is
+// written separately.  L = log2(num_leaves) - cap_height.
+int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t leaf_len, uint32_t log_leaves,
+                 uint32_t cap_height, gl_t* digests, gl_t* cap, cudaStream_t st);
+size_t merkle_digest_words(uint32_t log_leaves, uint32_t cap_height);
+size_t merkle_level_offset(uint32_t log_leaves, uint32_t level);  // in words
+
+// poseidon microbenchmark (roofline denominator for the INT pipe): runs `iters` chained
+// permutations per thread
+int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st);

@@ -1,0 +1,46 @@
+// Internal context/batch structures of libp2gpu.so.
+#pragma once
+#include "common.h"
+#include "../../include/p2gpu.h"
+#include <map>
+#include <string>
+#include <vector>
+#include <tuple>
+
+struct p2g_batch {
+    uint32_t ncols, log_n, rate_bits, cap_height;
+    gl_t* coeffs;    // [ncols][n]  natural coefficient order
+    gl_t* lde;       // [ncols][N]  column-major, bit-reversed point order (== Merkle leaf order)
+    gl_t* digests;   // tree levels 0..L-1
+    gl_t* cap;       // [2^cap_height][4] device
+    std::vector<gl_t> cap_host;
+    size_t n() const { return (size_t)1 << log_n; }
+    size_t N() const { return (size_t)1 << (log_n + rate_bits); }
+    uint32_t log_N() const { return log_n + rate_bits; }
+    uint32_t path_len() const { return log_N() - cap_height; }
+};
+
+struct ProveScratch;  // prover.cu
+
+struct p2g_ctx {
+    int device;
+    cudaStream_t st;
+    std::string err;
+    std::map<std::tuple<int, int, int>, NttPlan> plans;
+    gl_t* pinned; size_t pinned_words;     // small pinned staging buffer for D2H results
+    bool timing;
+    p2g_timings timings;
+    p2g_transcript transcript;
+    std::vector<gl_t> last_zs, last_quotient_chunks;
+    bool keep_debug;
+};
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return P2G_E_CUDA; } } while (0)
+
+int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan** out);
+int ctx_alloc(p2g_ctx* ctx, gl_t** p, size_t words);
+void ctx_free(p2g_ctx* ctx, void* p);
+// builds coefficients (optional inverse NTT), LDE and Merkle tree for device-resident columns
+int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+               uint32_t cap_height, bool from_values, p2g_batch** out, bool sync_cap);

@@ -1,0 +1,126 @@
+// Goldilocks field GF(2^64 - 2^32 + 1) and its quadratic extension F[X]/(X^2-7) for sm_100a.
+// Montgomery-free: a 128-bit product is folded with 2^64 = 2^32 - 1 and 2^96 = -1 (mod p).
+// Replaces plonky2's field/src/goldilocks_field.rs + goldilocks_extensions.rs (un-vendored
+// dependency pinned at /root/reference/Cargo.toml:12) on the device side.
+// Convention: every value stored to HBM is canonical (< p); in-register values may be any u64
+// where a function says "lazy".
+#pragma once
+#include <stdint.h>
+
+#define GL_P   0xFFFFFFFF00000001ULL
+#define GL_EPS 0x00000000FFFFFFFFULL
+
+#if defined(__CUDACC__)
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_HD inline
+#endif
+
+typedef uint64_t gl_t;
+
+GL_HD gl_t gl_canon(gl_t a) { return a >= GL_P ? a - GL_P : a; }
+
+// canonical + canonical -> canonical
+GL_HD gl_t gl_add(gl_t a, gl_t b) {
+    gl_t s = a + b;
+    return (s < a || s >= GL_P) ? s - GL_P : s;
+}
+GL_HD gl_t gl_sub(gl_t a, gl_t b) {
+    gl_t d = a - b;
+    return (a < b) ? d + GL_P : d;
+}
+GL_HD gl_t gl_neg(gl_t a) { return a ? GL_P - a : 0; }
+
+// lazy add: a any u64, b any u64 with at least one of them canonical -> any u64 (same residue)
+GL_HD gl_t gl_add_lazy(gl_t a, gl_t b) {
+    gl_t s = a + b;
+    return (s < a) ? s + GL_EPS : s;
+}
+
+// (hi:lo) 128-bit -> u64 residue (not necessarily canonical)
+GL_HD gl_t gl_reduce128_lazy(gl_t lo, gl_t hi) {
+    gl_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
+    gl_t t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= GL_EPS;          // borrow: subtract 2^64 = EPS (mod p)
+    gl_t t1 = (hi_lo << 32) - hi_lo;        // hi_lo * (2^32 - 1)
+    gl_t t2 = t0 + t1;
+    if (t2 < t1) t2 += GL_EPS;
+    return t2;
+}
+GL_HD void gl_mul_wide(gl_t a, gl_t b, gl_t& lo, gl_t& hi) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umul64hi(a, b);
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    lo = (gl_t)x; hi = (gl_t)(x >> 64);
+#endif
+}
+// any u64 * any u64 -> lazy residue
+GL_HD gl_t gl_mul_lazy(gl_t a, gl_t b) {
+    gl_t lo, hi;
+    gl_mul_wide(a, b, lo, hi);
+    return gl_reduce128_lazy(lo, hi);
+}
+// any * any -> canonical
+GL_HD gl_t gl_mul(gl_t a, gl_t b) { return gl_canon(gl_mul_lazy(a, b)); }
+GL_HD gl_t gl_sqr(gl_t a) { return gl_mul(a, a); }
+
+GL_HD gl_t gl_pow(gl_t b, uint64_t e) {
+    gl_t r = 1;
+    while (e) { if (e & 1) r = gl_mul(r, b); b = gl_sqr(b); e >>= 1; }
+    return r;
+}
+// Fermat inverse, a^(p-2); p-2 = 0xFFFFFFFEFFFFFFFF
+GL_HD gl_t gl_inv(gl_t a) {
+    // addition chain: a^(2^32-1) then assemble exponent 2^64 - 2^32 - 1
+    gl_t t = a;                       // a^(2^1-1)
+    gl_t x = a;
+    // e31 = a^(2^31-1)
+    for (int i = 1; i < 31; i++) { x = gl_sqr(x); x = gl_mul(x, a); }
+    gl_t e31 = x;
+    // a^(2^32-2) = e31^2 ; a^(2^32 - 1) not needed.  exponent p-2 = (2^31-1)*2^33 + (2^32-1)
+    // = e31 << 33 | (2^32 - 1):  p-2 = 0xFFFFFFFE_FFFFFFFF = (2^31-1)<<33 + 2^32-1
+    gl_t y = e31;
+    for (int i = 0; i < 33; i++) y = gl_sqr(y);
+    gl_t e32 = gl_mul(gl_sqr(e31), a);  // a^(2^32-1)
+    (void)t;
+    return gl_mul(y, e32);
+}
+GL_HD gl_t gl_root_of_unity(int k) {
+    gl_t g = 1753635133440165772ULL;  // POWER_OF_TWO_GENERATOR, order 2^32
+    for (int i = 0; i < 32 - k; i++) g = gl_sqr(g);
+    return g;
+}
+
+struct ext_t { gl_t c0, c1; };
+GL_HD ext_t ext_make(gl_t a, gl_t b) { ext_t r; r.c0 = a; r.c1 = b; return r; }
+GL_HD ext_t ext_add(ext_t a, ext_t b) { return ext_make(gl_add(a.c0, b.c0), gl_add(a.c1, b.c1)); }
+GL_HD ext_t ext_sub(ext_t a, ext_t b) { return ext_make(gl_sub(a.c0, b.c0), gl_sub(a.c1, b.c1)); }
+GL_HD ext_t ext_mul(ext_t a, ext_t b) {
+    gl_t a1b1 = gl_mul(a.c1, b.c1);
+    gl_t c0 = gl_add(gl_mul(a.c0, b.c0), gl_mul(7, a1b1));
+    gl_t c1 = gl_add(gl_mul(a.c0, b.c1), gl_mul(a.c1, b.c0));
+    return ext_make(c0, c1);
+}
+GL_HD ext_t ext_mul_base(ext_t a, gl_t b) { return ext_make(gl_mul(a.c0, b), gl_mul(a.c1, b)); }
+GL_HD ext_t ext_add_base(ext_t a, gl_t b) { return ext_make(gl_add(a.c0, b), a.c1); }
+GL_HD ext_t ext_inv(ext_t a) {
+    gl_t d = gl_sub(gl_sqr(a.c0), gl_mul(7, gl_sqr(a.c1)));
+    gl_t di = gl_inv(d);
+    return ext_make(gl_mul(a.c0, di), gl_mul(gl_neg(a.c1), di));
+}
+GL_HD ext_t ext_pow(ext_t b, uint64_t e) {
+    ext_t r = ext_make(1, 0);
+    while (e) { if (e & 1) r = ext_mul(r, b); b = ext_mul(b, b); e >>= 1; }
+    return r;
+}
+GL_HD uint32_t gl_bitrev(uint32_t x, int bits) {
+#if defined(__CUDA_ARCH__)
+    return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+#endif
+}

@@ -1,0 +1,165 @@
+// Poseidon Merkle commitment for sm_100a: MerkleTree::new(leaves, cap_height) of the pinned
+// plonky2 dependency (hash/merkle_tree.rs; /root/reference/Cargo.toml:12).
+//
+// Leaves are hashed straight out of the column-major, bit-reversed LDE buffer the NTT kernel
+// wrote (thread j reads word j of every column: fully coalesced, no transposed copy exists).
+// One thread = one leaf sponge; the block then folds log2(blockDim) tree levels through shared
+// memory, writing every level's digests (needed later for Merkle paths).  The few levels above
+// that are finished by a single block.
+#include "common.h"
+#include "poseidon.cuh"
+
+#define MERKLE_BLOCK 256
+#define MERKLE_BLOCK_LOG 8
+
+size_t merkle_level_offset(uint32_t log_leaves, uint32_t level) {
+    size_t off = 0;
+    for (uint32_t k = 0; k < level; k++) off += ((size_t)4 << (log_leaves - k));
+    return off;
+}
+size_t merkle_digest_words(uint32_t log_leaves, uint32_t cap_height) {
+    uint32_t L = log_leaves > cap_height ? log_leaves - cap_height : 0;
+    size_t w = merkle_level_offset(log_leaves, L);
+    return w ? w : 4;
+}
+
+// level pointer: levels < L live in `digests`, level L is the cap
+__device__ __forceinline__ gl_t* level_ptr(gl_t* digests, gl_t* cap, uint32_t log_leaves, uint32_t L, uint32_t level) {
+    if (level >= L) return cap;
+    size_t off = 0;
+    for (uint32_t k = 0; k < level; k++) off += ((size_t)4 << (log_leaves - k));
+    return digests + off;
+}
+
+template <bool COL_MAJOR>
+__global__ void __launch_bounds__(MERKLE_BLOCK)
+merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t leaf_len, uint32_t log_leaves,
+                     uint32_t L, uint32_t levels_here, gl_t* __restrict__ digests, gl_t* __restrict__ cap) {
+    __shared__ gl_t sh[MERKLE_BLOCK][4];
+    const uint32_t tid = threadIdx.x;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + tid;
+    const size_t num_leaves = (size_t)1 << log_leaves;
+    gl_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    if (j < num_leaves) {
+        if (leaf_len <= 4) {                       // hash_or_noop
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++)
+                if (c < leaf_len) s[c] = COL_MAJOR ? __ldg(data + (size_t)c * col_stride + j) : __ldg(data + j * leaf_len + c);
+        } else {
+            for (uint32_t c0 = 0; c0 < leaf_len; c0 += 8) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    uint32_t c = c0 + i;
+                    if (c < leaf_len)
+                        s[i] = COL_MAJOR ? __ldg(data + (size_t)c * col_stride + j) : __ldg(data + j * leaf_len + c);
+                }
+                poseidon_permute(s);
+            }
+        }
+        gl_t* d0 = level_ptr(digests, cap, log_leaves, L, 0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) d0[4 * j + i] = s[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) sh[tid][i] = s[i];
+    __syncthreads();
+    // fold levels inside the block
+    for (uint32_t lv = 1; lv <= levels_here; lv++) {
+        uint32_t active = blockDim.x >> lv;
+        gl_t l[4], r[4], o[4];
+        if (tid < active) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { l[i] = sh[2 * tid][i]; r[i] = sh[2 * tid + 1][i]; }
+            poseidon_two_to_one(l, r, o);
+        }
+        __syncthreads();
+        if (tid < active) {
+            size_t node = ((size_t)blockIdx.x * blockDim.x >> lv) + tid;
+            gl_t* d = level_ptr(digests, cap, log_leaves, L, lv);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { sh[tid][i] = o[i]; d[4 * node + i] = o[i]; }
+        }
+        __syncthreads();
+    }
+}
+
+// finishes levels (from_level, L] with one block; level `from_level` is complete in global memory
+__global__ void __launch_bounds__(1024)
+merkle_top_kernel(gl_t* digests, gl_t* cap, uint32_t log_leaves, uint32_t L, uint32_t from_level) {
+    for (uint32_t lv = from_level + 1; lv <= L; lv++) {
+        const gl_t* src = level_ptr(digests, cap, log_leaves, L, lv - 1);
+        gl_t* dst = level_ptr(digests, cap, log_leaves, L, lv);
+        size_t cnt = (size_t)1 << (log_leaves - lv);
+        for (size_t t = threadIdx.x; t < cnt; t += blockDim.x) {
+            gl_t l[4], r[4], o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { l[i] = src[8 * t + i]; r[i] = src[8 * t + 4 + i]; }
+            poseidon_two_to_one(l, r, o);
+#pragma unroll
+            for (int i = 0; i < 4; i++) dst[4 * t + i] = o[i];
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+// one grid-wide level (used when the level is too wide for the single-block finisher)
+__global__ void __launch_bounds__(256)
+merkle_level_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, size_t cnt) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    gl_t l[4], r[4], o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { l[i] = src[8 * t + i]; r[i] = src[8 * t + 4 + i]; }
+    poseidon_two_to_one(l, r, o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[4 * t + i] = o[i];
+}
+
+int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t leaf_len, uint32_t log_leaves,
+                 uint32_t cap_height, gl_t* digests, gl_t* cap, cudaStream_t st) {
+    if (cap_height > log_leaves) return -2;
+    const uint32_t L = log_leaves - cap_height;
+    const size_t num_leaves = (size_t)1 << log_leaves;
+    uint32_t threads = num_leaves < MERKLE_BLOCK ? (uint32_t)num_leaves : MERKLE_BLOCK;
+    if (threads < 32) threads = 32;   // keep full warps; surplus threads hash nothing
+    uint32_t block_log = 0; while ((1u << block_log) < threads) block_log++;
+    uint32_t real_log = log_leaves < block_log ? log_leaves : block_log;
+    uint32_t levels_here = real_log < L ? real_log : L;
+    uint32_t blocks = (uint32_t)((num_leaves + threads - 1) / threads);
+    if (col_major)
+        merkle_leaves_kernel<true><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
+    else
+        merkle_leaves_kernel<false><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
+    uint32_t lv = levels_here;
+    // wide levels: one launch each until <= 2048 nodes remain, then a single block finishes
+    while (lv < L && ((size_t)1 << (log_leaves - lv - 1)) > 2048) {
+        size_t cnt = (size_t)1 << (log_leaves - lv - 1);
+        const gl_t* src = digests + merkle_level_offset(log_leaves, lv);
+        gl_t* dst = (lv + 1 >= L) ? cap : digests + merkle_level_offset(log_leaves, lv + 1);
+        merkle_level_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(src, dst, cnt);
+        lv++;
+    }
+    if (lv < L) merkle_top_kernel<<<1, 1024, 0, st>>>(digests, cap, log_leaves, L, lv);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---- INT-pipe roofline microbenchmark: chained permutations, no memory traffic ------------
+__global__ void __launch_bounds__(256)
+poseidon_bench_kernel(gl_t* out, uint32_t iters) {
+    gl_t s[12];
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = (gl_t)g * 12 + i;
+    for (uint32_t k = 0; k < iters; k++) poseidon_permute(s);
+    gl_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc ^= s[i];
+    out[g] = acc;
+}
+int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st) {
+    poseidon_bench_kernel<<<nthreads_total / 256, 256, 0, st>>>(out, iters);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

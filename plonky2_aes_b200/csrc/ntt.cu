@@ -1,0 +1,153 @@
+// Goldilocks NTT kernels for sm_100a: inverse NTT and coset low-degree extension behind
+// PolynomialBatch::from_values / from_coeffs (plonky2 fri/oracle.rs, field/src/fft.rs of the
+// dependency pinned at /root/reference/Cargo.toml:12).
+//
+// Design (B200-first, not a translation of the CPU radix-2 loop):
+//  * one thread block owns one (column, coset, chunk) and keeps its 2^LOG_M points in shared
+//    memory for the whole transform: HBM sees one read of the coefficients (L2-served for the
+//    8 cosets of a column) and one coalesced write of the result;
+//  * the coset shift 7*w_N^s, the zero padding of lde(), the 1/n of the inverse and the first
+//    log2(R) decimation stages are folded into a single table multiply on load;
+//  * decimation in frequency leaves the output in bit-reversed order, which IS the leaf order
+//    of MerkleTree::new after reverse_index_bits_in_place, and coset s lands in the contiguous
+//    block bitrev3(s) -- so the reference's transpose + bit-reverse pass disappears;
+//  * radix-16 register passes (4 butterfly stages per shared-memory round trip), padded
+//    shared-memory indexing (idx + idx/16) to stay bank-conflict free at every stride.
+#include "common.h"
+#include <vector>
+#include <stdio.h>
+
+__device__ __forceinline__ uint32_t smpad(uint32_t i) { return i + (i >> 4); }
+
+// K butterfly stages on 2^K register-resident points.  DIF: (a,b) -> (a+b, (a-b)*w).
+// log_b = log2 of the block size at the first stage of this pass.
+template <int K>
+__device__ __forceinline__ void dif_pass(gl_t* sm, int log_m, int log_b, const gl_t* __restrict__ tw,
+                                         uint32_t tid, uint32_t nthreads) {
+    constexpr int E = 1 << K;
+    const uint32_t M = 1u << log_m;
+    const int log_s = log_b - K;           // stride between a thread's points
+    const uint32_t S = 1u << log_s;
+    for (uint32_t g = tid; g < (M >> K); g += nthreads) {
+        uint32_t blk = g >> log_s, lowpos = g & (S - 1);
+        uint32_t base = (blk << log_b) + lowpos;
+        gl_t a[E];
+#pragma unroll
+        for (int i = 0; i < E; i++) a[i] = sm[smpad(base + ((uint32_t)i << log_s))];
+#pragma unroll
+        for (int u = 0; u < K; u++) {
+            const int half = E >> (u + 1);            // in units of i
+            const int tw_shift = log_m - (log_b - u); // twiddle index scale: M / B_u
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+                if ((i & half) == 0) {
+                    uint32_t p = lowpos + ((uint32_t)(i & (half - 1)) << log_s);  // position of the lower point in its block
+                    gl_t w = __ldg(tw + ((size_t)p << tw_shift));
+                    gl_t x = a[i], y = a[i + half];
+                    a[i] = gl_add(x, y);
+                    a[i + half] = gl_mul(gl_sub(x, y), w);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < E; i++) sm[smpad(base + ((uint32_t)i << log_s))] = a[i];
+    }
+}
+
+__global__ void __launch_bounds__(512, 1)
+ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__ out, size_t out_stride,
+               const gl_t* __restrict__ T, const gl_t* __restrict__ tw,
+               int log_n, int log_m, int log_variants, int out_mode) {
+    extern __shared__ gl_t sm[];
+    const int log_r = log_n - log_m;
+    const uint32_t M = 1u << log_m, R = 1u << log_r;
+    const uint32_t variant = blockIdx.x >> log_r, q = blockIdx.x & (R - 1);
+    const uint32_t col = blockIdx.y;
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    const gl_t* x = in + (size_t)col * in_stride;
+    const gl_t* Tq = T + ((size_t)(variant * R + q) << log_n);   // [k][t]
+
+    // load + fold: y[t] = sum_k x[t + kM] * T[k][t]
+    for (uint32_t t = tid; t < M; t += nth) {
+        gl_t acc = gl_mul(__ldg(x + t), __ldg(Tq + t));
+        for (uint32_t k = 1; k < R; k++)
+            acc = gl_add(acc, gl_mul(__ldg(x + t + ((size_t)k << log_m)), __ldg(Tq + ((size_t)k << log_m) + t)));
+        sm[smpad(t)] = acc;
+    }
+    __syncthreads();
+
+    int log_b = log_m;
+    int rem = log_m & 3;
+    if (rem == 1) { dif_pass<1>(sm, log_m, log_b, tw, tid, nth); log_b -= 1; __syncthreads(); }
+    else if (rem == 2) { dif_pass<2>(sm, log_m, log_b, tw, tid, nth); log_b -= 2; __syncthreads(); }
+    else if (rem == 3) { dif_pass<3>(sm, log_m, log_b, tw, tid, nth); log_b -= 3; __syncthreads(); }
+    while (log_b > 0) {
+        dif_pass<4>(sm, log_m, log_b, tw, tid, nth);
+        log_b -= 4;
+        __syncthreads();
+    }
+
+    gl_t* o = out + (size_t)col * out_stride;
+    if (out_mode == 0) {
+        size_t base = ((size_t)gl_bitrev(variant, log_variants) << log_n) + ((size_t)q << log_m);
+        for (uint32_t m = tid; m < M; m += nth) o[base + m] = sm[smpad(m)];
+    } else {
+        uint32_t qr = gl_bitrev(q, log_r);
+        for (uint32_t j = tid; j < M; j += nth) o[((size_t)j << log_r) + qr] = sm[smpad(gl_bitrev(j, log_m))];
+    }
+}
+
+int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream_t st) {
+    plan->kind = kind; plan->log_n = log_n;
+    plan->log_m = log_n < P2G_MAX_LOG_M ? log_n : P2G_MAX_LOG_M;
+    if (log_n == 13) plan->log_m = 13;
+    plan->log_r = log_n - plan->log_m;
+    plan->log_variants = kind == NTT_KIND_LDE ? rate_bits : 0;
+    const size_t n = (size_t)1 << log_n, M = (size_t)1 << plan->log_m, R = (size_t)1 << plan->log_r;
+    const size_t V = (size_t)1 << plan->log_variants;
+    std::vector<gl_t> T(V * R * n), tw(M / 2 ? M / 2 : 1);
+    gl_t wn = gl_root_of_unity(log_n);
+    gl_t wN = gl_root_of_unity(log_n + plan->log_variants);
+    gl_t wm = gl_root_of_unity(plan->log_m);
+    if (kind == NTT_KIND_INV) { wn = gl_inv(wn); wm = gl_inv(wm); }
+    gl_t ninv = gl_inv((gl_t)1 << log_n);
+    for (size_t v = 0; v < V; v++) {
+        gl_t shift = kind == NTT_KIND_LDE ? gl_mul(7, gl_pow(wN, v)) : 1;
+        for (size_t q = 0; q < R; q++) {
+            gl_t base = gl_mul(shift, gl_pow(wn, gl_bitrev((uint32_t)q, plan->log_r)));
+            gl_t x = kind == NTT_KIND_INV ? ninv : 1;
+            gl_t* dst = T.data() + (v * R + q) * n;   // index j = t + k*M  == [k][t]
+            for (size_t j = 0; j < n; j++) { dst[j] = x; x = gl_mul(x, base); }
+        }
+    }
+    { gl_t x = 1; for (size_t k = 0; k < M / 2; k++) { tw[k] = x; x = gl_mul(x, wm); } if (M / 2 == 0) tw[0] = 1; }
+    if (cudaMalloc(&plan->T, T.size() * sizeof(gl_t)) != cudaSuccess) return -1;
+    if (cudaMalloc(&plan->tw, tw.size() * sizeof(gl_t)) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(plan->T, T.data(), T.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(plan->tw, tw.data(), tw.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;   // host vectors die here
+    return 0;
+}
+void ntt_plan_free(NttPlan* plan) { cudaFree(plan->T); cudaFree(plan->tw); plan->T = plan->tw = nullptr; }
+
+int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out, size_t out_stride,
+               int ncols, int out_mode, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t M = (size_t)1 << plan->log_m;
+    size_t smem = (M + (M >> 4) + 1) * sizeof(gl_t);
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(ntt_dif_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+        attr_set = true;
+    }
+    uint32_t threads = (uint32_t)(M >> 4);
+    if (threads < 32) threads = 32;
+    if (threads > 512) threads = 512;
+    for (int c0 = 0; c0 < ncols; c0 += 65535) {
+        int nc = ncols - c0 < 65535 ? ncols - c0 : 65535;
+        dim3 grid((1u << plan->log_variants) << plan->log_r, nc);
+        ntt_dif_kernel<<<grid, threads, smem, st>>>(in + (size_t)c0 * in_stride, in_stride, out + (size_t)c0 * out_stride,
+                                                    out_stride, plan->T, plan->tw, plan->log_n, plan->log_m,
+                                                    plan->log_variants, out_mode);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
