@@ -23,14 +23,17 @@ static inline gl_t sbox7(gl_t x) {
     return gl_mul(x3, x4);
 }
 static inline void mds_layer(gl_t s[12]) {
-    gl_t out[12];
+    /* out[r] = sum_i s[(i+r)%12]*CIRC[i] + s[r]*DIAG[r].  The coefficients are < 2^6, so the
+     * 32-bit halves of the state can be accumulated separately in u64 without overflow and
+     * recombined with one reduction (same value as the u128 accumulation upstream uses). */
+    uint64_t lo[24], hi[24];
+    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = s[i] & 0xFFFFFFFFULL; hi[i] = hi[i + 12] = s[i] >> 32; }
     for (int r = 0; r < 12; r++) {
-        unsigned __int128 acc = 0;
-        for (int i = 0; i < 12; i++) acc += (unsigned __int128)s[(i + r) % 12] * MDS_CIRC[i];
-        acc += (unsigned __int128)s[r] * MDS_DIAG[r];
-        out[r] = gl_reduce128(acc);
+        uint64_t al = 0, ah = 0;
+        for (int i = 0; i < 12; i++) { al += lo[i + r] * MDS_CIRC[i]; ah += hi[i + r] * MDS_CIRC[i]; }
+        al += lo[r] * MDS_DIAG[r]; ah += hi[r] * MDS_DIAG[r];
+        s[r] = gl_reduce128((unsigned __int128)al + ((unsigned __int128)ah << 32));
     }
-    memcpy(s, out, sizeof(out));
 }
 void orc_poseidon(gl_t s[12]) {
     int r = 0;

@@ -27,7 +27,17 @@ static inline gl_t gl_add(gl_t a, gl_t b) {
 }
 static inline gl_t gl_sub(gl_t a, gl_t b) { return a >= b ? a - b : a + (GL_P - b); }
 static inline gl_t gl_neg(gl_t a) { return a ? GL_P - a : 0; }
-static inline gl_t gl_reduce128(unsigned __int128 x) { return (gl_t)(x % GL_P); }
+static inline gl_t gl_reduce128(unsigned __int128 x) {
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
+    uint64_t t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= GL_EPS;
+    uint64_t t1 = hi_lo * GL_EPS;
+    uint64_t t2 = t0 + t1;
+    if (t2 < t1) t2 += GL_EPS;
+    if (t2 >= GL_P) t2 -= GL_P;
+    return t2;
+}
 static inline gl_t gl_mul(gl_t a, gl_t b) {
     /* upstream reduce128: x_lo - x_hi_hi + x_hi_lo * EPSILON; the result is the same residue. */
     unsigned __int128 x = (unsigned __int128)a * b;

@@ -1,14 +1,651 @@
-// placeholder until the whole-proof driver lands (replaced in the next milestone)
+// C ABI of libp2gpu.so, part 2: circuit upload and the whole prove() path
+// (plonk/prover.rs::prove_with_partition_witness of the dependency pinned at
+// /root/reference/Cargo.toml:12; reference call sites: every `data.prove(pw)`, e.g.
+// /root/reference/aes-gcm/src/circuit_gcm.rs:781).  Everything O(n) or larger runs on the
+// device; the host only drives the Fiat-Shamir transcript (a few hundred Poseidon permutations
+// per proof), inverts the 64..256-point final FRI layer and assembles the proof words.
 #include "ctx.h"
-extern "C" int32_t p2g_circuit_load(p2g_ctx*, const p2g_circuit_desc*, p2g_circuit**, uint64_t*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_circuit_free(p2g_ctx*, p2g_circuit*) { return P2G_E_BADARG; }
-extern "C" size_t p2g_proof_words(const p2g_circuit*) { return 0; }
-extern "C" int32_t p2g_prove(p2g_ctx*, const p2g_circuit*, const uint64_t*, const uint64_t*, uint64_t*, size_t, size_t*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_prove_dev(p2g_ctx*, const p2g_circuit*, const uint64_t*, const uint64_t*, uint64_t*, size_t, size_t*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_last_transcript(p2g_ctx*, p2g_transcript*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_last_zs_values(p2g_ctx*, uint64_t*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_last_quotient_chunks(p2g_ctx*, uint64_t*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_last_timings(p2g_ctx*, p2g_timings*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_set_timing(p2g_ctx*, int32_t) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_pow_grind(p2g_ctx*, const uint64_t*, uint32_t, uint32_t, uint64_t*) { return P2G_E_BADARG; }
-extern "C" int32_t p2g_fri_fold(p2g_ctx*, const uint64_t*, uint32_t, uint32_t, uint64_t, const uint64_t*, uint64_t*) { return P2G_E_BADARG; }
+#include "prover_kernels.cuh"
+#include <string.h>
+#include <stdio.h>
+#include <algorithm>
+
+// ---------------------------------------------------------------------------------------------
+// host transcript: Challenger<F, PoseidonHash> (iop/challenger.rs)
+// ---------------------------------------------------------------------------------------------
+struct Challenger {
+    gl_t state[12]; gl_t in_buf[8]; int in_len; gl_t out_buf[8]; int out_len;
+    Challenger() { memset(this, 0, sizeof(*this)); }
+    void duplexing() {
+        for (int i = 0; i < in_len; i++) state[i] = in_buf[i];
+        in_len = 0;
+        poseidon_permute(state);
+        memcpy(out_buf, state, sizeof(out_buf)); out_len = 8;
+    }
+    void observe(gl_t x) { out_len = 0; in_buf[in_len++] = x; if (in_len == 8) duplexing(); }
+    void observe_many(const gl_t* x, size_t n) { for (size_t i = 0; i < n; i++) observe(x[i]); }
+    gl_t get() { if (in_len != 0 || out_len == 0) duplexing(); return out_buf[--out_len]; }
+    ext_t get_ext() { ext_t r; r.c0 = get(); r.c1 = get(); return r; }
+};
+static void host_hash_no_pad(const gl_t* in, size_t n, gl_t out[4]) {
+    gl_t s[12] = {0};
+    for (size_t off = 0; off < n; off += 8) {
+        size_t len = std::min<size_t>(8, n - off);
+        memcpy(s, in + off, len * sizeof(gl_t));
+        poseidon_permute(s);
+    }
+    memcpy(out, s, 4 * sizeof(gl_t));
+}
+
+// ---------------------------------------------------------------------------------------------
+struct p2g_circuit {
+    p2g_circuit_desc d;
+    std::vector<p2g_gate> gates; std::vector<int32_t> lut_lens, lookup_rows; std::vector<uint16_t> lut_data;
+    std::vector<gl_t> k_is;
+    CircuitDev cd;
+    p2g_batch* cs;            // constants_sigmas commitment
+    gl_t* d_sigmas;           // [R][n] values on H
+    gl_t* d_subgroup;         // g^i
+    gl_t* d_domain;           // x_j = 7 w_N^bitrev(j)
+    gl_t* d_qtable;           // [8][n]: h_s^(-j)/8
+    gl_t* d_small;            // w8inv_pows[8], shift_n_inv_pows[8]
+    p2g_gate* d_gates;
+    uint8_t* d_row_kind;
+    size_t proof_words;
+    int final_len;
+};
+
+static int num_lookup_polys(const p2g_circuit_desc& d) {
+    if (d.num_luts == 0) return 0;
+    int lu_slots = d.num_routed_wires / 2, lu_degree = d.quotient_degree_factor - 1;
+    return (lu_slots + lu_degree - 1) / lu_degree + 1;
+}
+static size_t proof_len(const p2g_circuit_desc& d) {
+    size_t cap = (size_t)4 << d.cap_height;
+    int nlp = num_lookup_polys(d), nch = d.num_challenges;
+    int NC = d.num_selectors + d.num_lookup_selectors + d.num_constants;
+    int logN = d.degree_bits + d.rate_bits;
+    int zs_cols = nch * (1 + d.num_partial_products + nlp);
+    size_t open = 2 * ((size_t)NC + d.num_routed_wires + d.num_wires + 2 * nch + (size_t)nch * d.num_partial_products +
+                       (size_t)nch * d.quotient_degree_factor + 2 * (size_t)nch * nlp);
+    size_t len = 3 * cap + open + (size_t)d.num_reduction_arity_bits * cap;
+    size_t per_q = 0;
+    int cols[4] = {NC + d.num_routed_wires, d.num_wires, zs_cols, nch * d.quotient_degree_factor};
+    for (int o = 0; o < 4; o++) per_q += cols[o] + 1 + 4 * (size_t)(logN - d.cap_height);
+    int lg = logN;
+    size_t fin = (size_t)1 << d.degree_bits;
+    for (int l = 0; l < d.num_reduction_arity_bits; l++) {
+        int ab = d.reduction_arity_bits[l];
+        lg -= ab; fin >>= ab;
+        per_q += (2u << ab) + 1 + 4 * (size_t)(lg - d.cap_height);
+    }
+    return len + per_q * d.num_query_rounds + 2 * fin + 1 + d.num_public_inputs;
+}
+
+extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, p2g_circuit** out, uint64_t* cap_out) {
+    if (!ctx || !desc || !out) return P2G_E_BADARG;
+    const p2g_circuit_desc& d = *desc;
+    if (d.num_challenges < 1 || d.num_challenges > MAX_CH || d.num_routed_wires > MAX_ROUTED || d.num_luts > 8 ||
+        d.quotient_degree_factor != (1 << d.rate_bits) || d.rate_bits != 3 || d.num_public_inputs != 0 ||
+        d.degree_bits < 2 || d.degree_bits > 20 || d.num_partial_products + 1 > 16 ||
+        d.num_routed_wires / 2 > 8 * (d.quotient_degree_factor - 1) || d.quotient_degree_factor - 1 > 8) {
+        ctx->err = "unsupported circuit configuration"; return P2G_E_BADARG;
+    }
+    for (int g = 0; g < d.num_gates; g++)
+        if (d.gates[g].kind == P2G_GATE_POSEIDON) { ctx->err = "PoseidonGate constraints are not implemented yet"; return P2G_E_BADARG; }
+    CU(cudaSetDevice(ctx->device));
+    p2g_circuit* C = new p2g_circuit();
+    C->d = d;
+    C->gates.assign(d.gates, d.gates + d.num_gates);
+    C->lut_lens.assign(d.lut_lens, d.lut_lens + d.num_luts);
+    size_t lut_total = 0; for (int i = 0; i < d.num_luts; i++) lut_total += d.lut_lens[i];
+    C->lut_data.assign(d.lut_data, d.lut_data + 2 * lut_total);
+    C->lookup_rows.assign(d.lookup_rows, d.lookup_rows + 3 * d.num_luts);
+    C->k_is.assign(d.k_is, d.k_is + d.num_routed_wires);
+    C->d.gates = C->gates.data(); C->d.lut_lens = C->lut_lens.data(); C->d.lut_data = C->lut_data.data();
+    C->d.lookup_rows = C->lookup_rows.data(); C->d.k_is = C->k_is.data(); C->d.constants_sigmas = nullptr;
+    CircuitDev& cd = C->cd;
+    cd.logn = d.degree_bits; cd.rate_bits = d.rate_bits; cd.nch = d.num_challenges; cd.R = d.num_routed_wires; cd.W = d.num_wires;
+    cd.num_sel = d.num_selectors; cd.num_lsel = d.num_lookup_selectors; cd.num_consts = d.num_constants;
+    cd.NC = cd.num_sel + cd.num_lsel + cd.num_consts;
+    cd.num_prods = d.num_partial_products; cd.qdf = d.quotient_degree_factor;
+    cd.nlp = num_lookup_polys(d); cd.num_sldc = cd.nlp ? cd.nlp - 1 : 0;
+    cd.lu_slots = cd.R / 2; cd.lut_slots = cd.R / 3; cd.lu_degree = cd.qdf - 1;
+    cd.lut_degree = cd.num_sldc ? (cd.lut_slots + cd.num_sldc - 1) / cd.num_sldc : 0;
+    cd.num_luts = d.num_luts; cd.num_gates = d.num_gates; cd.num_gate_constraints = d.num_gate_constraints;
+    cd.zs_cols = cd.nch * (1 + cd.num_prods + cd.nlp);
+    if (cd.lut_degree > 8) { delete C; ctx->err = "lut_degree > 8"; return P2G_E_BADARG; }
+    int nterms = cd.nch + cd.nch * (cd.num_prods + 1) + (cd.num_luts ? cd.nch * (4 + cd.num_luts + 2 * cd.num_sldc) : 0) + cd.num_gate_constraints;
+    if (nterms > 160) { delete C; ctx->err = "too many vanishing terms"; return P2G_E_BADARG; }
+    C->proof_words = proof_len(d);
+    const size_t n = (size_t)1 << cd.logn, N = n << cd.rate_bits;
+    const int logN = cd.logn + cd.rate_bits;
+    int rc;
+    // preprocessed commitment
+    const int ncs = cd.NC + cd.R;
+    gl_t* d_vals;
+    if ((rc = ctx_alloc(ctx, &d_vals, (size_t)ncs * n))) return rc;
+    CU(cudaMemcpyAsync(d_vals, d.constants_sigmas, (size_t)ncs * n * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = commit_dev(ctx, d_vals, ncs, cd.logn, cd.rate_bits, d.cap_height, true, &C->cs, true))) return rc;
+    if (cap_out) memcpy(cap_out, C->cs->cap_host.data(), C->cs->cap_host.size() * sizeof(gl_t));
+    if ((rc = ctx_alloc(ctx, &C->d_sigmas, (size_t)cd.R * n))) return rc;
+    CU(cudaMemcpyAsync(C->d_sigmas, d_vals + (size_t)cd.NC * n, (size_t)cd.R * n * sizeof(gl_t), cudaMemcpyDeviceToDevice, ctx->st));
+    ctx_free(ctx, d_vals);
+    // domain tables
+    if ((rc = ctx_alloc(ctx, &C->d_subgroup, n))) return rc;
+    if ((rc = ctx_alloc(ctx, &C->d_domain, N))) return rc;
+    domain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(cd.logn, gl_root_of_unity(cd.logn), 1, C->d_subgroup, 0);
+    domain_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->st>>>(logN, gl_root_of_unity(logN), 7, C->d_domain, 1);
+    CU(cudaGetLastError());
+    // quotient coefficient recovery tables
+    {
+        std::vector<gl_t> tab(8 * n), small(16);
+        gl_t wN = gl_root_of_unity(logN), inv8 = gl_inv(8);
+        for (int s = 0; s < 8; s++) {
+            gl_t hinv = gl_inv(gl_mul(7, gl_pow(wN, s)));
+            gl_t x = inv8;
+            for (size_t j = 0; j < n; j++) { tab[(size_t)s * n + j] = x; x = gl_mul(x, hinv); }
+        }
+        gl_t w8inv = gl_inv(gl_root_of_unity(3)), sninv = gl_inv(gl_pow(7, n));
+        small[0] = 1; small[8] = 1;
+        for (int k = 1; k < 8; k++) { small[k] = gl_mul(small[k - 1], w8inv); small[8 + k] = gl_mul(small[8 + k - 1], sninv); }
+        if ((rc = ctx_alloc(ctx, &C->d_qtable, 8 * n))) return rc;
+        if ((rc = ctx_alloc(ctx, &C->d_small, 16))) return rc;
+        CU(cudaMemcpyAsync(C->d_qtable, tab.data(), tab.size() * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(C->d_small, small.data(), small.size() * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    // gates and row kinds
+    {
+        std::vector<uint8_t> kind(n, 0);
+        for (int l = 0; l < d.num_luts; l++) {
+            int last_lu = d.lookup_rows[3 * l], last_lut = d.lookup_rows[3 * l + 1], first_lut = d.lookup_rows[3 * l + 2];
+            if (last_lu < 0 || first_lut + 1 >= (int)n || last_lu > last_lut || last_lut > first_lut) { ctx->err = "bad lookup rows"; return P2G_E_BADARG; }
+            for (int r = last_lu; r < last_lut; r++) kind[r] = 1;
+            for (int r = last_lut; r <= first_lut; r++) kind[r] = 2;
+        }
+        CU(cudaMallocAsync((void**)&C->d_row_kind, n, ctx->st));
+        CU(cudaMallocAsync((void**)&C->d_gates, sizeof(p2g_gate) * std::max(1, d.num_gates), ctx->st));
+        CU(cudaMemcpyAsync(C->d_row_kind, kind.data(), n, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(C->d_gates, C->gates.data(), sizeof(p2g_gate) * d.num_gates, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    size_t fin = n; for (int l = 0; l < d.num_reduction_arity_bits; l++) fin >>= d.reduction_arity_bits[l];
+    C->final_len = (int)fin;
+    *out = C;
+    return P2G_OK;
+}
+extern "C" int32_t p2g_circuit_free(p2g_ctx* ctx, p2g_circuit* C) {
+    if (!ctx || !C) return P2G_E_BADARG;
+    p2g_batch_free(ctx, C->cs);
+    ctx_free(ctx, C->d_sigmas); ctx_free(ctx, C->d_subgroup); ctx_free(ctx, C->d_domain); ctx_free(ctx, C->d_qtable);
+    ctx_free(ctx, C->d_small); ctx_free(ctx, C->d_row_kind); ctx_free(ctx, C->d_gates);
+    delete C;
+    return P2G_OK;
+}
+extern "C" size_t p2g_proof_words(const p2g_circuit* C) { return C ? C->proof_words : 0; }
+
+// ---------------------------------------------------------------------------------------------
+struct StageTimer {
+    p2g_ctx* ctx; cudaEvent_t ev[16]; int n; bool on;
+    StageTimer(p2g_ctx* c) : ctx(c), n(0), on(c->timing) { if (on) for (auto& e : ev) cudaEventCreate(&e); mark(); }
+    void mark() { if (on && n < 16) cudaEventRecord(ev[n++], ctx->st); }
+    void finish(p2g_timings* t) {
+        if (!on) return;
+        cudaEventSynchronize(ev[n - 1]);
+        float* f = &t->h2d;
+        for (int i = 0; i + 1 < n && i < 11; i++) cudaEventElapsedTime(&f[i], ev[i], ev[i + 1]);
+        cudaEventElapsedTime(&t->total, ev[0], ev[n - 1]);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+};
+
+struct Pow2Table { ext_t p[32]; };
+__global__ void __launch_bounds__(256)
+ext_powers_kernel2(Pow2Table tb, size_t count, gl_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    ext_t r = ext_make(1, 0);
+    size_t e = j;
+    for (int b = 0; e; b++, e >>= 1) if (e & 1) r = ext_mul(r, tb.p[b]);
+    out[2 * j] = r.c0; out[2 * j + 1] = r.c1;
+}
+
+static ext_t ext_reduce_with_powers(const ext_t* v, size_t n, ext_t alpha) {
+    ext_t acc = ext_make(0, 0);
+    for (size_t i = n; i-- > 0;) acc = ext_add(ext_mul(acc, alpha), v[i]);
+    return acc;
+}
+
+static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wires_in, bool wires_on_host,
+                          const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap, size_t* proof_words_out) {
+    if (!ctx || !C || !d_wires_in || !proof_out) return P2G_E_BADARG;
+    if (proof_cap < C->proof_words) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    const p2g_circuit_desc& d = C->d;
+    const CircuitDev& cd = C->cd;
+    const int nch = cd.nch, R = cd.R, W = cd.W, NC = cd.NC, qdf = cd.qdf, num_prods = cd.num_prods, nlp = cd.nlp;
+    const int logn = cd.logn, logN = logn + cd.rate_bits;
+    const size_t n = (size_t)1 << logn, N = (size_t)1 << logN;
+    const int zs_cols = cd.zs_cols, zpp = nch * (1 + num_prods), nlz = zs_cols - zpp;
+    const size_t capw = (size_t)4 << d.cap_height;
+    const bool has_lookup = cd.num_luts > 0;
+    cudaStream_t st = ctx->st;
+    int rc;
+    StageTimer tm(ctx);
+
+    gl_t pi_hash[4];
+    host_hash_no_pad(public_inputs, (size_t)d.num_public_inputs, pi_hash);
+
+    // ---- stage A: wires ----
+    gl_t* d_wires = nullptr;
+    const gl_t* wires = d_wires_in;
+    if (wires_on_host) {
+        if ((rc = ctx_alloc(ctx, &d_wires, (size_t)W * n))) return rc;
+        CU(cudaMemcpyAsync(d_wires, d_wires_in, (size_t)W * n * sizeof(gl_t), cudaMemcpyHostToDevice, st));
+        wires = d_wires;
+    }
+    tm.mark();
+    p2g_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
+    if ((rc = commit_dev(ctx, wires, W, logn, cd.rate_bits, d.cap_height, true, &wb, true))) return rc;
+    tm.mark();
+
+    Challenger ch;
+    ch.observe_many(d.circuit_digest, 4);
+    ch.observe_many(pi_hash, 4);
+    ch.observe_many(wb->cap_host.data(), capw);
+    ProofConsts* pc_host = (ProofConsts*)(ctx->pinned + ctx->pinned_words / 2);   // upper half of the pinned staging buffer (the lower half receives D2H results)
+    static_assert(sizeof(ProofConsts) < 16384, "ProofConsts too large");
+    memset(pc_host, 0, sizeof(ProofConsts));
+    gl_t deltas_flat[16] = {0};
+    for (int i = 0; i < nch; i++) pc_host->betas[i] = ch.get();
+    for (int i = 0; i < nch; i++) pc_host->gammas[i] = ch.get();
+    if (has_lookup) {
+        int k = 0;
+        for (int i = 0; i < nch; i++) deltas_flat[k++] = pc_host->betas[i];
+        for (int i = 0; i < nch; i++) deltas_flat[k++] = pc_host->gammas[i];
+        for (int i = 0; i < 2 * nch; i++) deltas_flat[k++] = ch.get();
+        for (int i = 0; i < nch; i++) for (int j = 0; j < 4; j++) pc_host->deltas[i][j] = deltas_flat[4 * i + j];
+    }
+    for (int j = 0; j < R; j++) {
+        pc_host->k_is[j] = C->k_is[j];
+        for (int i = 0; i < nch; i++) pc_host->beta_kis[i][j] = gl_mul(pc_host->betas[i], C->k_is[j]);
+    }
+    memcpy(pc_host->pi_hash, pi_hash, sizeof(pi_hash));
+    {
+        gl_t sn = gl_pow(7, n), w8 = gl_root_of_unity(cd.rate_bits), t = 1;
+        for (int s = 0; s < (1 << cd.rate_bits); s++) { pc_host->zh[s] = gl_sub(gl_mul(sn, t), 1); pc_host->zh_inv[s] = gl_inv(pc_host->zh[s]); t = gl_mul(t, w8); }
+    }
+    if (has_lookup) {
+        for (int i = 0; i < nch; i++) {
+            gl_t b = pc_host->deltas[i][1], delta = pc_host->deltas[i][3];
+            pc_host->delta_pow_slots[i] = gl_pow(delta, cd.lut_slots);
+            const uint16_t* data = C->lut_data.data();
+            for (int r = 0; r < cd.num_luts; r++) {
+                int len = C->lut_lens[r];
+                int rows = (len + cd.lut_slots - 1) / cd.lut_slots, degree = rows * cd.lut_slots;
+                gl_t acc = 0;
+                for (int e = 0; e < degree; e++) {
+                    gl_t combo = e < len ? gl_add(data[2 * e], gl_mul(b, data[2 * e + 1])) : 0;
+                    acc = gl_add(gl_mul(acc, delta), combo);
+                }
+                pc_host->lut_evals[i][r] = acc;
+                data += 2 * len;
+            }
+        }
+    }
+    ProofConsts* d_pc;
+    CU(cudaMallocAsync((void**)&d_pc, sizeof(ProofConsts), st));
+    CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
+
+    // ---- Z, partial products, lookup polys ----
+    gl_t* d_zs;
+    if ((rc = ctx_alloc(ctx, &d_zs, (size_t)zs_cols * n))) return rc;
+    {
+        dim3 grid((unsigned)((n + 127) / 128), nch);
+        zs_chunk_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_sigmas, C->d_subgroup, d_zs);
+        zs_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_zs);
+        if (has_lookup) {
+            lookup_rows_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_row_kind, d_zs);
+            lookup_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_pc, C->d_row_kind, d_zs);
+        }
+        CU(cudaGetLastError());
+    }
+    if (ctx->keep_debug) {
+        ctx->last_zs.resize((size_t)zs_cols * n);
+        CU(cudaMemcpyAsync(ctx->last_zs.data(), d_zs, ctx->last_zs.size() * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+    }
+    tm.mark();
+    if ((rc = commit_dev(ctx, d_zs, zs_cols, logn, cd.rate_bits, d.cap_height, true, &zb, true))) return rc;
+    ctx_free(ctx, d_zs);
+    tm.mark();
+    ch.observe_many(zb->cap_host.data(), capw);
+    // pc_host (pinned) was consumed by the H2D copy above once commit_dev synchronised
+    for (int i = 0; i < nch; i++) {
+        pc_host->alphas[i] = ch.get();
+        gl_t p = 1;
+        for (int k = 0; k < 160; k++) { pc_host->alpha_pows[i][k] = p; p = gl_mul(p, pc_host->alphas[i]); }
+    }
+    CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
+
+    // ---- quotient ----
+    gl_t *d_qv, *d_qa, *d_qc;
+    if ((rc = ctx_alloc(ctx, &d_qv, (size_t)nch * N))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_qa, (size_t)nch * N))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_qc, (size_t)nch * N))) return rc;
+    quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
+    CU(cudaGetLastError());
+    {
+        const NttPlan* inv;
+        if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, logn, 0, &inv))) return rc;
+        if (ntt_launch(inv, d_qv, n, d_qa, n, nch * 8, 1, st)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
+        dim3 grid((unsigned)((n + 255) / 256), nch);
+        quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, d_qa, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
+        CU(cudaGetLastError());
+    }
+    if (ctx->keep_debug) {
+        ctx->last_quotient_chunks.resize((size_t)nch * N);
+        CU(cudaMemcpyAsync(ctx->last_quotient_chunks.data(), d_qc, (size_t)nch * N * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+    }
+    tm.mark();
+    if ((rc = commit_dev(ctx, d_qc, nch * qdf, logn, cd.rate_bits, d.cap_height, false, &qb, true))) return rc;
+    ctx_free(ctx, d_qv); ctx_free(ctx, d_qa); ctx_free(ctx, d_qc);
+    tm.mark();
+    ch.observe_many(qb->cap_host.data(), capw);
+    const ext_t zeta = ch.get_ext();
+    const gl_t g = gl_root_of_unity(logn);
+    const ext_t zeta_next = ext_mul_base(zeta, g);
+
+    // ---- openings ----
+    const p2g_batch* oracles[4] = {C->cs, wb, zb, qb};
+    const int tot0 = NC + R + W + zpp + nch * qdf + nlz, tot1 = nch + nlz;
+    std::vector<const gl_t*> plist(tot0 + tot1);
+    {
+        int k = 0;
+        for (int i = 0; i < NC + R; i++) plist[k++] = oracles[0]->coeffs + (size_t)i * n;
+        for (int i = 0; i < W; i++) plist[k++] = oracles[1]->coeffs + (size_t)i * n;
+        for (int i = 0; i < zpp; i++) plist[k++] = oracles[2]->coeffs + (size_t)i * n;
+        for (int i = 0; i < nch * qdf; i++) plist[k++] = oracles[3]->coeffs + (size_t)i * n;
+        for (int i = zpp; i < zs_cols; i++) plist[k++] = oracles[2]->coeffs + (size_t)i * n;
+        for (int i = 0; i < nch; i++) plist[k++] = oracles[2]->coeffs + (size_t)i * n;
+        for (int i = zpp; i < zs_cols; i++) plist[k++] = oracles[2]->coeffs + (size_t)i * n;
+    }
+    const gl_t** d_plist; gl_t *d_zp, *d_open;
+    CU(cudaMallocAsync((void**)&d_plist, plist.size() * sizeof(gl_t*), st));
+    CU(cudaMemcpyAsync(d_plist, plist.data(), plist.size() * sizeof(gl_t*), cudaMemcpyHostToDevice, st));
+    if ((rc = ctx_alloc(ctx, &d_zp, 4 * n))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_open, 2 * (size_t)(tot0 + tot1)))) return rc;
+    {
+        Pow2Table t0, t1;
+        t0.p[0] = zeta; t1.p[0] = zeta_next;
+        for (int b = 1; b < 32; b++) { t0.p[b] = ext_mul(t0.p[b - 1], t0.p[b - 1]); t1.p[b] = ext_mul(t1.p[b - 1], t1.p[b - 1]); }
+        ext_powers_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t0, n, d_zp);
+        ext_powers_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t1, n, d_zp + 2 * n);
+        eval_polys_kernel<<<tot0, 256, 0, st>>>(d_plist, d_zp, n, d_open);
+        eval_polys_kernel<<<tot1, 256, 0, st>>>(d_plist + tot0, d_zp + 2 * n, n, d_open + 2 * (size_t)tot0);
+        CU(cudaGetLastError());
+    }
+    std::vector<ext_t> open((size_t)tot0 + tot1);
+    CU(cudaMemcpyAsync(ctx->pinned, d_open, open.size() * sizeof(ext_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(open.data(), ctx->pinned, open.size() * sizeof(ext_t));
+    tm.mark();
+    ch.observe_many((const gl_t*)open.data(), 2 * open.size());
+
+    // ---- proof assembly starts: caps + openings ----
+    gl_t* w = proof_out;
+    memcpy(w, wb->cap_host.data(), capw * 8); w += capw;
+    memcpy(w, zb->cap_host.data(), capw * 8); w += capw;
+    memcpy(w, qb->cap_host.data(), capw * 8); w += capw;
+    {
+        const ext_t* o0 = open.data(); const ext_t* o1 = open.data() + tot0;
+        auto put = [&](const ext_t* p, int cnt) { memcpy(w, p, (size_t)cnt * sizeof(ext_t)); w += 2 * (size_t)cnt; };
+        int off = 0;
+        put(o0 + off, NC); off += NC;            // constants
+        put(o0 + off, R); off += R;              // plonk_sigmas
+        put(o0 + off, W); off += W;              // wires
+        put(o0 + off, nch);                      // plonk_zs
+        put(o1, nch);                            // plonk_zs_next
+        put(o0 + off + nch, nch * num_prods); off += zpp;   // partial_products
+        put(o0 + off, nch * qdf); off += nch * qdf;         // quotient_polys
+        put(o0 + off, nlz);                      // lookup_zs
+        put(o1 + nch, nlz);                      // lookup_zs_next
+    }
+
+    // ---- prove_openings: batch combination ----
+    const ext_t fri_alpha = ch.get_ext();
+    gl_t *d_comp, *d_comp_lde, *d_vals;
+    if ((rc = ctx_alloc(ctx, &d_comp, 4 * n))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_comp_lde, 4 * N))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_vals, 2 * N))) return rc;
+    fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist, tot0, fri_alpha, n, d_comp, d_comp + n);
+    fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist + tot0, tot1, fri_alpha, n, d_comp + 2 * n, d_comp + 3 * n);
+    CU(cudaGetLastError());
+    {
+        const NttPlan* lde;
+        if ((rc = ctx_get_plan(ctx, NTT_KIND_LDE, logn, cd.rate_bits, &lde))) return rc;
+        if (ntt_launch(lde, d_comp, n, d_comp_lde, N, 4, 0, st)) { ctx->err = "fri lde"; return P2G_E_CUDA; }
+        ext_t comp0_at = ext_reduce_with_powers(open.data(), tot0, fri_alpha);
+        ext_t comp1_at = ext_reduce_with_powers(open.data() + tot0, tot1, fri_alpha);
+        ext_t shift0 = ext_pow(fri_alpha, (uint64_t)tot1);
+        fri_final_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_comp_lde, N, C->d_domain, zeta, zeta_next, comp0_at, comp1_at, shift0, d_vals);
+        CU(cudaGetLastError());
+    }
+    tm.mark();
+
+    // ---- fri_committed_trees ----
+    const int nl = d.num_reduction_arity_bits;
+    struct Layer { gl_t* vals; gl_t* digests; gl_t* cap; int log_len, arity_bits; };
+    std::vector<Layer> layers(nl);
+    gl_t* cur_vals = d_vals; int cur_log = logN;
+    gl_t shift = 7;
+    ext_t fri_betas[16];
+    for (int l = 0; l < nl; l++) {
+        const int ab = d.reduction_arity_bits[l];
+        if (ab > 4) { ctx->err = "arity > 16"; return P2G_E_BADARG; }
+        Layer& L = layers[l];
+        L.vals = cur_vals; L.log_len = cur_log; L.arity_bits = ab;
+        const uint32_t log_leaves = cur_log - ab;
+        if ((rc = ctx_alloc(ctx, &L.digests, merkle_digest_words(log_leaves, d.cap_height)))) return rc;
+        if ((rc = ctx_alloc(ctx, &L.cap, capw))) return rc;
+        if (merkle_build(cur_vals, 0, 0, 2u << ab, log_leaves, d.cap_height, L.digests, L.cap, st)) { ctx->err = "fri merkle"; return P2G_E_CUDA; }
+        CU(cudaMemcpyAsync(ctx->pinned, L.cap, capw * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        memcpy(w, ctx->pinned, capw * sizeof(gl_t));
+        ch.observe_many(w, capw);
+        w += capw;
+        const ext_t beta = ch.get_ext();
+        fri_betas[l] = beta;
+        gl_t* nxt;
+        if ((rc = ctx_alloc(ctx, &nxt, (size_t)2 << log_leaves))) return rc;
+        const size_t chunks = (size_t)1 << log_leaves;
+        fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, st>>>(cur_vals, cur_log, ab, gl_inv(shift), gl_inv(gl_root_of_unity(cur_log)),
+                                                                           gl_inv(gl_root_of_unity(ab)), gl_inv((gl_t)1 << ab), beta, nxt);
+        CU(cudaGetLastError());
+        cur_vals = nxt; cur_log = (int)log_leaves;
+        shift = gl_pow(shift, (uint64_t)1 << ab);
+    }
+    // final polynomial: interpolate the last layer on the host (<= a few hundred points)
+    const size_t fl = (size_t)1 << cur_log;
+    std::vector<ext_t> fvals(fl), fcoef(fl);
+    CU(cudaMemcpyAsync(ctx->pinned, cur_vals, fl * sizeof(ext_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(fvals.data(), ctx->pinned, fl * sizeof(ext_t));
+    {
+        // natural-order values, then coset_ifft(shift): c_i = shift^-i / len * sum_m v[m] w^-(i m)
+        std::vector<ext_t> nat(fl);
+        for (size_t j = 0; j < fl; j++) nat[gl_bitrev((uint32_t)j, cur_log)] = fvals[j];
+        gl_t winv = gl_inv(gl_root_of_unity(cur_log)), linv = gl_inv((gl_t)fl), sinv = gl_inv(shift);
+        std::vector<gl_t> wp(fl);
+        wp[0] = 1; for (size_t i = 1; i < fl; i++) wp[i] = gl_mul(wp[i - 1], winv);
+        gl_t sc = linv;
+        for (size_t i = 0; i < fl; i++) {
+            ext_t acc = ext_make(0, 0);
+            for (size_t m = 0; m < fl; m++) acc = ext_add(acc, ext_mul_base(nat[m], wp[(i * m) & (fl - 1)]));
+            fcoef[i] = ext_mul_base(acc, sc);
+            sc = gl_mul(sc, sinv);
+        }
+    }
+    const size_t final_len = fl >> cd.rate_bits;
+    for (size_t i = final_len; i < fl; i++)
+        if (fcoef[i].c0 || fcoef[i].c1) { ctx->err = "FRI final polynomial has non-zero high coefficients"; return P2G_E_UNSAT; }
+    ch.observe_many((const gl_t*)fcoef.data(), 2 * final_len);
+    tm.mark();
+
+    // ---- fri_proof_of_work: lowest nonce ----
+    gl_t pow_witness = 0;
+    {
+        PowState ps; memcpy(ps.s, ch.state, sizeof(ps.s));
+        const int pos = ch.in_len;
+        for (int i = 0; i < pos; i++) ps.s[i] = ch.in_buf[i];
+        unsigned long long* d_best;
+        CU(cudaMallocAsync((void**)&d_best, 8, st));
+        const unsigned long long WIN = 1ull << 20;
+        bool found = false;
+        for (unsigned long long base = 0; !found && base < (1ull << 40); base += WIN) {
+            CU(cudaMemsetAsync(d_best, 0xFF, 8, st));
+            pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, st>>>(ps, pos, d.pow_bits, base, d_best);
+            CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            unsigned long long best = *(unsigned long long*)ctx->pinned;
+            if (best != ~0ull) { pow_witness = best; found = true; }
+        }
+        cudaFreeAsync(d_best, st);
+        if (!found) { ctx->err = "proof of work failed"; return P2G_E_POW; }
+        ch.observe(pow_witness);
+        gl_t resp = ch.get();
+        if ((resp >> (64 - d.pow_bits)) != 0) { ctx->err = "proof of work response mismatch"; return P2G_E_POW; }
+    }
+    tm.mark();
+
+    // ---- query rounds ----
+    const int nq = d.num_query_rounds;
+    std::vector<unsigned long long> qidx(nq);
+    for (int q = 0; q < nq; q++) qidx[q] = ch.get() % N;
+    std::vector<GatherTree> gt;
+    unsigned long long rec = 0;
+    const int ocols[4] = {NC + R, W, zs_cols, nch * qdf};
+    for (int o = 0; o < 4; o++) {
+        GatherTree T; T.data = oracles[o]->lde; T.digests = oracles[o]->digests; T.col_stride = N;
+        T.leaf_len = ocols[o]; T.log_leaves = logN; T.path_len = logN - d.cap_height; T.index_shift = 0; T.out_offset = rec;
+        rec += T.leaf_len + 1 + 4ull * T.path_len;
+        gt.push_back(T);
+    }
+    {
+        unsigned shift_bits = 0;
+        for (int l = 0; l < nl; l++) {
+            shift_bits += layers[l].arity_bits;
+            GatherTree T; T.data = layers[l].vals; T.digests = layers[l].digests; T.col_stride = 0;
+            T.leaf_len = 2u << layers[l].arity_bits; T.log_leaves = layers[l].log_len - layers[l].arity_bits;
+            T.path_len = T.log_leaves - d.cap_height; T.index_shift = shift_bits; T.out_offset = rec;
+            rec += T.leaf_len + 1 + 4ull * T.path_len;
+            gt.push_back(T);
+        }
+    }
+    GatherTree* d_gt; unsigned long long* d_qidx; gl_t* d_q;
+    CU(cudaMallocAsync((void**)&d_gt, gt.size() * sizeof(GatherTree), st));
+    CU(cudaMallocAsync((void**)&d_qidx, nq * 8, st));
+    if ((rc = ctx_alloc(ctx, &d_q, rec * nq))) return rc;
+    CU(cudaMemcpyAsync(d_gt, gt.data(), gt.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_qidx, qidx.data(), nq * 8, cudaMemcpyHostToDevice, st));
+    query_gather_kernel<<<dim3(nq, (unsigned)gt.size()), 128, 0, st>>>(d_gt, (int)gt.size(), d_qidx, rec, d_q);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(w, d_q, rec * nq * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    w += rec * nq;
+    memcpy(w, fcoef.data(), final_len * sizeof(ext_t)); w += 2 * final_len;
+    *w++ = pow_witness;
+    for (int i = 0; i < d.num_public_inputs; i++) *w++ = public_inputs[i];
+    tm.mark();
+    tm.finish(&ctx->timings);
+
+    // transcript for parity tests
+    {
+        p2g_transcript& tr = ctx->transcript; memset(&tr, 0, sizeof(tr));
+        for (int i = 0; i < nch; i++) { tr.betas[i] = pc_host->betas[i]; tr.gammas[i] = pc_host->gammas[i]; tr.alphas[i] = pc_host->alphas[i]; }
+        memcpy(tr.deltas, deltas_flat, sizeof(gl_t) * 4 * nch);
+        tr.zeta[0] = zeta.c0; tr.zeta[1] = zeta.c1; tr.fri_alpha[0] = fri_alpha.c0; tr.fri_alpha[1] = fri_alpha.c1;
+        for (int l = 0; l < nl; l++) { tr.fri_betas[2 * l] = fri_betas[l].c0; tr.fri_betas[2 * l + 1] = fri_betas[l].c1; }
+        tr.pow_witness = pow_witness;
+        for (int q = 0; q < nq && q < 64; q++) tr.query_indices[q] = qidx[q];
+    }
+    // release
+    for (int l = 0; l < nl; l++) { ctx_free(ctx, layers[l].digests); ctx_free(ctx, layers[l].cap); if (l > 0) ctx_free(ctx, layers[l].vals); }
+    if (nl > 0) ctx_free(ctx, cur_vals);
+    ctx_free(ctx, d_vals); ctx_free(ctx, d_comp); ctx_free(ctx, d_comp_lde); ctx_free(ctx, d_zp); ctx_free(ctx, d_open);
+    cudaFreeAsync((void*)d_plist, st); cudaFreeAsync(d_gt, st); cudaFreeAsync(d_qidx, st); ctx_free(ctx, d_q); cudaFreeAsync(d_pc, st);
+    p2g_batch_free(ctx, wb); p2g_batch_free(ctx, zb); p2g_batch_free(ctx, qb);
+    if (d_wires) ctx_free(ctx, d_wires);
+    if ((size_t)(w - proof_out) != C->proof_words) { ctx->err = "proof length mismatch"; return P2G_E_BADARG; }
+    if (proof_words_out) *proof_words_out = (size_t)(w - proof_out);
+    return P2G_OK;
+}
+
+extern "C" int32_t p2g_prove(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host, const uint64_t* public_inputs,
+                             uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {
+    return prove_impl(ctx, c, wires_host, true, public_inputs, proof_out, proof_cap_words, proof_words_out);
+}
+extern "C" int32_t p2g_prove_dev(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_dev, const uint64_t* public_inputs,
+                                 uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {
+    return prove_impl(ctx, c, wires_dev, false, public_inputs, proof_out, proof_cap_words, proof_words_out);
+}
+extern "C" int32_t p2g_last_transcript(p2g_ctx* ctx, p2g_transcript* out) {
+    if (!ctx || !out) return P2G_E_BADARG;
+    *out = ctx->transcript; return P2G_OK;
+}
+extern "C" int32_t p2g_last_zs_values(p2g_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out || ctx->last_zs.empty()) return P2G_E_BADARG;
+    memcpy(out, ctx->last_zs.data(), ctx->last_zs.size() * sizeof(gl_t)); return P2G_OK;
+}
+extern "C" int32_t p2g_last_quotient_chunks(p2g_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out || ctx->last_quotient_chunks.empty()) return P2G_E_BADARG;
+    memcpy(out, ctx->last_quotient_chunks.data(), ctx->last_quotient_chunks.size() * sizeof(gl_t)); return P2G_OK;
+}
+extern "C" int32_t p2g_last_timings(p2g_ctx* ctx, p2g_timings* out) {
+    if (!ctx || !out) return P2G_E_BADARG;
+    *out = ctx->timings; return P2G_OK;
+}
+// enabled bit 0: per-stage CUDA-event timing; bit 1: keep stage dumps (zs values, quotient chunks)
+extern "C" int32_t p2g_set_timing(p2g_ctx* ctx, int32_t enabled) {
+    if (!ctx) return P2G_E_BADARG;
+    ctx->timing = (enabled & 1) != 0; ctx->keep_debug = (enabled & 2) != 0; return P2G_OK;
+}
+
+extern "C" int32_t p2g_pow_grind(p2g_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t pow_bits, uint64_t* nonce_out) {
+    if (!ctx || !state || !nonce_out || pos >= 12 || pow_bits == 0 || pow_bits > 40) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    PowState ps; memcpy(ps.s, state, sizeof(ps.s));
+    unsigned long long* d_best;
+    CU(cudaMallocAsync((void**)&d_best, 8, ctx->st));
+    const unsigned long long WIN = 1ull << 20;
+    for (unsigned long long base = 0; base < (1ull << 44); base += WIN) {
+        CU(cudaMemsetAsync(d_best, 0xFF, 8, ctx->st));
+        pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, ctx->st>>>(ps, (int)pos, (int)pow_bits, base, d_best);
+        CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        unsigned long long best = *(unsigned long long*)ctx->pinned;
+        if (best != ~0ull) { *nonce_out = best; cudaFreeAsync(d_best, ctx->st); return P2G_OK; }
+    }
+    cudaFreeAsync(d_best, ctx->st);
+    return P2G_E_POW;
+}
+
+extern "C" int32_t p2g_fri_fold(p2g_ctx* ctx, const uint64_t* values_host, uint32_t log_len, uint32_t arity_bits, uint64_t shift,
+                                const uint64_t beta[2], uint64_t* out_host) {
+    if (!ctx || !values_host || !out_host || arity_bits == 0 || arity_bits > 4 || log_len < arity_bits || log_len > 26) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    const size_t len = (size_t)1 << log_len, chunks = len >> arity_bits;
+    gl_t *d_in, *d_out; int rc;
+    if ((rc = ctx_alloc(ctx, &d_in, 2 * len))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_out, 2 * chunks))) return rc;
+    CU(cudaMemcpyAsync(d_in, values_host, 2 * len * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+    ext_t b = ext_make(beta[0], beta[1]);
+    fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->st>>>(d_in, (int)log_len, (int)arity_bits, gl_inv(shift),
+                                                                         gl_inv(gl_root_of_unity((int)log_len)), gl_inv(gl_root_of_unity((int)arity_bits)),
+                                                                         gl_inv((gl_t)1 << arity_bits), b, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_host, d_out, 2 * chunks * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx_free(ctx, d_in); ctx_free(ctx, d_out);
+    return P2G_OK;
+}

@@ -1,0 +1,585 @@
+// Device kernels of the prove() hot path beyond commitment: Z / partial products, lookup
+// running sums, quotient evaluation, openings, FRI batch combination, FRI folding, proof-of-work
+// grind and query gathering.  Each kernel cites the plonky2 function it replaces (dependency
+// pinned at /root/reference/Cargo.toml:12, entered through `data.prove(pw)`,
+// /root/reference/aes-gcm/src/circuit_gcm.rs:781).
+#pragma once
+#include "common.h"
+#include "poseidon.cuh"
+#include "../../include/p2gpu.h"
+
+#define MAX_CH 2
+#define MAX_ROUTED 80
+
+// ---------------------------------------------------------------------------------------------
+// affine maps x -> a*x + b and their block-wide exclusive scan (prefix products, running sums,
+// the RE recurrence of the lookup argument are all instances)
+// ---------------------------------------------------------------------------------------------
+struct Aff { gl_t a, b; };
+__device__ __forceinline__ Aff aff_id() { Aff r; r.a = 1; r.b = 0; return r; }
+// f first, then g
+__device__ __forceinline__ Aff aff_then(Aff f, Aff g) {
+    Aff r; r.a = gl_mul(g.a, f.a); r.b = gl_add(gl_mul(g.a, f.b), g.b); return r;
+}
+__device__ __forceinline__ gl_t aff_apply(Aff f, gl_t x) { return gl_add(gl_mul(f.a, x), f.b); }
+__device__ __forceinline__ Aff aff_shfl_up(Aff v, int d) {
+    Aff r; r.a = __shfl_up_sync(0xffffffffu, v.a, d); r.b = __shfl_up_sync(0xffffffffu, v.b, d); return r;
+}
+// exclusive scan over the threads of a block (thread 0 gets the identity); sm: 32 entries
+__device__ __forceinline__ Aff block_scan_exclusive(Aff mine, Aff* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    Aff cur = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Aff o = aff_shfl_up(cur, d);
+        if (lane >= d) cur = aff_then(o, cur);
+    }
+    if (lane == 31) sm[warp] = cur;
+    __syncthreads();
+    if (warp == 0) {
+        Aff w = lane < nwarps ? sm[lane] : aff_id();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Aff o = aff_shfl_up(w, d);
+            if (lane >= d) w = aff_then(o, w);
+        }
+        sm[lane] = w;
+    }
+    __syncthreads();
+    Aff prev = aff_shfl_up(cur, 1);
+    if (lane == 0) prev = aff_id();
+    Aff base = warp > 0 ? sm[warp - 1] : aff_id();
+    Aff r = aff_then(base, prev);
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-proof constants shared by several kernels (uploaded once per proof)
+// ---------------------------------------------------------------------------------------------
+struct ProofConsts {
+    gl_t betas[MAX_CH], gammas[MAX_CH], alphas[MAX_CH];
+    gl_t deltas[MAX_CH][4];                 // (a, b, alpha, delta) per challenge
+    gl_t beta_kis[MAX_CH][MAX_ROUTED];      // beta_c * k_j
+    gl_t k_is[MAX_ROUTED];
+    gl_t lut_evals[MAX_CH][8];
+    gl_t pi_hash[4];
+    gl_t alpha_pows[MAX_CH][160];           // alpha_c^k for the reduce_with_powers of the vanishing terms
+    gl_t zh[16], zh_inv[16];                // Z_H on coset s (natural coset index), and inverse
+    gl_t delta_pow_slots[MAX_CH];           // delta^(num_lut_slots)
+};
+
+struct CircuitDev {
+    int logn, rate_bits, nch, R, W, NC, num_sel, num_lsel, num_consts, num_prods, qdf;
+    int nlp, num_sldc, lut_degree, lu_degree, lu_slots, lut_slots, num_luts, num_gates, num_gate_constraints;
+    int zs_cols;
+};
+
+// ---------------------------------------------------------------------------------------------
+// wires_permutation_partial_products_and_zs (plonk/prover.rs), step 1: per row and challenge
+// the quotient of every chunk of 8 routed wires  prod(num)/prod(den).
+// Output layout (temporary, finished by zs_scan_kernel): chunk ck < num_prods goes to the
+// partial-product column ck, the last chunk to the Z column.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+zs_chunk_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ wires,
+                const gl_t* __restrict__ sigmas, const gl_t* __restrict__ subgroup, gl_t* __restrict__ zs) {
+    const size_t n = (size_t)1 << cd.logn;
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (r >= n) return;
+    const gl_t x = subgroup[r], beta = pc->betas[ch], gamma = pc->gammas[ch];
+    gl_t nums[16], dens[16];
+    const int nchunks = cd.num_prods + 1;
+#pragma unroll 1
+    for (int ck = 0; ck < nchunks; ck++) {
+        gl_t np = 1, dp = 1;
+        int lo = ck * cd.qdf, hi = min(lo + cd.qdf, cd.R);
+        for (int j = lo; j < hi; j++) {
+            gl_t w = wires[(size_t)j * n + r];
+            gl_t num = gl_add(gl_add(w, gl_mul(pc->beta_kis[ch][j], x)), gamma);
+            gl_t den = gl_add(gl_add(w, gl_mul(beta, sigmas[(size_t)j * n + r])), gamma);
+            np = gl_mul(np, num); dp = gl_mul(dp, den);
+        }
+        nums[ck] = np; dens[ck] = dp;
+    }
+    // batch inverse of the chunk denominators (one field inversion per thread)
+    gl_t pre[16];
+    gl_t acc = 1;
+#pragma unroll
+    for (int ck = 0; ck < 16; ck++) if (ck < nchunks) { pre[ck] = acc; acc = gl_mul(acc, dens[ck]); }
+    gl_t inv = gl_inv(acc);
+#pragma unroll
+    for (int ck = 15; ck >= 0; ck--) if (ck < nchunks) {
+        gl_t q = gl_mul(nums[ck], gl_mul(inv, pre[ck]));
+        inv = gl_mul(inv, dens[ck]);
+        int col = ck < cd.num_prods ? cd.nch + ch * cd.num_prods + ck : ch;
+        zs[(size_t)col * n + r] = q;
+    }
+}
+
+// step 2: Z(g^r) = prod_{r' < r} rowquotient(r'), partial products = Z * running chunk products.
+// One block per challenge; each thread owns a contiguous run of rows.
+__global__ void __launch_bounds__(1024)
+zs_scan_kernel(CircuitDev cd, gl_t* __restrict__ zs) {
+    __shared__ Aff sm[32];
+    const size_t n = (size_t)1 << cd.logn;
+    const int ch = blockIdx.x, nchunks = cd.num_prods + 1;
+    const size_t per = (n + blockDim.x - 1) / blockDim.x;
+    const size_t r0 = min(n, (size_t)threadIdx.x * per), r1 = min(n, r0 + per);
+    gl_t* Z = zs + (size_t)ch * n;
+    gl_t* PP = zs + ((size_t)cd.nch + (size_t)ch * cd.num_prods) * n;
+    Aff mine = aff_id();
+    for (size_t r = r0; r < r1; r++) {
+        gl_t p = Z[r];
+        for (int ck = 0; ck < cd.num_prods; ck++) p = gl_mul(p, PP[(size_t)ck * n + r]);
+        mine.a = gl_mul(mine.a, p);
+    }
+    Aff pre = block_scan_exclusive(mine, sm);
+    gl_t z = pre.a;   // Z at row r0 (Z(1) = 1)
+    for (size_t r = r0; r < r1; r++) {
+        gl_t q_last = Z[r];
+        gl_t accp = z;
+        for (int ck = 0; ck < cd.num_prods; ck++) {
+            accp = gl_mul(accp, PP[(size_t)ck * n + r]);
+            PP[(size_t)ck * n + r] = accp;
+        }
+        Z[r] = z;
+        z = gl_mul(accp, q_last);
+    }
+    (void)nchunks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compute_lookup_polys (plonk/prover.rs), step 1: per active row the row-local contributions.
+// row_kind: 0 = none, 1 = LookupGate row, 2 = LookupTableGate row.
+//   RE column      <- sum_s (in_s + b*out_s) * delta^(slots-1-s)            (LUT rows)
+//   SLDC column k  <- cumulative sum over slot groups 0..k of
+//                       mult_s / (alpha - looked_s)      (LUT rows)
+//                     -1 / (alpha - looking_s)            (LookupGate rows)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+lookup_rows_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ wires,
+                   const uint8_t* __restrict__ row_kind, gl_t* __restrict__ zs) {
+    const size_t n = (size_t)1 << cd.logn;
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (r >= n) return;
+    gl_t* base = zs + ((size_t)cd.nch * (1 + cd.num_prods) + (size_t)ch * cd.nlp) * n;
+    const int kind = row_kind[r];
+    if (kind == 0) {
+        for (int k = 0; k < cd.nlp; k++) base[(size_t)k * n + r] = 0;
+        return;
+    }
+    const gl_t da = pc->deltas[ch][0], db = pc->deltas[ch][1], dalpha = pc->deltas[ch][2], ddelta = pc->deltas[ch][3];
+    gl_t cum = 0;
+    if (kind == 2) {
+        gl_t re = 0;
+        for (int k = 0; k < cd.num_sldc; k++) {
+            int s0 = k * cd.lut_degree, s1 = min(s0 + cd.lut_degree, cd.lut_slots);
+            for (int s = s0; s < s1; s++) {
+                gl_t in = wires[(size_t)(3 * s) * n + r], o = wires[(size_t)(3 * s + 1) * n + r], m = wires[(size_t)(3 * s + 2) * n + r];
+                re = gl_add(gl_mul(re, ddelta), gl_add(in, gl_mul(db, o)));
+                gl_t den = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
+                cum = gl_add(cum, gl_mul(m, gl_inv(den)));
+            }
+            base[(size_t)(k + 1) * n + r] = cum;
+        }
+        base[r] = re;
+    } else {
+        for (int k = 0; k < cd.num_sldc; k++) {
+            int s0 = k * cd.lu_degree, s1 = min(s0 + cd.lu_degree, cd.lu_slots);
+            gl_t den[8], pre[8];
+            gl_t acc = 1;
+            for (int s = s0; s < s1; s++) {
+                gl_t in = wires[(size_t)(2 * s) * n + r], o = wires[(size_t)(2 * s + 1) * n + r];
+                den[s - s0] = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
+                pre[s - s0] = acc; acc = gl_mul(acc, den[s - s0]);
+            }
+            gl_t inv = gl_inv(acc);
+            for (int s = s1 - 1; s >= s0; s--) {
+                cum = gl_sub(cum, gl_mul(inv, pre[s - s0]));
+                inv = gl_mul(inv, den[s - s0]);
+            }
+            base[(size_t)(k + 1) * n + r] = cum;
+        }
+        base[r] = 0;
+    }
+}
+
+// step 2: backward recurrences over the rows (the lookup rows are deliberately upside down):
+//   SLDC_k(row) = X(row+1) + cum_k(row),  X(row) = SLDC_last(row)     on active rows, 0 elsewhere
+//   RE(row)     = RE(row+1) * delta^slots + B(row)                     on LUT rows, 0 elsewhere
+__global__ void __launch_bounds__(1024)
+lookup_scan_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const uint8_t* __restrict__ row_kind,
+                   gl_t* __restrict__ zs) {
+    __shared__ Aff sm[32];
+    const size_t n = (size_t)1 << cd.logn;
+    const int ch = blockIdx.x;
+    gl_t* base = zs + ((size_t)cd.nch * (1 + cd.num_prods) + (size_t)ch * cd.nlp) * n;
+    const gl_t dpow = pc->delta_pow_slots[ch];
+    // thread t owns rows [n - (t+1)*per, n - t*per) and walks them downwards
+    const size_t per = (n + blockDim.x - 1) / blockDim.x;
+    const size_t hi = n > (size_t)threadIdx.x * per ? n - (size_t)threadIdx.x * per : 0;
+    const size_t lo = hi > per ? hi - per : 0;
+    Aff fx = aff_id(), fre = aff_id();
+    for (size_t r = hi; r-- > lo;) {
+        int kind = row_kind[r];
+        if (kind == 0) { fx.a = 0; fx.b = 0; } else fx.b = gl_add(fx.b, base[(size_t)cd.num_sldc * n + r]);
+        if (kind == 2) { Aff g; g.a = dpow; g.b = base[r]; fre = aff_then(fre, g); } else { fre.a = 0; fre.b = 0; }
+    }
+    Aff px = block_scan_exclusive(fx, sm);
+    Aff pre_ = block_scan_exclusive(fre, sm);
+    gl_t X = px.b, RE = pre_.b;      // values entering from row `hi` (initial state 0)
+    for (size_t r = hi; r-- > lo;) {
+        int kind = row_kind[r];
+        if (kind == 0) { X = 0; RE = 0; continue; }
+        gl_t last = 0;
+        for (int k = 0; k < cd.num_sldc; k++) {
+            last = gl_add(X, base[(size_t)(k + 1) * n + r]);
+            base[(size_t)(k + 1) * n + r] = last;
+        }
+        X = last;
+        if (kind == 2) { RE = gl_add(gl_mul(RE, dpow), base[r]); base[r] = RE; } else { RE = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compute_quotient_polys + eval_vanishing_poly_base_batch (plonk/prover.rs, vanishing_poly.rs).
+// One thread per LDE point, reading the column-major bit-reversed LDE buffers directly
+// (coalesced: consecutive threads = consecutive leaf indices).  "next row" = natural index + 8
+// = same coset block, position bitrev(k + 1).  The result is scattered to natural order inside
+// each coset block so the inverse NTT that follows can take natural input.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ gl_t gate_filter(int row, int gs, int ge, gl_t s, bool many) {
+    gl_t f = 1;
+    for (int i = gs; i < ge; i++) if (i != row) f = gl_mul(f, gl_sub((gl_t)i, s));
+    if (many) f = gl_mul(f, gl_sub(0xFFFFFFFFULL, s));
+    return f;
+}
+
+__global__ void __launch_bounds__(128)
+quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const p2g_gate* __restrict__ gates,
+                const gl_t* __restrict__ cs, const gl_t* __restrict__ wl, const gl_t* __restrict__ zl,
+                const gl_t* __restrict__ domain, gl_t* __restrict__ out) {
+    const int logn = cd.logn, logN = logn + cd.rate_bits;
+    const size_t n = (size_t)1 << logn, N = (size_t)1 << logN;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const uint32_t blk = (uint32_t)(j >> logn), within = (uint32_t)(j & (n - 1));
+    const uint32_t k = gl_bitrev(within, logn);
+    const size_t jn = ((size_t)blk << logn) + gl_bitrev((k + 1) & (uint32_t)(n - 1), logn);
+    const uint32_t coset = gl_bitrev(blk, cd.rate_bits);
+    const gl_t x = domain[j];
+    const gl_t zh = pc->zh[coset];
+    const gl_t l0 = gl_mul(zh, gl_inv(gl_mul((gl_t)n, gl_sub(x, 1))));
+    const int nch = cd.nch, R = cd.R;
+    gl_t acc[MAX_CH];
+#pragma unroll
+    for (int c = 0; c < MAX_CH; c++) acc[c] = 0;
+    int t = 0;   // running term index
+#define ADD_TERM(idx, val) do { gl_t v_ = (val); _Pragma("unroll") for (int c_ = 0; c_ < MAX_CH; c_++) if (c_ < nch) \
+        acc[c_] = gl_add(acc[c_], gl_mul(v_, pc->alpha_pows[c_][(idx)])); } while (0)
+    // Z(x) - 1 terms
+    for (int c = 0; c < nch; c++) ADD_TERM(t + c, gl_mul(l0, gl_sub(zl[(size_t)c * N + j], 1)));
+    t += nch;
+    // partial products: both challenges share the wire / sigma loads
+    {
+        gl_t prev[MAX_CH];
+        for (int c = 0; c < nch; c++) prev[c] = zl[(size_t)c * N + j];
+        for (int ck = 0; ck <= cd.num_prods; ck++) {
+            gl_t np[MAX_CH], dp[MAX_CH];
+#pragma unroll
+            for (int c = 0; c < MAX_CH; c++) { np[c] = 1; dp[c] = 1; }
+            int lo = ck * cd.qdf, hi = min(lo + cd.qdf, R);
+            for (int w = lo; w < hi; w++) {
+                gl_t wv = wl[(size_t)w * N + j], sv = cs[(size_t)(cd.NC + w) * N + j];
+#pragma unroll
+                for (int c = 0; c < MAX_CH; c++) if (c < nch) {
+                    gl_t num = gl_add(gl_add(wv, gl_mul(pc->beta_kis[c][w], x)), pc->gammas[c]);
+                    gl_t den = gl_add(gl_add(wv, gl_mul(pc->betas[c], sv)), pc->gammas[c]);
+                    np[c] = gl_mul(np[c], num); dp[c] = gl_mul(dp[c], den);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < MAX_CH; c++) if (c < nch) {
+                gl_t next = ck == cd.num_prods ? zl[(size_t)c * N + jn] : zl[(size_t)(nch + c * cd.num_prods + ck) * N + j];
+                gl_t term = gl_sub(gl_mul(prev[c], np[c]), gl_mul(next, dp[c]));
+                ADD_TERM(t + c * (cd.num_prods + 1) + ck, term);
+                prev[c] = next;
+            }
+        }
+        t += nch * (cd.num_prods + 1);
+    }
+    // lookup terms (check_lookup_constraints_batch)
+    if (cd.num_luts > 0) {
+        const int zpp = nch * (1 + cd.num_prods);
+        const gl_t* lsel = cs + (size_t)cd.num_sel * N;       // lookup selector columns
+        const gl_t s_trans_sre = lsel[0 * N + j], s_trans_ldc = lsel[1 * N + j], s_init = lsel[2 * N + j], s_last = lsel[3 * N + j];
+        const int n_lookup_terms = 4 + cd.num_luts + 2 * cd.num_sldc;
+        for (int c = 0; c < nch; c++) {
+            const gl_t da = pc->deltas[c][0], db = pc->deltas[c][1], dalpha = pc->deltas[c][2], ddelta = pc->deltas[c][3];
+            const gl_t* lz = zl + (size_t)(zpp + c * cd.nlp) * N;
+            const int tb = t + c * n_lookup_terms;
+            const gl_t z_re = lz[j], next_z_re = lz[jn];
+            ADD_TERM(tb + 0, gl_mul(s_last, lz[(size_t)cd.num_sldc * N + j]));
+            ADD_TERM(tb + 1, gl_mul(s_init, lz[(size_t)1 * N + j]));
+            ADD_TERM(tb + 2, gl_mul(s_init, z_re));
+            for (int r = 0; r < cd.num_luts; r++)
+                ADD_TERM(tb + 3 + r, gl_mul(lsel[(size_t)(4 + r) * N + j], gl_sub(z_re, pc->lut_evals[c][r])));
+            gl_t re_cur = next_z_re;
+            const int tt = tb + 4 + cd.num_luts;   // index of the first per-poly term (after RE transition at tt-1)
+            for (int poly = 0; poly < cd.num_sldc; poly++) {
+                gl_t fl[8], fu[8];
+                int a0 = poly * cd.lut_degree, a1 = min(a0 + cd.lut_degree, cd.lut_slots);
+                int b0 = poly * cd.lu_degree, b1 = min(b0 + cd.lu_degree, cd.lu_slots);
+                gl_t mults[8];
+                for (int s = a0; s < a1; s++) {
+                    gl_t in = wl[(size_t)(3 * s) * N + j], o = wl[(size_t)(3 * s + 1) * N + j];
+                    mults[s - a0] = wl[(size_t)(3 * s + 2) * N + j];
+                    fl[s - a0] = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
+                    re_cur = gl_add(gl_mul(re_cur, ddelta), gl_add(in, gl_mul(db, o)));
+                }
+                for (int s = b0; s < b1; s++) {
+                    gl_t in = wl[(size_t)(2 * s) * N + j], o = wl[(size_t)(2 * s + 1) * N + j];
+                    fu[s - b0] = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
+                }
+                // prod and sum_i prod_{j != i} via prefix/suffix products
+                const int na = a1 - a0, nb = b1 - b0;
+                gl_t lut_prod = 1, lut_sum = 0, lu_prod = 1, lu_sum = 0;
+                {
+                    gl_t suf[9]; suf[na] = 1;
+                    for (int i = na - 1; i >= 0; i--) suf[i] = gl_mul(suf[i + 1], fl[i]);
+                    gl_t pre = 1;
+                    for (int i = 0; i < na; i++) { lut_sum = gl_add(lut_sum, gl_mul(mults[i], gl_mul(pre, suf[i + 1]))); pre = gl_mul(pre, fl[i]); }
+                    lut_prod = pre;
+                }
+                {
+                    gl_t suf[9]; suf[nb] = 1;
+                    for (int i = nb - 1; i >= 0; i--) suf[i] = gl_mul(suf[i + 1], fu[i]);
+                    gl_t pre = 1;
+                    for (int i = 0; i < nb; i++) { lu_sum = gl_add(lu_sum, gl_mul(pre, suf[i + 1])); pre = gl_mul(pre, fu[i]); }
+                    lu_prod = pre;
+                }
+                gl_t cur = lz[(size_t)(poly + 1) * N + j];
+                gl_t prev = poly == 0 ? lz[(size_t)cd.num_sldc * N + jn] : lz[(size_t)poly * N + j];
+                gl_t diff = gl_sub(cur, prev);
+                ADD_TERM(tt + 2 * poly, gl_mul(s_trans_sre, gl_sub(gl_mul(lut_prod, diff), lut_sum)));
+                ADD_TERM(tt + 2 * poly + 1, gl_mul(s_trans_ldc, gl_add(gl_mul(lu_prod, diff), lu_sum)));
+            }
+            ADD_TERM(tt - 1, gl_mul(s_trans_sre, gl_sub(z_re, re_cur)));
+        }
+        t += nch * n_lookup_terms;
+    }
+    // gate constraints: slot k accumulates filter * constraint_k over all gates
+    {
+        const gl_t* gconst = cs + (size_t)(cd.num_sel + cd.num_lsel) * N;
+        const bool many = cd.num_sel > 1;
+        gl_t f_arith = 0, f_const = 0, f_pi = 0;
+        int arith_ops = 0, nconst = 0;
+        for (int g = 0; g < cd.num_gates; g++) {
+            const p2g_gate G = gates[g];
+            if (G.num_constraints == 0) continue;
+            gl_t f = gate_filter(g, G.group_start, G.group_end, cs[(size_t)G.selector_index * N + j], many);
+            if (G.kind == P2G_GATE_ARITHMETIC) { f_arith = f; arith_ops = G.param0; }
+            else if (G.kind == P2G_GATE_CONSTANT) { f_const = f; nconst = G.param0; }
+            else if (G.kind == P2G_GATE_PUBLIC_INPUT) f_pi = f;
+        }
+        const gl_t c0 = cd.num_consts > 0 ? gconst[j] : 0, c1 = cd.num_consts > 1 ? gconst[N + j] : 0;
+        for (int k = 0; k < cd.num_gate_constraints; k++) {
+            gl_t v = 0;
+            if (k < arith_ops) {
+                gl_t m0 = wl[(size_t)(4 * k) * N + j], m1 = wl[(size_t)(4 * k + 1) * N + j];
+                gl_t ad = wl[(size_t)(4 * k + 2) * N + j], o = wl[(size_t)(4 * k + 3) * N + j];
+                gl_t comp = gl_add(gl_mul(gl_mul(m0, m1), c0), gl_mul(ad, c1));
+                v = gl_mul(f_arith, gl_sub(o, comp));
+            }
+            if (k < nconst) v = gl_add(v, gl_mul(f_const, gl_sub(k == 0 ? c0 : c1, wl[(size_t)k * N + j])));
+            if (k < 4 && f_pi) v = gl_add(v, gl_mul(f_pi, gl_sub(wl[(size_t)k * N + j], pc->pi_hash[k])));
+            ADD_TERM(t + k, v);
+        }
+    }
+#undef ADD_TERM
+    const gl_t zi = pc->zh_inv[coset];
+    for (int c = 0; c < nch; c++)
+        out[(size_t)c * N + ((size_t)blk << logn) + k] = gl_mul(acc[c], zi);
+}
+
+// Recover the quotient chunk coefficients from the 8 per-coset inverse NTTs:
+//   t_c[j] = 7^(-n c)/8 * sum_s w_8^(-s c) * h_s^(-j) * a_s[j],  h_s = 7 w_N^s
+// in: [nch][8 blocks (bit-reversed coset order)][n]; table: [8 (natural coset s)][n] = h_s^(-j)/8
+__global__ void __launch_bounds__(256)
+quotient_combine_kernel(int logn, int nch, const gl_t* __restrict__ in, const gl_t* __restrict__ table,
+                        const gl_t* __restrict__ w8inv_pows /*[8]*/, const gl_t* __restrict__ shift_n_inv_pows /*[8]*/,
+                        gl_t* __restrict__ out /*[nch*8][n]*/) {
+    const size_t n = (size_t)1 << logn;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (j >= n) return;
+    gl_t v[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        uint32_t blk = gl_bitrev((uint32_t)s, 3);
+        v[s] = gl_mul(in[((size_t)ch * 8 + blk) * n + j], table[(size_t)s * n + j]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        gl_t acc = 0;
+#pragma unroll
+        for (int s = 0; s < 8; s++) acc = gl_add(acc, gl_mul(v[s], w8inv_pows[(s * c) & 7]));
+        out[((size_t)ch * 8 + c) * n + j] = gl_mul(acc, shift_n_inv_pows[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// OpeningSet::new (plonk/proof.rs): f(zeta) for every committed polynomial.
+// powers: zp[j] = zeta^j (ext, interleaved c0,c1).  One block per polynomial.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ext_powers_kernel(ext_t z, const ext_t* __restrict__ z_pow2 /*[32]: z^(2^b)*/, size_t count, gl_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    ext_t r = ext_make(1, 0);
+    size_t e = j;
+    for (int b = 0; e; b++, e >>= 1) if (e & 1) r = ext_mul(r, z_pow2[b]);
+    out[2 * j] = r.c0; out[2 * j + 1] = r.c1;
+    (void)z;
+}
+__global__ void __launch_bounds__(256)
+eval_polys_kernel(const gl_t* const* __restrict__ polys, const gl_t* __restrict__ zp, size_t n, gl_t* __restrict__ out) {
+    __shared__ gl_t s0[256], s1[256];
+    const gl_t* c = polys[blockIdx.x];
+    gl_t a0 = 0, a1 = 0;
+    for (size_t j = threadIdx.x; j < n; j += blockDim.x) {
+        gl_t cv = c[j];
+        a0 = gl_add(a0, gl_mul(cv, zp[2 * j])); a1 = gl_add(a1, gl_mul(cv, zp[2 * j + 1]));
+    }
+    s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) { s0[threadIdx.x] = gl_add(s0[threadIdx.x], s0[threadIdx.x + d]); s1[threadIdx.x] = gl_add(s1[threadIdx.x], s1[threadIdx.x + d]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = s0[0]; out[2 * blockIdx.x + 1] = s1[0]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PolynomialBatch::prove_openings (fri/oracle.rs): composition polynomial of one batch,
+// comp[k] = sum_j alpha^j f_j[k] (Horner from the last polynomial), output as two base columns.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fri_compose_kernel(const gl_t* const* __restrict__ polys, int npolys, ext_t alpha, size_t n,
+                   gl_t* __restrict__ out_c0, gl_t* __restrict__ out_c1) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ext_t acc = ext_make(0, 0);
+    for (int j = npolys - 1; j >= 0; j--) acc = ext_add_base(ext_mul(acc, alpha), polys[j][k]);
+    out_c0[k] = acc.c0; out_c1[k] = acc.c1;
+}
+// final(x) = alpha^{|b1|} (comp0(x) - comp0(zeta)) / (x - zeta) + (comp1(x) - comp1(g zeta)) / (x - g zeta)
+// lde: [4][N] = comp0.c0, comp0.c1, comp1.c0, comp1.c1 on the LDE domain (bit-reversed); out [N][2]
+__global__ void __launch_bounds__(256)
+fri_final_values_kernel(const gl_t* __restrict__ lde, size_t N, const gl_t* __restrict__ domain, ext_t zeta, ext_t zeta_next,
+                        ext_t comp0_at, ext_t comp1_at, ext_t shift0, gl_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const gl_t x = domain[j];
+    ext_t v0 = ext_sub(ext_make(lde[j], lde[N + j]), comp0_at);
+    ext_t v1 = ext_sub(ext_make(lde[2 * N + j], lde[3 * N + j]), comp1_at);
+    ext_t d0 = ext_make(gl_sub(x, zeta.c0), gl_neg(zeta.c1));
+    ext_t d1 = ext_make(gl_sub(x, zeta_next.c0), gl_neg(zeta_next.c1));
+    ext_t r = ext_add(ext_mul(shift0, ext_mul(v0, ext_inv(d0))), ext_mul(v1, ext_inv(d1)));
+    out[2 * j] = r.c0; out[2 * j + 1] = r.c1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fri_committed_trees (fri/prover.rs), fold step in the VALUE domain: the reference folds
+// coefficients (coeffs'[k] = sum_i coeffs[16k+i] beta^i) and re-FFTs; evaluating that on the
+// next coset gives, for chunk k of 16 bit-reversed values on {x0 * w_16^m}:
+//   r = iDFT16(values)  (coefficients of Q(x0 Y)),   out[k] = sum_i r_i (beta / x0)^i
+// values: [len][2] bit-reversed order on coset shift*<w_len>;  out: [len/arity][2]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+fri_fold_kernel(const gl_t* __restrict__ values, int log_len, int arity_bits, gl_t shift_inv, gl_t w_len_inv,
+                gl_t w_arity_inv, gl_t arity_inv, ext_t beta, gl_t* __restrict__ out) {
+    const int arity = 1 << arity_bits;
+    const size_t chunks = (size_t)1 << (log_len - arity_bits);
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= chunks) return;
+    ext_t u[16];
+    // u[m] = value at x0 * w_arity^m = chunk entry bitrev(m)
+    for (int m = 0; m < arity; m++) {
+        int tpos = gl_bitrev((uint32_t)m, arity_bits);
+        u[m] = ext_make(values[2 * (k * arity + tpos)], values[2 * (k * arity + tpos) + 1]);
+    }
+    // x0^-1 = shift^-1 * w_len^-(bitrev_{log_len - arity_bits}(k))
+    uint32_t e = gl_bitrev((uint32_t)k, log_len - arity_bits);
+    gl_t x0_inv = gl_mul(shift_inv, gl_pow(w_len_inv, e));
+    ext_t y = ext_mul_base(beta, x0_inv);
+    // out = sum_i r_i y^i with r_i = (1/arity) sum_m u[m] w^-(i m): evaluate directly (arity <= 16)
+    gl_t wp[16];
+    wp[0] = 1;
+    for (int i = 1; i < arity; i++) wp[i] = gl_mul(wp[i - 1], w_arity_inv);
+    ext_t acc = ext_make(0, 0);
+    for (int i = arity - 1; i >= 0; i--) {
+        ext_t r = ext_make(0, 0);
+        for (int m = 0; m < arity; m++) r = ext_add(r, ext_mul_base(u[m], wp[(i * m) & (arity - 1)]));
+        acc = ext_add(ext_mul(acc, y), r);
+    }
+    acc = ext_mul_base(acc, arity_inv);
+    out[2 * k] = acc.c0; out[2 * k + 1] = acc.c1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fri_proof_of_work (fri/prover.rs): lowest nonce in [base, base + count) whose response
+// (state[7] after the permutation) has pow_bits leading zeros; atomicMin keeps the minimum.
+// ---------------------------------------------------------------------------------------------
+struct PowState { gl_t s[12]; };
+__global__ void __launch_bounds__(256)
+pow_grind_kernel(PowState st, int pos, int pow_bits, unsigned long long base, unsigned long long* __restrict__ best) {
+    const unsigned long long cand = base + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    gl_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = st.s[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) if (i == pos) s[i] = cand;
+    poseidon_permute(s);
+    if ((s[7] >> (64 - pow_bits)) == 0) atomicMin(best, cand);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fri_prover_query_rounds: gather leaf rows and Merkle paths of all queries into one buffer.
+// One block per (query, tree).  Tree descriptor: column-major (LDE batches) or row-major (FRI).
+// ---------------------------------------------------------------------------------------------
+struct GatherTree {
+    const gl_t* data; const gl_t* digests;
+    unsigned long long col_stride;   // column-major stride (N); 0 = row-major
+    unsigned int leaf_len, log_leaves, path_len, index_shift;  // leaf index = query_index >> index_shift
+    unsigned long long out_offset;   // offset inside one query's record
+};
+__global__ void __launch_bounds__(128)
+query_gather_kernel(const GatherTree* __restrict__ trees, int ntrees, const unsigned long long* __restrict__ qidx,
+                    unsigned long long record_words, gl_t* __restrict__ out) {
+    const int q = blockIdx.x, t = blockIdx.y;
+    const GatherTree T = trees[t];
+    const size_t leaf = (size_t)(qidx[q] >> T.index_shift);
+    gl_t* o = out + (size_t)q * record_words + T.out_offset;
+    for (unsigned int c = threadIdx.x; c < T.leaf_len; c += blockDim.x)
+        o[c] = T.col_stride ? T.data[(size_t)c * T.col_stride + leaf] : T.data[leaf * T.leaf_len + c];
+    if (threadIdx.x == 0) o[T.leaf_len] = T.path_len;
+    for (unsigned int w = threadIdx.x; w < 4 * T.path_len; w += blockDim.x) {
+        unsigned int lvl = w >> 2;
+        size_t off = 0;
+        for (unsigned int k = 0; k < lvl; k++) off += ((size_t)4 << (T.log_leaves - k));
+        size_t node = (leaf >> lvl) ^ 1;
+        o[T.leaf_len + 1 + w] = T.digests[off + 4 * node + (w & 3)];
+    }
+}
+
+// domain points in leaf order: x_j = 7 * w_N^bitrev(j);  subgroup g^i
+__global__ void domain_kernel(int logN, gl_t wN, gl_t shift, gl_t* __restrict__ out, int bitrev_order) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ((size_t)1 << logN)) return;
+    uint32_t e = bitrev_order ? gl_bitrev((uint32_t)j, logN) : (uint32_t)j;
+    out[j] = gl_mul(shift, gl_pow(wN, e));
+}

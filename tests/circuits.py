@@ -1,0 +1,78 @@
+"""Shared circuit fixtures for the tests: the reference's own test shapes
+(/root/reference/aes-gcm/src/circuit_gcm.rs:737-783 `test_encrypt_op`, circuit_aes.rs:657-726)."""
+import functools
+
+import numpy as np
+
+from plonky2_aes_b200.host.circuit_builder import CircuitBuilder, PartialWitness
+from plonky2_aes_b200.host.gadgets import native
+from plonky2_aes_b200.host.gadgets.aes import (AESStateOps, byte_xor_lut, flatten, from_flat, gf_2_8_mul_lut, sbox_lut,
+                                               state_mix_matrix)
+from plonky2_aes_b200.host.gadgets.gcm import AesGcmTarget
+
+
+@functools.lru_cache(maxsize=None)
+def tiny_arith():
+    """arithmetic-only circuit (no lookups): exercises is_equal/select and n = 8"""
+    b = CircuitBuilder()
+    x, y = b.add_virtual_target(), b.add_virtual_target()
+    z = b.mul(x, y)
+    w = b.add(z, x)
+    e = b.is_equal(w, y)
+    s = b.select(e, x, y)
+    b.connect(s, b.add_virtual_target())
+    data = b.build()
+    pw = PartialWitness()
+    pw.set_target(x, 3)
+    pw.set_target(y, 5)
+    return data, data.generate_witness(pw)
+
+
+@functools.lru_cache(maxsize=None)
+def aes_block(nk=4, nr=10):
+    """single AES block encryption circuit, FIPS-197 App. B vector (circuit_aes.rs:619-726)"""
+    b = CircuitBuilder()
+    ops = AESStateOps(b)
+    sb, xo, gf = sbox_lut(b), byte_xor_lut(b), gf_2_8_mul_lut(b)
+    key_t = [ops.add_virtual_byte_target(sb) for _ in range(4 * nk)]
+    pt_t = [ops.add_virtual_byte_target(sb) for _ in range(16)]
+    ct_t = [ops.add_virtual_byte_target(sb) for _ in range(16)]
+    mix = state_mix_matrix(b)
+    w = ops.key_expansion(nk, nr, xo, sb, key_t)
+    out = flatten(ops.encrypt_block(nr, xo, gf, sb, mix, from_flat(pt_t), w))
+    for a, c in zip(out, ct_t):
+        b.connect(a, c)
+    data = b.build()
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    pt = bytes.fromhex("3243f6a8885a308d313198a2e0370734")
+    ct = bytes.fromhex("3925841d02dc09fbdc118597196a0b32")
+    targets = key_t + pt_t + ct_t
+    pw = PartialWitness()
+    for t, v in zip(targets, key + pt + ct):
+        pw.set_target(t, v)
+    return data, data.generate_witness(pw), (targets, key, pt, ct)
+
+
+@functools.lru_cache(maxsize=None)
+def aes_gcm(L=16, tag=True):
+    """AesGcmTarget::<4,4,10,L,TAG> with the reference's fixed test pattern
+    key=[42;16], nonce=[111;12], pt=[42;L] (circuit_gcm.rs:750-752)"""
+    b = CircuitBuilder()
+    tg = AesGcmTarget(b, 4, 10, L, tag)
+    data = b.build()
+    key, nonce, pt = bytes([42] * 16), bytes([111] * 12), bytes([42] * L)
+    ct, tagv = native.gcm_encrypt(key, nonce, pt)
+    pw = PartialWitness()
+    tg.set_targets(pw, key, nonce, pt, ct, tagv)
+    return data, data.generate_witness(pw), tg
+
+
+def gcm_inputs(tg, seed, count):
+    """`count` random (key, nonce, pt) with their ct/tag as witness input rows"""
+    rows = []
+    for i in range(count):
+        raw = np.random.default_rng(seed + i).bytes(28 + tg.L)
+        key, nonce, pt = raw[:16], raw[16:28], raw[28:]
+        ct, tagv = native.gcm_encrypt(key, nonce, pt)
+        rows.append(tg.input_values(key, nonce, pt, ct, tagv))
+    return np.array(rows, dtype=np.uint64)

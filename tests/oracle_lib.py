@@ -44,6 +44,17 @@ class Oracle:
         lib.orc_merkle_verify.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_int, vp, C.c_size_t]
         lib.orc_merkle_verify.restype = C.c_int
         lib.orc_num_threads.restype = C.c_int
+        lib.orc_circuit_load.argtypes = [vp]
+        lib.orc_circuit_load.restype = vp
+        lib.orc_circuit_free.argtypes = [vp]
+        lib.orc_circuit_cap.argtypes = [vp]
+        lib.orc_circuit_cap.restype = vp
+        lib.orc_proof_len.argtypes = [vp]
+        lib.orc_proof_len.restype = C.c_size_t
+        lib.orc_prove_debug.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp]
+        lib.orc_prove_debug.restype = C.c_long
+        lib.orc_verify.argtypes = [vp, vp, C.c_size_t]
+        lib.orc_verify.restype = C.c_int
 
     # --- small helpers returning numpy ---
     def poseidon(self, state):
@@ -140,6 +151,51 @@ class OracleBatch:
         if self.b:
             self.orc.lib.orc_batch_free(self.b)
             self.b = None
+
+
+class OracleTranscript(C.Structure):
+    _fields_ = [("betas", C.c_uint64 * 4), ("gammas", C.c_uint64 * 4), ("deltas", C.c_uint64 * 16),
+                ("alphas", C.c_uint64 * 4), ("zeta", C.c_uint64 * 2), ("fri_alpha", C.c_uint64 * 2),
+                ("fri_betas", C.c_uint64 * 32), ("pow_witness", C.c_uint64), ("query_indices", C.c_uint64 * 64)]
+
+
+class OracleCircuit:
+    """orc_circuit_load on the descriptor of a host CircuitData (same C layout as p2g_circuit_desc)."""
+
+    def __init__(self, orc, data):
+        self.orc, self.data = orc, data
+        self.desc = data.descriptor()
+        self.h = orc.lib.orc_circuit_load(C.addressof(self.desc))
+        self.proof_len = orc.lib.orc_proof_len(C.addressof(self.desc))
+        self.cap = _view(orc.lib.orc_circuit_cap(self.h), (1 << data.config.fri_config.cap_height, 4))
+
+    def prove(self, wires, debug=False):
+        wires = np.ascontiguousarray(wires, dtype=np.uint64)
+        out = np.zeros(self.proof_len, dtype=np.uint64)
+        tr = OracleTranscript()
+        zs = qc = None
+        zs_p = qc_p = None
+        if debug:
+            d = self.desc
+            nlp = 0 if d.num_luts == 0 else -(-(d.num_routed_wires // 2) // (d.quotient_degree_factor - 1)) + 1
+            zs_cols = d.num_challenges * (1 + d.num_partial_products + nlp)
+            zs = np.zeros((zs_cols, self.data.n), dtype=np.uint64)
+            qc = np.zeros((d.num_challenges * d.quotient_degree_factor, self.data.n), dtype=np.uint64)
+            zs_p, qc_p = zs.ctypes.data, qc.ctypes.data
+        rc = self.orc.lib.orc_prove_debug(self.h, wires.ctypes.data, None, out.ctypes.data, out.size, C.addressof(tr), zs_p, qc_p)
+        if rc < 0:
+            raise ValueError(f"oracle prove failed: {rc}")
+        assert rc == self.proof_len, (rc, self.proof_len)
+        return (out, tr, zs, qc) if debug else out
+
+    def verify(self, proof):
+        proof = np.ascontiguousarray(proof, dtype=np.uint64)
+        return self.orc.lib.orc_verify(self.h, proof.ctypes.data, proof.size)
+
+    def free(self):
+        if self.h:
+            self.orc.lib.orc_circuit_free(self.h)
+            self.h = None
 
 
 _ORACLE = None

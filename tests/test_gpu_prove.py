@@ -1,0 +1,120 @@
+"""GPU parity of the whole prove() path through the C ABI (p2g_prove) against the CPU oracle:
+identical transcript, identical Z / partial-product / lookup polynomials, identical quotient
+chunks, bit-identical proof words, and every GPU proof accepted by the restated verifier."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from plonky2_aes_b200.host import ffi
+from tests import circuits, oracle_lib
+
+pytestmark = pytest.mark.gpu
+P = 0xFFFFFFFF00000001
+
+
+def _gpu_debug(ctx, data, wires):
+    lib = ctx.lib
+    ctx.check(lib.p2g_set_timing(ctx.handle, 3))
+    proof = data.prove_wires(wires)
+    tr = ffi.Transcript()
+    ctx.check(lib.p2g_last_transcript(ctx.handle, C.byref(tr)))
+    d = data.descriptor()
+    nlp = 0 if d.num_luts == 0 else -(-(d.num_routed_wires // 2) // (d.quotient_degree_factor - 1)) + 1
+    zs = np.empty((d.num_challenges * (1 + d.num_partial_products + nlp), data.n), dtype=np.uint64)
+    qc = np.empty((d.num_challenges * d.quotient_degree_factor, data.n), dtype=np.uint64)
+    ctx.check(lib.p2g_last_zs_values(ctx.handle, zs.ctypes.data))
+    ctx.check(lib.p2g_last_quotient_chunks(ctx.handle, qc.ctypes.data))
+    ctx.check(lib.p2g_set_timing(ctx.handle, 0))
+    return proof, tr, zs, qc
+
+
+def _check(ctx, oracle, data, wires):
+    data.load(ctx)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    assert np.array_equal(oc.cap, data.constants_sigmas_cap)
+    o_proof, o_tr, o_zs, o_qc = oc.prove(wires, debug=True)
+    g_proof, g_tr, g_zs, g_qc = _gpu_debug(ctx, data, wires)
+    for f in ("betas", "gammas", "deltas"):
+        assert list(getattr(g_tr, f)) == list(getattr(o_tr, f)), f
+    assert np.array_equal(g_zs, o_zs), "Z / partial products / lookup polynomials"
+    assert list(g_tr.alphas) == list(o_tr.alphas)
+    assert np.array_equal(g_qc, o_qc), "quotient chunks"
+    for f in ("zeta", "fri_alpha", "fri_betas", "query_indices"):
+        assert list(getattr(g_tr, f)) == list(getattr(o_tr, f)), f
+    assert g_tr.pow_witness == o_tr.pow_witness
+    assert len(g_proof) == len(o_proof)
+    assert np.array_equal(g_proof, o_proof), "proof words"
+    assert oc.verify(g_proof) == 0
+    return oc
+
+
+def test_tiny_circuit(gpu_ctx, oracle):
+    data, wires = circuits.tiny_arith()
+    oc = _check(gpu_ctx, oracle, data, wires)
+    w2 = wires.copy(); w2[3, 0] = (int(w2[3, 0]) + 1) % P
+    assert oc.verify(data.prove_wires(w2)) == -20        # unsatisfied witness -> rejected proof
+    oc.free()
+
+
+def test_aes_block_c1(gpu_ctx, oracle):
+    data, wires, _ = circuits.aes_block()
+    _check(gpu_ctx, oracle, data, wires).free()
+
+
+def test_aes_gcm_tag_small(gpu_ctx, oracle):
+    data, wires, tg = circuits.aes_gcm(13, True)
+    oc = _check(gpu_ctx, oracle, data, wires)
+    many = data.generate_witnesses(tg.input_targets(), circuits.gcm_inputs(tg, 5, 2))
+    for w in many:
+        assert oc.verify(data.prove_wires(w)) == 0
+    oc.free()
+
+
+def test_aes_gcm_256_tag_c2(gpu_ctx, oracle):
+    """BASELINE config 2: AES-GCM-128, 256-byte plaintext, with tag; n = 2^15."""
+    data, wires, tg = circuits.aes_gcm(256, True)
+    assert data.n == 1 << 15
+    _check(gpu_ctx, oracle, data, wires).free()
+
+
+def test_stage_helpers(gpu_ctx, oracle):
+    rng = np.random.default_rng(3)
+    # proof-of-work grind: lowest nonce
+    st = rng.integers(0, P, size=12, dtype=np.uint64)
+    nonce = C.c_uint64()
+    gpu_ctx.check(gpu_ctx.lib.p2g_pow_grind(gpu_ctx.handle, st.ctypes.data, 5, 12, C.byref(nonce)))
+    best = None
+    for cand in range(nonce.value + 1):
+        s = st.copy(); s[5] = cand
+        if int(oracle.poseidon(s)[7]) >> 52 == 0:
+            best = cand
+            break
+    assert best == nonce.value
+    # FRI fold against the coefficient-domain definition
+    log_len, ab = 8, 4
+    ln = 1 << log_len
+    coeffs = rng.integers(0, P, size=(ln, 2), dtype=np.uint64)
+    shift = 7
+    vals = np.stack([oracle.coset_fft(coeffs[:, 0], shift), oracle.coset_fft(coeffs[:, 1], shift)], axis=1)
+    rev = np.array([int(format(i, f"0{log_len}b")[::-1], 2) for i in range(ln)])
+    vals_br = np.ascontiguousarray(vals[rev])
+    beta = rng.integers(0, P, size=2, dtype=np.uint64)
+    out = np.empty((ln >> ab, 2), dtype=np.uint64)
+    gpu_ctx.check(gpu_ctx.lib.p2g_fri_fold(gpu_ctx.handle, vals_br.ctypes.data, log_len, ab, shift, beta.ctypes.data, out.ctypes.data))
+
+    def emul(a, b):
+        return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+    folded = []
+    b = (int(beta[0]), int(beta[1]))
+    for k in range(ln >> ab):
+        acc = (0, 0)
+        for i in reversed(range(1 << ab)):
+            acc = emul(acc, b)
+            acc = ((acc[0] + int(coeffs[16 * k + i, 0])) % P, (acc[1] + int(coeffs[16 * k + i, 1])) % P)
+        folded.append(acc)
+    folded = np.array(folded, dtype=np.uint64)
+    nshift = pow(shift, 1 << ab, P)
+    nv = np.stack([oracle.coset_fft(folded[:, 0], nshift), oracle.coset_fft(folded[:, 1], nshift)], axis=1)
+    rev2 = np.array([int(format(i, f"0{log_len - ab}b")[::-1], 2) for i in range(ln >> ab)])
+    assert np.array_equal(out, nv[rev2])

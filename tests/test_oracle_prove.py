@@ -1,0 +1,96 @@
+"""CPU: the oracle's restated prover + verifier on the reference's circuit shapes, and the
+witness-source vectors the reference's tests pin (FIPS-197, NIST CAVP GCM)."""
+import numpy as np
+import pytest
+
+from plonky2_aes_b200.host.circuit_builder import PartialWitness
+from plonky2_aes_b200.host.gadgets import native
+from tests import circuits, oracle_lib
+
+P = 0xFFFFFFFF00000001
+
+
+def test_native_aes_fips197_vectors():
+    # /root/reference/aes-gcm/src/native_aes.rs:165-224 (FIPS-197 App. A first words, App. B block)
+    w = native.key_expansion(list(bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")), 4, 10)
+    assert bytes(w[4]).hex() == "a0fafe17" and bytes(w[43]).hex() == "b6630ca6"
+    w = native.key_expansion(list(bytes.fromhex("8e73b0f7da0e6452c810f32b809079e562f8ead2522c6b7b")), 6, 12)
+    assert bytes(w[6]).hex() == "fe0c91f7"
+    w = native.key_expansion(list(bytes.fromhex("603deb1015ca71be2b73aef0857d77811f352c073b6108d72d9810a30914dff4")), 8, 14)
+    assert bytes(w[8]).hex() == "9ba35411"
+    # FIPS-197 §4.2: {57} x {13} = {fe}  (circuit_aes.rs:488-498)
+    assert [native.gf_2_8_mul(0x57, v) for v in (1, 2, 4, 8, 0x10, 0x13)] == [0x57, 0xae, 0x47, 0x8e, 0x07, 0xfe]
+
+
+def test_native_gcm_nist_cavp_vectors():
+    # /root/reference/aes-gcm/src/native_gcm.rs:286-330: NIST CAVP AES-128-GCM, 96-bit IV, no AAD
+    vecs = [
+        ("11754cd72aec309bf52f7687212e8957", "3c819d9a9bed087615030b65", "", "", "250327c674aaf477aef2675748cf6971"),
+        ("7fddb57453c241d03efbed3ac44e371c", "ee283a3fc75575e33efd4887", "d5de42b461646c255c87bd2962d3b9a2",
+         "2ccda4a5415cb91e135c2a0f78c9b2fd", "b36d1df9b9d5e596f83e8b7f52971cb3"),
+    ]
+    for key, iv, pt, ct, tag in vecs:
+        c, t = native.gcm_encrypt(bytes.fromhex(key), bytes.fromhex(iv), bytes.fromhex(pt))
+        assert c.hex() == ct and t.hex() == tag
+    from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+    rng = np.random.default_rng(7)
+    for L in (0, 1, 13, 16, 33, 256):
+        k, n, p = rng.bytes(16), rng.bytes(12), rng.bytes(L)
+        c, t = native.gcm_encrypt(k, n, p)
+        assert c + t == AESGCM(k).encrypt(n, p, None)
+
+
+def test_tiny_circuit_prove_verify(oracle):
+    data, wires = circuits.tiny_arith()
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    proof = oc.prove(wires)
+    assert oc.verify(proof) == 0
+    bad = proof.copy(); bad[len(bad) // 2] ^= 1
+    assert oc.verify(bad) != 0
+    w2 = wires.copy(); w2[3, 0] = (int(w2[3, 0]) + 1) % P          # break an arithmetic gate
+    assert oc.verify(oc.prove(w2)) == -20
+    oc.free()
+
+
+def test_aes_block_circuit_prove_verify(oracle):
+    """C1: the reference's single-block test circuit with the FIPS-197 App. B witness."""
+    data, wires, (targets, key, pt, ct) = circuits.aes_block()
+    assert data.n == 8192
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    proof, tr, zs, qc = oc.prove(wires, debug=True)
+    assert oc.verify(proof) == 0
+    assert tr.pow_witness < (1 << 24)
+    assert int(zs[0, 0]) == 1 and int(zs[1, 0]) == 1          # Z(1) = 1
+    # wrong ciphertext: the witness generator refuses (prove() -> Err, circuit_aes.rs:403-405)
+    pw = PartialWitness()
+    badct = bytes([ct[0] ^ 1]) + ct[1:]
+    for t, v in zip(targets, key + pt + badct):
+        pw.set_target(t, v)
+    with pytest.raises(ValueError):
+        data.generate_witness(pw)
+    # non-byte input (test_assert_byte, circuit_aes.rs:385-411)
+    pw = PartialWitness()
+    for t, v in zip(targets, [256] + list(key[1:]) + list(pt) + list(ct)):
+        pw.set_target(t, v)
+    with pytest.raises(ValueError):
+        data.generate_witness(pw)
+    # a forged witness cell is caught by the verifier
+    w2 = wires.copy(); w2[1, 5] ^= 1
+    assert oc.verify(oc.prove(w2)) != 0
+    oc.free()
+
+
+def test_aes_gcm_tag_circuit(oracle):
+    """AesGcmTarget<4,4,10,13,true> — the reference's TAG=true test shape (circuit_gcm.rs:698)."""
+    data, wires, tg = circuits.aes_gcm(13, True)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    assert oc.verify(oc.prove(wires)) == 0
+    # batch witness generation agrees with the single path
+    vals = circuits.gcm_inputs(tg, 99, 3)
+    many = data.generate_witnesses(tg.input_targets(), vals)
+    pw = PartialWitness()
+    for t, v in zip(tg.input_targets(), vals[1]):
+        pw.set_target(t, int(v))
+    assert np.array_equal(many[1], data.generate_witness(pw))
+    assert oc.verify(oc.prove(many[2])) == 0
+    oc.free()
