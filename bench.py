@@ -1,0 +1,276 @@
+#!/usr/bin/env python3
+"""bench.py — AES-GCM proofs/sec on B200 (BASELINE.json metric), with the LDE+Merkle roofline
+and the CPU prover timed beside it.
+
+A "step" = proving one batch of PROOFS_PER_STEP independent proofs of BASELINE config 2
+(AES-GCM-128, 256-byte plaintext, GHASH tag; n = 2^15 rows, 135 wire columns) per GPU, each with
+a different witness.  `value` is measured with the witnesses already resident in HBM
+(p2g_prove_dev); `e2e` goes through the host API a user calls (CircuitData.prove_wires ->
+p2g_prove) with pinned host witnesses, so it includes the 35 MB H2D copy per proof and the D2H
+of every proof.  N > 1 shards independent proofs over ranks (no data-path collective; NCCL only
+carries the barrier and the max-over-ranks time): weak scaling.
+
+`--impl reference` times the CPU restatement of plonky2's prover (oracle/, OpenMP on all host
+cores) on the same circuit and witnesses; one step = one proof.  The Rust reference itself cannot
+be built in this image (no cargo/rustc; the prover lives in an un-vendored git dependency).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+L_BYTES = 256
+PROOFS_PER_STEP = 4
+METRIC = "AES-128 block proofs/sec at 1/2/4/8 B200; LDE+Merkle GB/s vs HBM peak"
+UNIT = "proofs/s"
+WORKLOAD = ("AES-GCM-128 16-block (256 B) plaintext with GHASH tag, standard_recursion_config, "
+            "n=2^15, 135 wires (BASELINE configs[1])")
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_workload(count, seed=20261018):
+    from tests import circuits
+    data, _, tg = circuits.aes_gcm(L_BYTES, True)
+    vals = circuits.gcm_inputs(tg, seed, count)
+    return data, tg, vals
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle prover (port of the reference's CPU algorithm) on all host cores."""
+    if rank != 0:
+        return
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    data, tg, vals = build_workload(2)
+    wires = data.generate_witnesses(tg.input_targets(), vals)
+    oc = oracle_lib.OracleCircuit(orc, data)
+    for i in range(args.warmup):
+        oc.prove(wires[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        proof = oc.prove(wires[i % 2])
+    dt = time.perf_counter() - t0
+    assert oc.verify(proof) == 0
+    v = args.steps / dt
+    cores = orc.lib.orc_num_threads()
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "proofs_per_step": 1},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{args.steps} proofs of the same circuit, one proof per step, OpenMP on {cores} threads"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from plonky2_aes_b200.host.polynomial_batch import Context, PolynomialBatch
+    from plonky2_aes_b200.host import ffi
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(local_rank)
+    lib = ctx.lib
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    # ---- workload: distinct witnesses per proof and per rank ----
+    B = PROOFS_PER_STEP
+    data, tg, vals = build_workload(B, seed=20261018 + 1000 * rank)
+    data.load(ctx)
+    n, W = data.n, 135
+    host_wires = torch.empty((B, W, n), dtype=torch.int64).pin_memory()
+    data.generate_witnesses(tg.input_targets(), vals, out=host_wires.numpy().view(np.uint64))
+    dev_wires = host_wires.cuda(non_blocking=False)
+    words = data.proof_words
+    proofs = torch.empty((B, words), dtype=torch.int64).pin_memory()
+    got = C.c_size_t()
+
+    def step_device():
+        for i in range(B):
+            ctx.check(lib.p2g_prove_dev(ctx.handle, data._gpu_circuit, dev_wires[i].data_ptr(), None,
+                                        proofs[i].data_ptr(), words, C.byref(got)))
+
+    def step_e2e():
+        for i in range(B):
+            ctx.check(lib.p2g_prove(ctx.handle, data._gpu_circuit, host_wires[i].data_ptr(), None,
+                                    proofs[i].data_ptr(), words, C.byref(got)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = lib.p2g_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps)
+    launches = lib.p2g_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    total_proofs = B * args.steps * world
+    value = total_proofs / (ms_dev * 1e-3)
+    e2e = total_proofs / (ms_e2e * 1e-3)
+
+    # ---- parity spot check of what was just timed (rank 0): the restated verifier accepts ----
+    verified = None
+    stages = None
+    roof = None
+    cpu = None
+    if rank == 0:
+        from tests import oracle_lib
+        orc = oracle_lib.load()
+        oc = oracle_lib.OracleCircuit(orc, data)
+        verified = oc.verify(proofs[B - 1].numpy().view(np.uint64)) == 0
+        # per-stage device times of one proof
+        ctx.check(lib.p2g_set_timing(ctx.handle, 1))
+        step_device()
+        tms = ffi.Timings()
+        ctx.check(lib.p2g_last_timings(ctx.handle, C.byref(tms)))
+        stages = {k: round(getattr(tms, k), 3) for k, _ in ffi.Timings._fields_}
+        # ---- roofline of the dominant kernel group: LDE + Merkle of the 135-column wires batch ----
+        peak, peak_kind = measured_peaks()
+        times = []
+        for _ in range(4):
+            b = PolynomialBatch.from_values_device(ctx, dev_wires[0].data_ptr(), W, data.degree_bits)
+            cm = (C.c_float * 3)()
+            ctx.check(lib.p2g_last_commit_timings(ctx.handle, C.byref(cm)))
+            times.append(list(cm))
+            b.free()
+        ctx.check(lib.p2g_set_timing(ctx.handle, 0))
+        intt_ms, lde_ms, merkle_ms = [min(t[i] for t in times[1:]) for i in range(3)]
+        N = 8 * n
+        lde_bytes = 72 * W * n                    # read coeffs once, write the LDE once
+        merkle_bytes = 8 * W * N + 96 * N         # read leaves, write digests + levels
+        perms = N * ((W + 7) // 8) + N - 16
+        poseidon_peak = ctx.poseidon_peak(32)
+        roof = {"bound": "hbm", "kernel": "merkle_leaves_kernel (Poseidon leaf sponge + in-block tree levels)",
+                "achieved": merkle_bytes / merkle_ms / 1e6, "peak": peak, "unit": "GB/s",
+                "frac": merkle_bytes / merkle_ms / 1e6 / peak, "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
+                "int_pipe": {"perms_per_s": perms / merkle_ms * 1e3, "peak_perms_per_s": poseidon_peak,
+                             "frac": perms / merkle_ms * 1e3 / poseidon_peak,
+                             "note": "Poseidon is INT-pipe bound (63 B of input per permutation); peak = chained "
+                                     "permutations without memory traffic (p2g_poseidon_peak)"},
+                "lde": {"ms": lde_ms, "achieved": lde_bytes / lde_ms / 1e6, "frac": lde_bytes / lde_ms / 1e6 / peak},
+                "intt_ms": intt_ms, "merkle_ms": merkle_ms,
+                "lde_merkle_gbs": (136 * W + 768) * n / (intt_ms + lde_ms + merkle_ms) / 1e6}
+        # ---- CPU baseline: the oracle prover on the host cores, bounded sample ----
+        if not args.no_cpu_baseline:
+            w0 = host_wires[0].numpy().view(np.uint64)
+            t0 = time.perf_counter()
+            cnt = 0
+            while cnt < 2 and (cnt == 0 or time.perf_counter() - t0 < 12):
+                p = oc.prove(w0)
+                cnt += 1
+            dt = time.perf_counter() - t0
+            ctx.check(lib.p2g_prove(ctx.handle, data._gpu_circuit, host_wires[0].data_ptr(), None, proofs[0].data_ptr(), words, C.byref(got)))
+            same = bool(np.array_equal(p, proofs[0].numpy().view(np.uint64)))
+            cores = orc.lib.orc_num_threads()
+            cpu = {"value": cnt / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cnt} proof(s) of the same circuit/witness by the CPU restatement (oracle/), OpenMP {cores} threads",
+                   "proof_bit_identical_to_gpu": same}
+        oc.free()
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u64 (Goldilocks p=2^64-2^32+1, exact)", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "proofs_per_step_per_gpu": B, "aes_blocks_per_proof": L_BYTES // 16,
+                          "aes_block_proofs_per_s": value * (L_BYTES // 16), "l2": "per-proof working set 1.0 GB > 126 MB L2",
+                          "parallelism": f"independent proofs sharded over {world} GPU(s)"},
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * W * n * 8, "d2h_bytes_per_step": B * words * 8,
+                       "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "stages_ms_one_proof": stages, "verifier_accepts": verified}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -136,7 +136,12 @@ typedef struct {
           fri_commit, pow, queries, total;
 } p2g_timings;
 int32_t p2g_last_timings(p2g_ctx* ctx, p2g_timings* out);
+/* bit 0: per-stage CUDA-event timing; bit 1: keep stage dumps for the read-backs above */
 int32_t p2g_set_timing(p2g_ctx* ctx, int32_t enabled);
+/* device ms of the last commit's three kernels groups: inverse NTT, coset LDE, Merkle tree */
+int32_t p2g_last_commit_timings(p2g_ctx* ctx, float out[3]);
+/* kernels launched by the library since it was loaded (all contexts) */
+uint64_t p2g_launch_count(void);
 
 /* ---- individual hot-path stages, exposed for parity tests and kernel benchmarks -------------- */
 /* fri_proof_of_work (fri/prover.rs): lowest nonce whose response has >= pow_bits leading zeros.

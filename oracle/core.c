@@ -26,16 +26,27 @@ static inline void mds_layer(gl_t s[12]) {
     /* out[r] = sum_i s[(i+r)%12]*CIRC[i] + s[r]*DIAG[r].  The coefficients are < 2^6, so the
      * 32-bit halves of the state can be accumulated separately in u64 without overflow and
      * recombined with one reduction (same value as the u128 accumulation upstream uses). */
-    uint64_t lo[24], hi[24];
-    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = s[i] & 0xFFFFFFFFULL; hi[i] = hi[i + 12] = s[i] >> 32; }
-    for (int r = 0; r < 12; r++) {
-        uint64_t al = 0, ah = 0;
-        for (int i = 0; i < 12; i++) { al += lo[i + r] * MDS_CIRC[i]; ah += hi[i + r] * MDS_CIRC[i]; }
-        al += lo[r] * MDS_DIAG[r]; ah += hi[r] * MDS_DIAG[r];
-        s[r] = gl_reduce128((unsigned __int128)al + ((unsigned __int128)ah << 32));
-    }
+    static const uint32_t C32[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t lo[24], hi[24];
+    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = (uint32_t)s[i]; hi[i] = hi[i + 12] = (uint32_t)(s[i] >> 32); }
+    uint64_t al[12], ah[12];
+    for (int r = 0; r < 12; r++) { al[r] = 0; ah[r] = 0; }
+    for (int i = 0; i < 12; i++)
+        for (int r = 0; r < 12; r++) { al[r] += (uint64_t)lo[i + r] * C32[i]; ah[r] += (uint64_t)hi[i + r] * C32[i]; }
+    al[0] += (uint64_t)lo[0] * 8; ah[0] += (uint64_t)hi[0] * 8;
+    for (int r = 0; r < 12; r++) s[r] = gl_reduce128((unsigned __int128)al[r] + ((unsigned __int128)ah[r] << 32));
 }
-void orc_poseidon(gl_t s[12]) {
+/* sum_j a[j]*b[j] mod p for 11 terms: the 32-bit halves of b are accumulated separately so no
+ * 128-bit carry tracking is needed (12 * 2^96 < 2^128) */
+static inline gl_t dot11(const gl_t* a, const gl_t* b, unsigned __int128 init) {
+    unsigned __int128 accl = init, acch = 0;
+    for (int j = 0; j < 11; j++) {
+        accl += (unsigned __int128)a[j] * (uint32_t)b[j];
+        acch += (unsigned __int128)a[j] * (uint32_t)(b[j] >> 32);
+    }
+    return gl_add(gl_reduce128(accl), gl_mul(gl_reduce128(acch), (gl_t)1 << 32));
+}
+void orc_poseidon_naive(gl_t s[12]) {
     int r = 0;
     for (int phase = 0; phase < 3; phase++) {
         int nr = phase == 1 ? 22 : 4;
@@ -46,6 +57,32 @@ void orc_poseidon(gl_t s[12]) {
             mds_layer(s);
         }
     }
+}
+
+/* The 22 partial rounds in their sparse form (upstream poseidon.rs: partial_first_constant_layer,
+ * mds_partial_layer_init, mds_partial_layer_fast); constants derived by tools/gen_poseidon_fast.py
+ * and checked there against the naive rounds (the leading FIRST_C / K values also match the
+ * recalled upstream FAST_PARTIAL_* tables). */
+#include "poseidon_fast.inc"
+static inline void full_round(gl_t s[12], int r) {
+    for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], RC[12 * r + i]));
+    mds_layer(s);
+}
+void orc_poseidon(gl_t s[12]) {
+    for (int r = 0; r < 4; r++) full_round(s, r);
+    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], PFAST_FIRST_C[i]);
+    {
+        gl_t t[11];
+        for (int r = 0; r < 11; r++) t[r] = dot11(PFAST_INIT + r * 11, s + 1, 0);
+        for (int r = 0; r < 11; r++) s[r + 1] = t[r];
+    }
+    for (int r = 0; r < 22; r++) {
+        gl_t t = gl_add(sbox7(s[0]), PFAST_K[r]);
+        gl_t s0 = dot11(PFAST_VROW + r * 11, s + 1, (unsigned __int128)t * 25);
+        for (int j = 0; j < 11; j++) s[j + 1] = gl_add(s[j + 1], gl_mul(PFAST_WCOL[r * 11 + j], t));
+        s[0] = s0;
+    }
+    for (int r = 26; r < 30; r++) full_round(s, r);
 }
 
 /* hashing.rs: hash_n_to_m_no_pad — overwrite-mode sponge, rate 8 */

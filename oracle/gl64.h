@@ -20,37 +20,30 @@ typedef uint64_t gl_t;
 #define GL_POW2_GENERATOR 1753635133440165772ULL /* POWER_OF_TWO_GENERATOR, order 2^32 */
 #define GL_EXT_W 7ULL
 
+/* all reductions are written branch-free (data-dependent branches mispredict heavily) */
 static inline gl_t gl_add(gl_t a, gl_t b) {
-    unsigned __int128 s = (unsigned __int128)a + b;
-    if (s >= GL_P) s -= GL_P;
-    return (gl_t)s;
+    uint64_t s = a + b;
+    uint64_t over = (uint64_t)(s < a) | (uint64_t)(s >= GL_P);
+    return s - (GL_P & (0 - over));
 }
-static inline gl_t gl_sub(gl_t a, gl_t b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline gl_t gl_sub(gl_t a, gl_t b) {
+    uint64_t d = a - b;
+    return d + (GL_P & (0 - (uint64_t)(a < b)));
+}
 static inline gl_t gl_neg(gl_t a) { return a ? GL_P - a : 0; }
 static inline gl_t gl_reduce128(unsigned __int128 x) {
+    /* upstream reduce128: x_lo - x_hi_hi + x_hi_lo * EPSILON, folded with 2^64 = 2^32 - 1, 2^96 = -1 */
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     uint64_t t0 = lo - hi_hi;
-    if (lo < hi_hi) t0 -= GL_EPS;
+    t0 -= GL_EPS & (0 - (uint64_t)(lo < hi_hi));
     uint64_t t1 = hi_lo * GL_EPS;
     uint64_t t2 = t0 + t1;
-    if (t2 < t1) t2 += GL_EPS;
-    if (t2 >= GL_P) t2 -= GL_P;
+    t2 += GL_EPS & (0 - (uint64_t)(t2 < t1));
+    t2 -= GL_P & (0 - (uint64_t)(t2 >= GL_P));
     return t2;
 }
-static inline gl_t gl_mul(gl_t a, gl_t b) {
-    /* upstream reduce128: x_lo - x_hi_hi + x_hi_lo * EPSILON; the result is the same residue. */
-    unsigned __int128 x = (unsigned __int128)a * b;
-    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
-    uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
-    uint64_t t0 = lo - hi_hi;
-    if (lo < hi_hi) t0 -= GL_EPS;
-    uint64_t t1 = hi_lo * GL_EPS;
-    uint64_t t2 = t0 + t1;
-    if (t2 < t1) t2 += GL_EPS;
-    if (t2 >= GL_P) t2 -= GL_P;
-    return t2;
-}
+static inline gl_t gl_mul(gl_t a, gl_t b) { return gl_reduce128((unsigned __int128)a * b); }
 static inline gl_t gl_sqr(gl_t a) { return gl_mul(a, a); }
 static inline gl_t gl_pow(gl_t b, uint64_t e) {
     gl_t r = 1;

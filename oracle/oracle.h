@@ -22,7 +22,8 @@ extern "C" {
 #endif
 
 /* ---- Poseidon / hashing ---- */
-void orc_poseidon(gl_t s[12]);
+void orc_poseidon(gl_t s[12]);        /* sparse partial rounds (what the prover uses) */
+void orc_poseidon_naive(gl_t s[12]);  /* textbook rounds; tests check both agree */
 void orc_hash_n_to_m_no_pad(const gl_t* in, size_t n, gl_t* out, size_t m);
 void orc_hash_no_pad(const gl_t* in, size_t n, gl_t out[4]);
 void orc_hash_or_noop(const gl_t* in, size_t n, gl_t out[4]);

@@ -5,7 +5,9 @@
 #include <string.h>
 #include <stdio.h>
 
+unsigned long long g_p2g_launches = 0;
 extern "C" int32_t p2g_version(void) { return 1; }
+extern "C" uint64_t p2g_launch_count(void) { return g_p2g_launches; }
 
 extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
     if (!out) return P2G_E_BADARG;
@@ -70,15 +72,25 @@ int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_
     if ((rc = ctx_alloc(ctx, &b->digests, merkle_digest_words(b->log_N(), cap_height)))) return rc;
     if ((rc = ctx_alloc(ctx, &b->cap, (size_t)4 << cap_height))) return rc;
     const NttPlan *inv, *lde;
+    cudaEvent_t ev[4];
+    const bool tim = ctx->timing;
+    if (tim) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->st); }
     if (from_values) {
         if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, log_n, 0, &inv))) return rc;
         if (ntt_launch(inv, cols_dev, n, b->coeffs, n, ncols, 1, ctx->st)) { ctx->err = "intt launch"; return P2G_E_CUDA; }
     } else {
         CU(cudaMemcpyAsync(b->coeffs, cols_dev, (size_t)ncols * n * sizeof(gl_t), cudaMemcpyDeviceToDevice, ctx->st));
     }
+    if (tim) cudaEventRecord(ev[1], ctx->st);
     if ((rc = ctx_get_plan(ctx, NTT_KIND_LDE, log_n, rate_bits, &lde))) return rc;
     if (ntt_launch(lde, b->coeffs, n, b->lde, N, ncols, 0, ctx->st)) { ctx->err = "lde launch"; return P2G_E_CUDA; }
+    if (tim) cudaEventRecord(ev[2], ctx->st);
     if (merkle_build(b->lde, 1, N, ncols, b->log_N(), cap_height, b->digests, b->cap, ctx->st)) { ctx->err = "merkle launch"; return P2G_E_CUDA; }
+    if (tim) {
+        cudaEventRecord(ev[3], ctx->st); cudaEventSynchronize(ev[3]);
+        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&ctx->commit_ms[i], ev[i], ev[i + 1]);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     b->cap_host.resize((size_t)4 << cap_height);
     if (sync_cap) {
         CU(cudaMemcpyAsync(ctx->pinned, b->cap, b->cap_host.size() * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
@@ -123,6 +135,11 @@ extern "C" int32_t p2g_commit_from_values_dev(p2g_ctx* ctx, const uint64_t* c, u
 extern "C" int32_t p2g_commit_from_coeffs_dev(p2g_ctx* ctx, const uint64_t* c, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
                                               uint32_t cap_height, p2g_batch** out, uint64_t* cap_out) {
     return commit_any(ctx, c, false, false, ncols, log_n, rate_bits, cap_height, out, cap_out);
+}
+extern "C" int32_t p2g_last_commit_timings(p2g_ctx* ctx, float out[3]) {
+    if (!ctx || !out) return P2G_E_BADARG;
+    for (int i = 0; i < 3; i++) out[i] = ctx->commit_ms[i];
+    return P2G_OK;
 }
 extern "C" int32_t p2g_batch_free(p2g_ctx* ctx, p2g_batch* b) {
     if (!ctx || !b) return P2G_E_BADARG;

@@ -5,6 +5,10 @@
 #include <stddef.h>
 #include "gl64.cuh"
 
+// number of kernels launched by this library since load (reported by bench.py as gpu_launches)
+extern unsigned long long g_p2g_launches;
+#define P2G_COUNT_LAUNCH(k) (g_p2g_launches += (k))
+
 #define P2G_MAX_LOG_M 14   // largest sub-transform held in shared memory (2^14 * 8 B = 128 KB)
 
 // ---- NTT (ntt.cu) -------------------------------------------------------------------------

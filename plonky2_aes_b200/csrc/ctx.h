@@ -33,6 +33,7 @@ struct p2g_ctx {
     p2g_transcript transcript;
     std::vector<gl_t> last_zs, last_quotient_chunks;
     bool keep_debug;
+    float commit_ms[3];     // last commit: inverse NTT, coset LDE, Merkle (when timing is on)
 };
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \

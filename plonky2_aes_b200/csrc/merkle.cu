@@ -133,6 +133,7 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
         merkle_leaves_kernel<true><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
     else
         merkle_leaves_kernel<false><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
+    P2G_COUNT_LAUNCH(1);
     uint32_t lv = levels_here;
     // wide levels: one launch each until <= 2048 nodes remain, then a single block finishes
     while (lv < L && ((size_t)1 << (log_leaves - lv - 1)) > 2048) {
@@ -140,9 +141,10 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
         const gl_t* src = digests + merkle_level_offset(log_leaves, lv);
         gl_t* dst = (lv + 1 >= L) ? cap : digests + merkle_level_offset(log_leaves, lv + 1);
         merkle_level_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(src, dst, cnt);
+        P2G_COUNT_LAUNCH(1);
         lv++;
     }
-    if (lv < L) merkle_top_kernel<<<1, 1024, 0, st>>>(digests, cap, log_leaves, L, lv);
+    if (lv < L) { merkle_top_kernel<<<1, 1024, 0, st>>>(digests, cap, log_leaves, L, lv); P2G_COUNT_LAUNCH(1); }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -161,5 +163,6 @@ poseidon_bench_kernel(gl_t* out, uint32_t iters) {
 }
 int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st) {
     poseidon_bench_kernel<<<nthreads_total / 256, 256, 0, st>>>(out, iters);
+    P2G_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

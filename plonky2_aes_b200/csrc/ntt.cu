@@ -148,6 +148,7 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
         ntt_dif_kernel<<<grid, threads, smem, st>>>(in + (size_t)c0 * in_stride, in_stride, out + (size_t)c0 * out_stride,
                                                     out_stride, plan->T, plan->tw, plan->log_n, plan->log_m,
                                                     plan->log_variants, out_mode);
+        P2G_COUNT_LAUNCH(1);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -134,8 +134,8 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
     // domain tables
     if ((rc = ctx_alloc(ctx, &C->d_subgroup, n))) return rc;
     if ((rc = ctx_alloc(ctx, &C->d_domain, N))) return rc;
-    domain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(cd.logn, gl_root_of_unity(cd.logn), 1, C->d_subgroup, 0);
-    domain_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->st>>>(logN, gl_root_of_unity(logN), 7, C->d_domain, 1);
+    P2G_COUNT_LAUNCH(1); domain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(cd.logn, gl_root_of_unity(cd.logn), 1, C->d_subgroup, 0);
+    P2G_COUNT_LAUNCH(1); domain_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->st>>>(logN, gl_root_of_unity(logN), 7, C->d_domain, 1);
     CU(cudaGetLastError());
     // quotient coefficient recovery tables
     {
@@ -303,11 +303,11 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = ctx_alloc(ctx, &d_zs, (size_t)zs_cols * n))) return rc;
     {
         dim3 grid((unsigned)((n + 127) / 128), nch);
-        zs_chunk_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_sigmas, C->d_subgroup, d_zs);
-        zs_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_zs);
+        P2G_COUNT_LAUNCH(1); zs_chunk_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_sigmas, C->d_subgroup, d_zs);
+        P2G_COUNT_LAUNCH(1); zs_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_zs);
         if (has_lookup) {
-            lookup_rows_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_row_kind, d_zs);
-            lookup_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_pc, C->d_row_kind, d_zs);
+            P2G_COUNT_LAUNCH(1); lookup_rows_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_row_kind, d_zs);
+            P2G_COUNT_LAUNCH(1); lookup_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_pc, C->d_row_kind, d_zs);
         }
         CU(cudaGetLastError());
     }
@@ -333,14 +333,14 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = ctx_alloc(ctx, &d_qv, (size_t)nch * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_qa, (size_t)nch * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_qc, (size_t)nch * N))) return rc;
-    quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
+    P2G_COUNT_LAUNCH(1); quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
     CU(cudaGetLastError());
     {
         const NttPlan* inv;
         if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, logn, 0, &inv))) return rc;
         if (ntt_launch(inv, d_qv, n, d_qa, n, nch * 8, 1, st)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
         dim3 grid((unsigned)((n + 255) / 256), nch);
-        quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, d_qa, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
+        P2G_COUNT_LAUNCH(1); quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, d_qa, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
         CU(cudaGetLastError());
     }
     if (ctx->keep_debug) {
@@ -379,10 +379,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         Pow2Table t0, t1;
         t0.p[0] = zeta; t1.p[0] = zeta_next;
         for (int b = 1; b < 32; b++) { t0.p[b] = ext_mul(t0.p[b - 1], t0.p[b - 1]); t1.p[b] = ext_mul(t1.p[b - 1], t1.p[b - 1]); }
-        ext_powers_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t0, n, d_zp);
-        ext_powers_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t1, n, d_zp + 2 * n);
-        eval_polys_kernel<<<tot0, 256, 0, st>>>(d_plist, d_zp, n, d_open);
-        eval_polys_kernel<<<tot1, 256, 0, st>>>(d_plist + tot0, d_zp + 2 * n, n, d_open + 2 * (size_t)tot0);
+        P2G_COUNT_LAUNCH(1); ext_powers_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t0, n, d_zp);
+        P2G_COUNT_LAUNCH(1); ext_powers_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t1, n, d_zp + 2 * n);
+        P2G_COUNT_LAUNCH(1); eval_polys_kernel<<<tot0, 256, 0, st>>>(d_plist, d_zp, n, d_open);
+        P2G_COUNT_LAUNCH(1); eval_polys_kernel<<<tot1, 256, 0, st>>>(d_plist + tot0, d_zp + 2 * n, n, d_open + 2 * (size_t)tot0);
         CU(cudaGetLastError());
     }
     std::vector<ext_t> open((size_t)tot0 + tot1);
@@ -418,8 +418,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = ctx_alloc(ctx, &d_comp, 4 * n))) return rc;
     if ((rc = ctx_alloc(ctx, &d_comp_lde, 4 * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_vals, 2 * N))) return rc;
-    fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist, tot0, fri_alpha, n, d_comp, d_comp + n);
-    fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist + tot0, tot1, fri_alpha, n, d_comp + 2 * n, d_comp + 3 * n);
+    P2G_COUNT_LAUNCH(1); fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist, tot0, fri_alpha, n, d_comp, d_comp + n);
+    P2G_COUNT_LAUNCH(1); fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist + tot0, tot1, fri_alpha, n, d_comp + 2 * n, d_comp + 3 * n);
     CU(cudaGetLastError());
     {
         const NttPlan* lde;
@@ -428,7 +428,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         ext_t comp0_at = ext_reduce_with_powers(open.data(), tot0, fri_alpha);
         ext_t comp1_at = ext_reduce_with_powers(open.data() + tot0, tot1, fri_alpha);
         ext_t shift0 = ext_pow(fri_alpha, (uint64_t)tot1);
-        fri_final_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_comp_lde, N, C->d_domain, zeta, zeta_next, comp0_at, comp1_at, shift0, d_vals);
+        P2G_COUNT_LAUNCH(1); fri_final_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_comp_lde, N, C->d_domain, zeta, zeta_next, comp0_at, comp1_at, shift0, d_vals);
         CU(cudaGetLastError());
     }
     tm.mark();
@@ -459,7 +459,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         gl_t* nxt;
         if ((rc = ctx_alloc(ctx, &nxt, (size_t)2 << log_leaves))) return rc;
         const size_t chunks = (size_t)1 << log_leaves;
-        fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, st>>>(cur_vals, cur_log, ab, gl_inv(shift), gl_inv(gl_root_of_unity(cur_log)),
+        P2G_COUNT_LAUNCH(1); fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, st>>>(cur_vals, cur_log, ab, gl_inv(shift), gl_inv(gl_root_of_unity(cur_log)),
                                                                            gl_inv(gl_root_of_unity(ab)), gl_inv((gl_t)1 << ab), beta, nxt);
         CU(cudaGetLastError());
         cur_vals = nxt; cur_log = (int)log_leaves;
@@ -504,7 +504,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         bool found = false;
         for (unsigned long long base = 0; !found && base < (1ull << 40); base += WIN) {
             CU(cudaMemsetAsync(d_best, 0xFF, 8, st));
-            pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, st>>>(ps, pos, d.pow_bits, base, d_best);
+            P2G_COUNT_LAUNCH(1); pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, st>>>(ps, pos, d.pow_bits, base, d_best);
             CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             unsigned long long best = *(unsigned long long*)ctx->pinned;
@@ -548,7 +548,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = ctx_alloc(ctx, &d_q, rec * nq))) return rc;
     CU(cudaMemcpyAsync(d_gt, gt.data(), gt.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_qidx, qidx.data(), nq * 8, cudaMemcpyHostToDevice, st));
-    query_gather_kernel<<<dim3(nq, (unsigned)gt.size()), 128, 0, st>>>(d_gt, (int)gt.size(), d_qidx, rec, d_q);
+    P2G_COUNT_LAUNCH(1); query_gather_kernel<<<dim3(nq, (unsigned)gt.size()), 128, 0, st>>>(d_gt, (int)gt.size(), d_qidx, rec, d_q);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(w, d_q, rec * nq * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -620,7 +620,7 @@ extern "C" int32_t p2g_pow_grind(p2g_ctx* ctx, const uint64_t state[12], uint32_
     const unsigned long long WIN = 1ull << 20;
     for (unsigned long long base = 0; base < (1ull << 44); base += WIN) {
         CU(cudaMemsetAsync(d_best, 0xFF, 8, ctx->st));
-        pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, ctx->st>>>(ps, (int)pos, (int)pow_bits, base, d_best);
+        P2G_COUNT_LAUNCH(1); pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, ctx->st>>>(ps, (int)pos, (int)pow_bits, base, d_best);
         CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
         unsigned long long best = *(unsigned long long*)ctx->pinned;
@@ -640,7 +640,7 @@ extern "C" int32_t p2g_fri_fold(p2g_ctx* ctx, const uint64_t* values_host, uint3
     if ((rc = ctx_alloc(ctx, &d_out, 2 * chunks))) return rc;
     CU(cudaMemcpyAsync(d_in, values_host, 2 * len * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
     ext_t b = ext_make(beta[0], beta[1]);
-    fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->st>>>(d_in, (int)log_len, (int)arity_bits, gl_inv(shift),
+    P2G_COUNT_LAUNCH(1); fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->st>>>(d_in, (int)log_len, (int)arity_bits, gl_inv(shift),
                                                                          gl_inv(gl_root_of_unity((int)log_len)), gl_inv(gl_root_of_unity((int)arity_bits)),
                                                                          gl_inv((gl_t)1 << arity_bits), b, d_out);
     CU(cudaGetLastError());

@@ -88,6 +88,8 @@ SIGNATURES = {
     "p2g_last_quotient_chunks": (C.c_int32, [_vp, _vp]),
     "p2g_last_timings": (C.c_int32, [_vp, C.POINTER(Timings)]),
     "p2g_set_timing": (C.c_int32, [_vp, C.c_int32]),
+    "p2g_last_commit_timings": (C.c_int32, [_vp, C.POINTER(C.c_float * 3)]),
+    "p2g_launch_count": (C.c_uint64, []),
     "p2g_pow_grind": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "p2g_fri_fold": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _vp]),
     "p2g_poseidon_peak": (C.c_int32, [_vp, C.c_uint32, C.POINTER(C.c_double)]),

@@ -25,6 +25,7 @@ class Oracle:
         self.lib = lib
         vp = C.c_void_p
         lib.orc_poseidon.argtypes = [vp]
+        lib.orc_poseidon_naive.argtypes = [vp]
         lib.orc_hash_n_to_m_no_pad.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
         lib.orc_two_to_one.argtypes = [vp, vp, vp]
         for f in (lib.orc_fft, lib.orc_ifft):
@@ -60,6 +61,11 @@ class Oracle:
     def poseidon(self, state):
         s = np.array(state, dtype=np.uint64)
         self.lib.orc_poseidon(s.ctypes.data)
+        return s
+
+    def poseidon_naive(self, state):
+        s = np.array(state, dtype=np.uint64)
+        self.lib.orc_poseidon_naive(s.ctypes.data)
         return s
 
     def hash_n_to_m_no_pad(self, inputs, m):

@@ -29,6 +29,11 @@ def test_poseidon_kat_upstream(oracle):
     for vec in kat["permutation"]:
         out = oracle.poseidon([int(x, 16) for x in vec["input"]])
         assert [hex(int(v)) for v in out] == vec["output"]
+        assert list(oracle.poseidon_naive([int(x, 16) for x in vec["input"]])) == list(out)
+    rng = np.random.default_rng(11)
+    for _ in range(50):
+        s = rng.integers(0, P, size=12, dtype=np.uint64)
+        assert list(oracle.poseidon(s)) == list(oracle.poseidon_naive(s))
 
 
 def test_hash_sponge_semantics(oracle):
