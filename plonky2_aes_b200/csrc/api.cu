@@ -210,10 +210,10 @@ __global__ void hash_no_pad_many_kernel(const gl_t* __restrict__ in, uint32_t co
     for (uint32_t c0 = 0; c0 < len; c0 += 8) {
 #pragma unroll
         for (int i = 0; i < 8; i++) if (c0 + i < len) s[i] = in[(size_t)j * len + c0 + i];
-        poseidon_permute(s);
+        poseidon_permute_lazy(s);
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) out[4 * (size_t)j + i] = s[i];
+    for (int i = 0; i < 4; i++) out[4 * (size_t)j + i] = gl_canon(s[i]);
 }
 extern "C" int32_t p2g_hash_no_pad_many(p2g_ctx* ctx, const uint64_t* in_host, uint32_t count, uint32_t len, uint64_t* out_host) {
     if (!ctx || !in_host || !out_host || !count) return P2G_E_BADARG;

@@ -32,7 +32,7 @@ __device__ __forceinline__ gl_t* level_ptr(gl_t* digests, gl_t* cap, uint32_t lo
 }
 
 template <bool COL_MAJOR>
-__global__ void __launch_bounds__(MERKLE_BLOCK)
+__global__ void __launch_bounds__(MERKLE_BLOCK, 4)
 merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t leaf_len, uint32_t log_leaves,
                      uint32_t L, uint32_t levels_here, gl_t* __restrict__ digests, gl_t* __restrict__ cap) {
     __shared__ gl_t sh[MERKLE_BLOCK][4];
@@ -55,8 +55,10 @@ merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t 
                     if (c < leaf_len)
                         s[i] = COL_MAJOR ? __ldg(data + (size_t)c * col_stride + j) : __ldg(data + j * leaf_len + c);
                 }
-                poseidon_permute(s);
+                poseidon_permute_lazy(s);
             }
+#pragma unroll
+            for (int i = 0; i < 4; i++) s[i] = gl_canon(s[i]);
         }
         gl_t* d0 = level_ptr(digests, cap, log_leaves, L, 0);
 #pragma unroll
@@ -106,7 +108,7 @@ merkle_top_kernel(gl_t* digests, gl_t* cap, uint32_t log_leaves, uint32_t L, uin
 }
 
 // one grid-wide level (used when the level is too wide for the single-block finisher)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 merkle_level_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, size_t cnt) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
@@ -149,13 +151,13 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
 }
 
 // ---- INT-pipe roofline microbenchmark: chained permutations, no memory traffic ------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 poseidon_bench_kernel(gl_t* out, uint32_t iters) {
     gl_t s[12];
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = (gl_t)g * 12 + i;
-    for (uint32_t k = 0; k < iters; k++) poseidon_permute(s);
+    for (uint32_t k = 0; k < iters; k++) poseidon_permute_lazy(s);
     gl_t acc = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) acc ^= s[i];

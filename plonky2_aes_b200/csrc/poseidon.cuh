@@ -4,91 +4,214 @@
 // /root/reference/aes-gcm/src/circuit_gcm.rs:781 `data.prove(pw)` and directly from
 // /root/reference/feistel/src/lib.rs:106 `hash_n_to_hash_no_pad`).
 //
-// One permutation per thread.  The MDS layer exploits the small circulant coefficients (<= 41):
-// state words are split in 32-bit halves, each half is accumulated with IMAD.WIDE into a 64-bit
-// sum (12 * 41 * 2^32 < 2^42, no overflow), and the two sums are recombined with one fold.
+// Device design (one permutation per thread, everything in registers):
+//  * the INT pipes are the roofline (profiles/r1_int_pipes_microbench.jsonl: IMAD.WIDE.U32 and
+//    IADD3 both issue every 2nd/1st cycle per SM sub-partition, 64-bit mul.hi is 13 cycles), so
+//    the field multiply is written on 32-bit halves: 4 IMAD.WIDE + a carry chain, then the
+//    Goldilocks fold  hi*2^64 = hi_lo*(2^32-1) - hi_hi  with ONE more IMAD.WIDE;
+//  * the MDS layer uses the small circulant coefficients (<= 41): 32-bit halves of the state
+//    are accumulated with IMAD.WIDE chains (12 * 41 * 2^32 < 2^42, no carries) and the NEXT
+//    round's constants are the initial value of those accumulators, so adding round constants
+//    costs nothing;
+//  * intermediate values are lazy residues (any u64); only outputs are canonicalised;
+//  * the 4+4 full rounds share one loop body and the 22 partial rounds another, keeping the hot
+//    code inside the 32 KB instruction cache.
 #pragma once
 #include "gl64.cuh"
 
-#if defined(__CUDACC__)
-__constant__ gl_t POSEIDON_RC_DEV[360] = {
-#include "poseidon_rc.inc"
-};
-#endif
 static const gl_t POSEIDON_RC_HOST[360] = {
 #include "poseidon_rc.inc"
 };
 
-#if defined(__CUDA_ARCH__)
-#define POSEIDON_RC POSEIDON_RC_DEV
-#else
-#define POSEIDON_RC POSEIDON_RC_HOST
+#if defined(__CUDACC__)
+__constant__ gl_t POSEIDON_RC_DEV[372] = {      // 30 rounds + one all-zero row ("next" of the last round)
+#include "poseidon_rc.inc"
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0
+};
+__constant__ uint32_t GL_EPS_DEV = 0xffffffffu;  // kept in constant memory so ptxas keeps h*EPS as one IMAD.WIDE
+// sparse form of the 22 partial rounds (tools/gen_poseidon_fast.py, verified against the naive rounds)
+#define PFAST_QUAL __constant__
+#include "poseidon_fast.inc"
+#undef PFAST_QUAL
 #endif
 
-GL_HD gl_t poseidon_sbox(gl_t x) {
-    gl_t x2 = gl_mul_lazy(x, x);
-    gl_t x4 = gl_mul_lazy(x2, x2);
-    gl_t x3 = gl_mul_lazy(x, x2);
-    return gl_mul_lazy(x3, x4);
-}
+#if defined(__CUDA_ARCH__)
+// ------------------------------------------------------------------------------------------
+// device implementation
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gl_unpack(gl_t x, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
+__device__ __forceinline__ gl_t gl_pack(uint32_t lo, uint32_t hi) { gl_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ gl_t gl_mulw(uint32_t a, uint32_t b) { gl_t r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
 
-// s: any u64 residues in, lazy residues out
-GL_HD void poseidon_mds(gl_t s[12]) {
+// (l1:l0) + h0*2^64 -> lazy residue:  one IMAD.WIDE, then +EPS if the 64-bit sum wrapped
+// (h0*EPS <= 2^64 - 2^33 + 1, so a wrap always lowers the high word: one 32-bit compare)
+__device__ __forceinline__ void gl_fold3w(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t& w0, uint32_t& w1) {
+    gl_t v;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(v) : "r"(h0), "r"(GL_EPS_DEV), "l"(gl_pack(l0, l1)));
+    uint32_t v0, v1; gl_unpack(v, v0, v1);
+    uint32_t c = v1 < l1 ? 0xffffffffu : 0u;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(w0), "=&r"(w1) : "r"(v0), "r"(c), "r"(v1));
+}
+__device__ __forceinline__ gl_t gl_fold3(uint32_t l0, uint32_t l1, uint32_t h0) {
+    uint32_t w0, w1; gl_fold3w(l0, l1, h0, w0, w1);
+    return gl_pack(w0, w1);
+}
+// (l1:l0) + h0*2^64 + (h2:h1)*2^96 -> lazy residue  (2^96 = -1: subtract (h2:h1), -EPS on borrow;
+// h2 is the small overflow word of multi-term accumulations, 2^128 = -2^32)
+__device__ __forceinline__ gl_t gl_fold5(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t h1, uint32_t h2) {
+    uint32_t w0, w1, m; gl_fold3w(l0, l1, h0, w0, w1);
+    asm("sub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;"
+        : "+r"(w0), "+r"(w1), "=&r"(m) : "r"(h1), "r"(h2));
+    return gl_pack(w0, w1);
+}
+__device__ __forceinline__ gl_t gl_fold4(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t h1) { return gl_fold5(l0, l1, h0, h1, 0); }
+// 128-bit product of two u64 as four 32-bit words
+__device__ __forceinline__ void pmul128(gl_t a, gl_t b, uint32_t& l0, uint32_t& l1, uint32_t& h0, uint32_t& h1) {
+    uint32_t a0, a1, b0, b1; gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
+    uint32_t c0, m1l, m1h, m2l, m2h, p11l, p11h;
+    gl_unpack(gl_mulw(a0, b0), l0, c0); gl_unpack(gl_mulw(a0, b1), m1l, m1h);
+    gl_unpack(gl_mulw(a1, b0), m2l, m2h); gl_unpack(gl_mulw(a1, b1), p11l, p11h);
+    asm("add.cc.u32 %0, %3, %4;\n\taddc.cc.u32 %1, %5, %6;\n\taddc.u32 %2, %7, 0;\n\t"
+        "add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %9;\n\taddc.u32 %2, %2, 0;"
+        : "=&r"(l1), "=&r"(h0), "=&r"(h1)
+        : "r"(c0), "r"(m1l), "r"(p11l), "r"(m1h), "r"(p11h), "r"(m2l), "r"(m2h));
+}
+// any u64 * any u64 -> lazy residue (about 21 SASS instructions, 5 of them IMAD.WIDE)
+__device__ __forceinline__ gl_t pmul(gl_t a, gl_t b) {
+    uint32_t l0, l1, h0, h1; pmul128(a, b, l0, l1, h0, h1);
+    return gl_fold4(l0, l1, h0, h1);
+}
+// a * b + c (all lazy) -> lazy residue; the sum still fits 128 bits
+__device__ __forceinline__ gl_t pmul_add(gl_t a, gl_t b, gl_t c) {
+    uint32_t l0, l1, h0, h1, c0, c1; pmul128(a, b, l0, l1, h0, h1); gl_unpack(c, c0, c1);
+    asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1) : "r"(c0), "r"(c1));
+    return gl_fold4(l0, l1, h0, h1);
+}
+// 160-bit accumulator for sums of up to 2^32 128-bit products
+struct Acc160 { uint32_t w[5]; };
+__device__ __forceinline__ void acc_mul(Acc160& A, gl_t a, gl_t b) {
+    uint32_t l0, l1, h0, h1; pmul128(a, b, l0, l1, h0, h1);
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, %4, 0;"
+        : "+r"(A.w[0]), "+r"(A.w[1]), "+r"(A.w[2]), "+r"(A.w[3]), "+r"(A.w[4]) : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
+}
+__device__ __forceinline__ gl_t acc_fold(const Acc160& A) { return gl_fold5(A.w[0], A.w[1], A.w[2], A.w[3], A.w[4]); }
+__device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
+    gl_t x2 = pmul(x, x), x4 = pmul(x2, x2), x3 = pmul(x, x2);
+    return pmul(x3, x4);
+}
+// s <- MDS * s + next   (next = 12 canonical constants; lazy in, lazy out)
+__device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], const gl_t* __restrict__ next) {
     const uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     uint32_t lo[12], hi[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) { lo[i] = (uint32_t)s[i]; hi[i] = (uint32_t)(s[i] >> 32); }
+    for (int i = 0; i < 12; i++) gl_unpack(s[i], lo[i], hi[i]);
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        uint64_t al = 0, ah = 0;
+        uint32_t nl, nh; gl_unpack(next[r], nl, nh);
+        uint64_t al = nl, ah = nh;
 #pragma unroll
         for (int i = 0; i < 12; i++) {
             al += (uint64_t)lo[(i + r) % 12] * C[i];
             ah += (uint64_t)hi[(i + r) % 12] * C[i];
         }
         if (r == 0) { al += (uint64_t)lo[0] * 8u; ah += (uint64_t)hi[0] * 8u; }
-        // value = al + ah * 2^32  (ah < 2^42)
-        uint64_t low = al + (ah << 32);
-        uint64_t carry = low < al ? 1 : 0;
-        uint64_t top = (ah >> 32) + carry;           // < 2^11, weight 2^64 = EPS
-        uint64_t t = top * GL_EPS;                   // < 2^43
-        uint64_t res = low + t;
-        if (res < t) res += GL_EPS;
-        s[r] = res;
+        // value = al + ah * 2^32 with al, ah < 2^43
+        uint32_t al0, al1, ah0, ah1; gl_unpack(al, al0, al1); gl_unpack(ah, ah0, ah1);
+        uint32_t m, t;
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
+        s[r] = gl_fold3(al0, m, t);
     }
 }
-
-GL_HD void poseidon_permute(gl_t s[12]) {
-    int r = 0;
-#pragma unroll 1
-    for (int k = 0; k < 4; k++, r++) {
+__device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonical
+    gl_t s = a + c;
+    return s < a ? s + GL_EPS : s;
+}
+// "next constants" of the 8 full rounds: RC[1..3], the first-partial-round constants of the
+// sparse form, RC[27..29], and zero after the last round
+__device__ __forceinline__ const gl_t* poseidon_next_row(int k) {
+    return k < 3 ? POSEIDON_RC_DEV + 12 * (k + 1) : k == 3 ? PFAST_FIRST_C : POSEIDON_RC_DEV + 12 * (k + 23);
+}
+// lazy in (any u64), lazy out
+__device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add_lazy(s[i], POSEIDON_RC[12 * r + i]));
-        poseidon_mds(s);
-    }
+    for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_dev(s[i], POSEIDON_RC_DEV[i]);
 #pragma unroll 1
-    for (int k = 0; k < 22; k++, r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_add_lazy(s[i], POSEIDON_RC[12 * r + i]);
-        s[0] = poseidon_sbox(s[0]);
-        poseidon_mds(s);
-    }
+    for (int phase = 0; phase < 2; phase++) {
 #pragma unroll 1
-    for (int k = 0; k < 4; k++, r++) {
+        for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add_lazy(s[i], POSEIDON_RC[12 * r + i]));
-        poseidon_mds(s);
+            for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(s[i]);
+            poseidon_mds_rc(s, poseidon_next_row(4 * phase + r));      // rows 0..3, then 7..10 -> RC[27..30]
+        }
+        if (phase == 0) {
+            // mds_partial_layer_init: s[1..] <- INIT * s[1..]  (one row per iteration)
+            gl_t t[11];
+#pragma unroll 1
+            for (int row = 0; row < 11; row++) {
+                Acc160 A = {{0, 0, 0, 0, 0}};
+#pragma unroll
+                for (int c = 0; c < 11; c++) acc_mul(A, PFAST_INIT[row * 11 + c], s[c + 1]);
+                t[row] = acc_fold(A);      // dynamic index: t lives in (L1-resident) local memory on purpose
+            }
+#pragma unroll
+            for (int q = 0; q < 11; q++) s[q + 1] = t[q];
+            // 22 sparse partial rounds
+#pragma unroll 1
+            for (int r = 0; r < 22; r++) {
+                gl_t tt = gl_add_lazy_dev(poseidon_sbox(s[0]), PFAST_K[r]);
+                Acc160 A = {{0, 0, 0, 0, 0}};
+                acc_mul(A, tt, 25);
+#pragma unroll
+                for (int j = 0; j < 11; j++) acc_mul(A, PFAST_VROW[r * 11 + j], s[j + 1]);
+#pragma unroll
+                for (int j = 0; j < 11; j++) s[j + 1] = pmul_add(PFAST_WCOL[r * 11 + j], tt, s[j + 1]);
+                s[0] = acc_fold(A);
+            }
+            // constants of the first of the last four full rounds
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_dev(s[i], POSEIDON_RC_DEV[12 * 26 + i]);
+        }
     }
+}
+__device__ __forceinline__ void poseidon_permute(gl_t s[12]) {
+    poseidon_permute_lazy(s);
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
 }
+#else
+// ------------------------------------------------------------------------------------------
+// host implementation (transcript only: a few hundred permutations per proof)
+// ------------------------------------------------------------------------------------------
+inline void poseidon_permute(gl_t s[12]) {
+    static const uint64_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    for (int r = 0; r < 30; r++) {
+        const bool full = r < 4 || r >= 26;
+        for (int i = 0; i < 12; i++) s[i] = gl_add(gl_canon(s[i]), POSEIDON_RC_HOST[12 * r + i]);
+        for (int i = 0; i < (full ? 12 : 1); i++) {
+            gl_t x = s[i], x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x, x2);
+            s[i] = gl_mul(x3, x4);
+        }
+        gl_t o[12];
+        for (int q = 0; q < 12; q++) {
+            unsigned __int128 acc = 0;
+            for (int i = 0; i < 12; i++) acc += (unsigned __int128)s[(i + q) % 12] * C[i];
+            if (q == 0) acc += (unsigned __int128)s[0] * 8;
+            o[q] = gl_canon(gl_reduce128_lazy((gl_t)acc, (gl_t)(acc >> 64)));
+        }
+        for (int i = 0; i < 12; i++) s[i] = o[i];
+    }
+}
+inline void poseidon_permute_lazy(gl_t s[12]) { poseidon_permute(s); }
+#endif
 
 // two_to_one(l, r): Poseidon([l, r, 0, 0, 0, 0])[0..4]
 GL_HD void poseidon_two_to_one(const gl_t l[4], const gl_t r[4], gl_t out[4]) {
     gl_t s[12];
 #pragma unroll
     for (int i = 0; i < 4; i++) { s[i] = l[i]; s[4 + i] = r[i]; s[8 + i] = 0; }
-    poseidon_permute(s);
+    poseidon_permute_lazy(s);
 #pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = s[i];
+    for (int i = 0; i < 4; i++) out[i] = gl_canon(s[i]);
 }

@@ -31,6 +31,10 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
             if (OP == 11) asm volatile("mad.wide.u32 %0, %1, %2, %0; add.u32 %1, %1, %3;" : "+l"(w[i]), "+r"(a[i]) : "r"(b[i]), "r"(seed)); // IMAD.WIDE + IADD3 mix (dual pipe)
             if (OP == 12) asm volatile("mad.lo.u32 %0, %0, %2, %3; add.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(seed)); // IMAD + IADD3 mix
             if (OP == 13) asm volatile("add.cc.u64 %0, %0, %1; " : "+l"(w[i]) : "l"((uint64_t)seed));                    // 64-bit add (2 SASS)
+            if (OP == 15) { double d = __longlong_as_double(w[(i + 4) % ILP]); asm volatile("mad.wide.u32 %0, %2, %3, %0; fma.rn.f64 %1, %1, %4, %4;" : "+l"(w[i]), "+d"(d) : "r"(a[i]), "r"(b[i]), "d"(1.0000001)); w[(i + 4) % ILP] = __double_as_longlong(d); }
+            if (OP == 16) { double d = __longlong_as_double(w[i]); asm volatile("fma.rn.f64 %0, %0, %2, %2; add.u32 %1, %1, %3;" : "+d"(d), "+r"(a[i]) : "d"(1.0000001), "r"(seed)); w[i] = __double_as_longlong(d); }
+            if (OP == 17) { double d = __longlong_as_double(w[(i + 4) % ILP]); asm volatile("mad.wide.u32 %0, %2, %3, %0; fma.rn.f64 %1, %1, %4, %4; add.u32 %2, %2, %5; add.u32 %3, %3, %5;" : "+l"(w[i]), "+d"(d), "+r"(a[i]), "+r"(b[i]) : "d"(1.0000001), "r"(seed)); w[(i + 4) % ILP] = __double_as_longlong(d); }
+            if (OP == 18) asm volatile("mad.wide.u32 %0, %1, 41, %0;" : "+l"(w[i]) : "r"(a[i]));
             if (OP == 14) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(seed + 1)); // mad.cc chain
         }
     }
@@ -67,6 +71,7 @@ int main() {
     run<6>("shf", 1, d, sms, 0); run<7>("isetp+sel", 2, d, sms, 0); run<8>("mul.lo.u64", 0, d, sms, 0);
     run<9>("mul.hi.u64", 0, d, sms, 0); run<10>("dfma", 1, d, sms, 0); run<11>("imad.wide+iadd3", 2, d, sms, 0);
     run<12>("imad.lo+iadd3", 2, d, sms, 0); run<13>("add.u64", 2, d, sms, 0); run<14>("mad.lo.cc+madc.hi", 2, d, sms, 0);
+    run<15>("imad.wide+dfma", 2, d, sms, 0); run<16>("dfma+iadd3", 2, d, sms, 0); run<17>("imad.wide+dfma+2iadd3", 4, d, sms, 0); run<18>("imad.wide.imm", 1, d, sms, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(e)); return 1; }
     return 0;
