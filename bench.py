@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="proofs in flight per GPU (one p2g context + host thread each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -136,7 +137,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = Context(local_rank)
     lib = ctx.lib
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    T = max(1, args.streams)
+    ctxs = [ctx] + [Context(local_rank) for _ in range(T - 1)]
+    streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local_rank)) for c in ctxs]
 
     # ---- workload: distinct witnesses per proof and per rank ----
     B = PROOFS_PER_STEP
@@ -149,32 +152,46 @@ def main():
     words = data.proof_words
     proofs = torch.empty((B, words), dtype=torch.int64).pin_memory()
     got = C.c_size_t()
+    handles = [data._gpu_circuit] + [data.load_handle(c) for c in ctxs[1:]]
+
+    def run_worker(t, fn, src):
+        g = C.c_size_t()
+        for i in range(t, B, T):      # proofs dealt round-robin to the in-flight contexts
+            ctxs[t].check(fn(ctxs[t].handle, handles[t], src[i].data_ptr(), None, proofs[i].data_ptr(), words, C.byref(g)))
+
+    def step(fn, src):
+        if T == 1:
+            return run_worker(0, fn, src)
+        ths = [threading.Thread(target=run_worker, args=(t, fn, src)) for t in range(T)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
 
     def step_device():
-        for i in range(B):
-            ctx.check(lib.p2g_prove_dev(ctx.handle, data._gpu_circuit, dev_wires[i].data_ptr(), None,
-                                        proofs[i].data_ptr(), words, C.byref(got)))
+        step(lib.p2g_prove_dev, dev_wires)
 
     def step_e2e():
-        for i in range(B):
-            ctx.check(lib.p2g_prove(ctx.handle, data._gpu_circuit, host_wires[i].data_ptr(), None,
-                                    proofs[i].data_ptr(), words, C.byref(got)))
+        step(lib.p2g_prove, host_wires)
 
     def barrier():
         torch.cuda.synchronize()
-        ctx.sync()
+        for c in ctxs:
+            c.sync()
         if world > 1:
             dist.barrier()
 
     def timed(fn, steps):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        e0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in streams]
+        e0.record(streams[0])
         for _ in range(steps):
             fn()
-        e1.record(stream)
+        for e, st_ in zip(ends, streams):
+            e.record(st_)
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e) for e in ends)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -260,6 +277,7 @@ def main():
                "dtype": "u64 (Goldilocks p=2^64-2^32+1, exact)", "data": "synthetic",
                "config": {"workload": WORKLOAD, "proofs_per_step_per_gpu": B, "aes_blocks_per_proof": L_BYTES // 16,
                           "aes_block_proofs_per_s": value * (L_BYTES // 16), "l2": "per-proof working set 1.0 GB > 126 MB L2",
+                          "proofs_in_flight_per_gpu": T,
                           "parallelism": f"independent proofs sharded over {world} GPU(s)"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * W * n * 8, "d2h_bytes_per_step": B * words * 8,
                        "ms_per_step": ms_e2e / args.steps},
@@ -269,7 +287,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    for c in ctxs:
+        c.close()
 
 
 if __name__ == "__main__":

@@ -29,10 +29,6 @@ __constant__ gl_t POSEIDON_RC_DEV[372] = {      // 30 rounds + one all-zero row 
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0
 };
 __constant__ uint32_t GL_EPS_DEV = 0xffffffffu;  // kept in constant memory so ptxas keeps h*EPS as one IMAD.WIDE
-// sparse form of the 22 partial rounds (tools/gen_poseidon_fast.py, verified against the naive rounds)
-#define PFAST_QUAL __constant__
-#include "poseidon_fast.inc"
-#undef PFAST_QUAL
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -128,50 +124,27 @@ __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonic
     gl_t s = a + c;
     return s < a ? s + GL_EPS : s;
 }
-// "next constants" of the 8 full rounds: RC[1..3], the first-partial-round constants of the
-// sparse form, RC[27..29], and zero after the last round
-__device__ __forceinline__ const gl_t* poseidon_next_row(int k) {
-    return k < 3 ? POSEIDON_RC_DEV + 12 * (k + 1) : k == 3 ? PFAST_FIRST_C : POSEIDON_RC_DEV + 12 * (k + 23);
-}
-// lazy in (any u64), lazy out
+// lazy in (any u64), lazy out.  Dense partial rounds: the sparse ("fast") form was measured at
+// the same throughput (profiles/r1_poseidon_kernel_ncu_summary.txt: 677 vs 673 M perm/s) and
+// costs an 11x11 initial matrix plus 5 KB of constants, so the simpler form is kept.
 __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_dev(s[i], POSEIDON_RC_DEV[i]);
+    int k = 0;
 #pragma unroll 1
     for (int phase = 0; phase < 2; phase++) {
 #pragma unroll 1
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < 4; r++, k++) {
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(s[i]);
-            poseidon_mds_rc(s, poseidon_next_row(4 * phase + r));      // rows 0..3, then 7..10 -> RC[27..30]
+            poseidon_mds_rc(s, POSEIDON_RC_DEV + 12 * (k + 1));
         }
         if (phase == 0) {
-            // mds_partial_layer_init: s[1..] <- INIT * s[1..]  (one row per iteration)
-            gl_t t[11];
 #pragma unroll 1
-            for (int row = 0; row < 11; row++) {
-                Acc160 A = {{0, 0, 0, 0, 0}};
-#pragma unroll
-                for (int c = 0; c < 11; c++) acc_mul(A, PFAST_INIT[row * 11 + c], s[c + 1]);
-                t[row] = acc_fold(A);      // dynamic index: t lives in (L1-resident) local memory on purpose
+            for (int r = 0; r < 22; r++, k++) {
+                s[0] = poseidon_sbox(s[0]);
+                poseidon_mds_rc(s, POSEIDON_RC_DEV + 12 * (k + 1));
             }
-#pragma unroll
-            for (int q = 0; q < 11; q++) s[q + 1] = t[q];
-            // 22 sparse partial rounds
-#pragma unroll 1
-            for (int r = 0; r < 22; r++) {
-                gl_t tt = gl_add_lazy_dev(poseidon_sbox(s[0]), PFAST_K[r]);
-                Acc160 A = {{0, 0, 0, 0, 0}};
-                acc_mul(A, tt, 25);
-#pragma unroll
-                for (int j = 0; j < 11; j++) acc_mul(A, PFAST_VROW[r * 11 + j], s[j + 1]);
-#pragma unroll
-                for (int j = 0; j < 11; j++) s[j + 1] = pmul_add(PFAST_WCOL[r * 11 + j], tt, s[j + 1]);
-                s[0] = acc_fold(A);
-            }
-            // constants of the first of the last four full rounds
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_dev(s[i], POSEIDON_RC_DEV[12 * 26 + i]);
         }
     }
 }

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <algorithm>
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------------------
 // host transcript: Challenger<F, PoseidonHash> (iop/challenger.rs)
@@ -51,6 +52,7 @@ struct p2g_circuit {
     gl_t* d_small;            // w8inv_pows[8], shift_n_inv_pows[8]
     p2g_gate* d_gates;
     uint8_t* d_row_kind;
+    uint16_t* d_lut_data; int* d_lut_off; int* d_lut_len;
     size_t proof_words;
     int final_len;
 };
@@ -168,6 +170,14 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
         CU(cudaMallocAsync((void**)&C->d_gates, sizeof(p2g_gate) * std::max(1, d.num_gates), ctx->st));
         CU(cudaMemcpyAsync(C->d_row_kind, kind.data(), n, cudaMemcpyHostToDevice, ctx->st));
         CU(cudaMemcpyAsync(C->d_gates, C->gates.data(), sizeof(p2g_gate) * d.num_gates, cudaMemcpyHostToDevice, ctx->st));
+        std::vector<int> off(8, 0), len(8, 0);
+        { int t = 0; for (int l = 0; l < d.num_luts; l++) { off[l] = t; len[l] = d.lut_lens[l]; t += d.lut_lens[l]; } }
+        CU(cudaMallocAsync((void**)&C->d_lut_data, std::max<size_t>(4, 4 * lut_total), ctx->st));
+        CU(cudaMallocAsync((void**)&C->d_lut_off, 8 * sizeof(int), ctx->st));
+        CU(cudaMallocAsync((void**)&C->d_lut_len, 8 * sizeof(int), ctx->st));
+        CU(cudaMemcpyAsync(C->d_lut_data, C->lut_data.data(), 4 * lut_total, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(C->d_lut_off, off.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(C->d_lut_len, len.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
     }
     size_t fin = n; for (int l = 0; l < d.num_reduction_arity_bits; l++) fin >>= d.reduction_arity_bits[l];
@@ -180,6 +190,7 @@ extern "C" int32_t p2g_circuit_free(p2g_ctx* ctx, p2g_circuit* C) {
     p2g_batch_free(ctx, C->cs);
     ctx_free(ctx, C->d_sigmas); ctx_free(ctx, C->d_subgroup); ctx_free(ctx, C->d_domain); ctx_free(ctx, C->d_qtable);
     ctx_free(ctx, C->d_small); ctx_free(ctx, C->d_row_kind); ctx_free(ctx, C->d_gates);
+    ctx_free(ctx, C->d_lut_data); ctx_free(ctx, C->d_lut_off); ctx_free(ctx, C->d_lut_len);
     delete C;
     return P2G_OK;
 }
@@ -233,6 +244,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     cudaStream_t st = ctx->st;
     int rc;
     StageTimer tm(ctx);
+    const bool dbg = getenv("P2G_DEBUG") != nullptr;
+#define DBG(msg) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[p2g] %s (%s)\n", msg, cudaGetErrorString(e_)); } } while (0)
 
     gl_t pi_hash[4];
     host_hash_no_pad(public_inputs, (size_t)d.num_public_inputs, pi_hash);
@@ -250,6 +263,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = commit_dev(ctx, wires, W, logn, cd.rate_bits, d.cap_height, true, &wb, true))) return rc;
     tm.mark();
 
+    DBG("wires committed");
     Challenger ch;
     ch.observe_many(d.circuit_digest, 4);
     ch.observe_many(pi_hash, 4);
@@ -276,27 +290,15 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         gl_t sn = gl_pow(7, n), w8 = gl_root_of_unity(cd.rate_bits), t = 1;
         for (int s = 0; s < (1 << cd.rate_bits); s++) { pc_host->zh[s] = gl_sub(gl_mul(sn, t), 1); pc_host->zh_inv[s] = gl_inv(pc_host->zh[s]); t = gl_mul(t, w8); }
     }
-    if (has_lookup) {
-        for (int i = 0; i < nch; i++) {
-            gl_t b = pc_host->deltas[i][1], delta = pc_host->deltas[i][3];
-            pc_host->delta_pow_slots[i] = gl_pow(delta, cd.lut_slots);
-            const uint16_t* data = C->lut_data.data();
-            for (int r = 0; r < cd.num_luts; r++) {
-                int len = C->lut_lens[r];
-                int rows = (len + cd.lut_slots - 1) / cd.lut_slots, degree = rows * cd.lut_slots;
-                gl_t acc = 0;
-                for (int e = 0; e < degree; e++) {
-                    gl_t combo = e < len ? gl_add(data[2 * e], gl_mul(b, data[2 * e + 1])) : 0;
-                    acc = gl_add(gl_mul(acc, delta), combo);
-                }
-                pc_host->lut_evals[i][r] = acc;
-                data += 2 * len;
-            }
-        }
-    }
+    if (has_lookup) for (int i = 0; i < nch; i++) pc_host->delta_pow_slots[i] = gl_pow(pc_host->deltas[i][3], cd.lut_slots);
     ProofConsts* d_pc;
     CU(cudaMallocAsync((void**)&d_pc, sizeof(ProofConsts), st));
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
+    gl_t* d_lut_evals;
+    if ((rc = ctx_alloc(ctx, &d_lut_evals, MAX_CH * 8))) return rc;
+    if (has_lookup) {
+        P2G_COUNT_LAUNCH(1); lut_eval_kernel<<<dim3(cd.num_luts, nch), 256, 0, st>>>(cd, d_pc, C->d_lut_data, C->d_lut_off, C->d_lut_len, d_lut_evals);
+    }
 
     // ---- Z, partial products, lookup polys ----
     gl_t* d_zs;
@@ -311,6 +313,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         }
         CU(cudaGetLastError());
     }
+    DBG("zs built");
     if (ctx->keep_debug) {
         ctx->last_zs.resize((size_t)zs_cols * n);
         CU(cudaMemcpyAsync(ctx->last_zs.data(), d_zs, ctx->last_zs.size() * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
@@ -328,12 +331,13 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
 
+    DBG("zs committed");
     // ---- quotient ----
     gl_t *d_qv, *d_qa, *d_qc;
     if ((rc = ctx_alloc(ctx, &d_qv, (size_t)nch * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_qa, (size_t)nch * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_qc, (size_t)nch * N))) return rc;
-    P2G_COUNT_LAUNCH(1); quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
+    P2G_COUNT_LAUNCH(1); quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
     CU(cudaGetLastError());
     {
         const NttPlan* inv;
@@ -343,6 +347,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         P2G_COUNT_LAUNCH(1); quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, d_qa, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
         CU(cudaGetLastError());
     }
+    DBG("quotient evaluated");
     if (ctx->keep_debug) {
         ctx->last_quotient_chunks.resize((size_t)nch * N);
         CU(cudaMemcpyAsync(ctx->last_quotient_chunks.data(), d_qc, (size_t)nch * N * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
@@ -356,6 +361,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     const gl_t g = gl_root_of_unity(logn);
     const ext_t zeta_next = ext_mul_base(zeta, g);
 
+    DBG("quotient committed");
     // ---- openings ----
     const p2g_batch* oracles[4] = {C->cs, wb, zb, qb};
     const int tot0 = NC + R + W + zpp + nch * qdf + nlz, tot1 = nch + nlz;
@@ -412,6 +418,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         put(o1 + nch, nlz);                      // lookup_zs_next
     }
 
+    DBG("openings done");
     // ---- prove_openings: batch combination ----
     const ext_t fri_alpha = ch.get_ext();
     gl_t *d_comp, *d_comp_lde, *d_vals;
@@ -433,6 +440,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     tm.mark();
 
+    DBG("fri combined");
     // ---- fri_committed_trees ----
     const int nl = d.num_reduction_arity_bits;
     struct Layer { gl_t* vals; gl_t* digests; gl_t* cap; int log_len, arity_bits; };
@@ -492,6 +500,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     ch.observe_many((const gl_t*)fcoef.data(), 2 * final_len);
     tm.mark();
 
+    DBG("fri committed");
     // ---- fri_proof_of_work: lowest nonce ----
     gl_t pow_witness = 0;
     {
@@ -500,11 +509,12 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         for (int i = 0; i < pos; i++) ps.s[i] = ch.in_buf[i];
         unsigned long long* d_best;
         CU(cudaMallocAsync((void**)&d_best, 8, st));
-        const unsigned long long WIN = 1ull << 20;
+        const unsigned long long WIN = 1ull << 18;   // expected hit within 2^16 candidates; P(miss) = e^-4
         bool found = false;
-        for (unsigned long long base = 0; !found && base < (1ull << 40); base += WIN) {
+        for (unsigned long long base = 0; !found && base < (1ull << 30); base += WIN) {
             CU(cudaMemsetAsync(d_best, 0xFF, 8, st));
             P2G_COUNT_LAUNCH(1); pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, st>>>(ps, pos, d.pow_bits, base, d_best);
+            CU(cudaGetLastError());
             CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             unsigned long long best = *(unsigned long long*)ctx->pinned;
@@ -518,6 +528,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     tm.mark();
 
+    DBG("pow done");
     // ---- query rounds ----
     const int nq = d.num_query_rounds;
     std::vector<unsigned long long> qidx(nq);
@@ -573,6 +584,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     for (int l = 0; l < nl; l++) { ctx_free(ctx, layers[l].digests); ctx_free(ctx, layers[l].cap); if (l > 0) ctx_free(ctx, layers[l].vals); }
     if (nl > 0) ctx_free(ctx, cur_vals);
     ctx_free(ctx, d_vals); ctx_free(ctx, d_comp); ctx_free(ctx, d_comp_lde); ctx_free(ctx, d_zp); ctx_free(ctx, d_open);
+    ctx_free(ctx, d_lut_evals);
     cudaFreeAsync((void*)d_plist, st); cudaFreeAsync(d_gt, st); cudaFreeAsync(d_qidx, st); ctx_free(ctx, d_q); cudaFreeAsync(d_pc, st);
     p2g_batch_free(ctx, wb); p2g_batch_free(ctx, zb); p2g_batch_free(ctx, qb);
     if (d_wires) ctx_free(ctx, d_wires);

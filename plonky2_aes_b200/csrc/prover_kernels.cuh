@@ -62,7 +62,6 @@ struct ProofConsts {
     gl_t deltas[MAX_CH][4];                 // (a, b, alpha, delta) per challenge
     gl_t beta_kis[MAX_CH][MAX_ROUTED];      // beta_c * k_j
     gl_t k_is[MAX_ROUTED];
-    gl_t lut_evals[MAX_CH][8];
     gl_t pi_hash[4];
     gl_t alpha_pows[MAX_CH][160];           // alpha_c^k for the reduce_with_powers of the vanishing terms
     gl_t zh[16], zh_inv[16];                // Z_H on coset s (natural coset index), and inverse
@@ -258,8 +257,35 @@ __device__ __forceinline__ gl_t gate_filter(int row, int gs, int ge, gl_t s, boo
     return f;
 }
 
+// get_lut_poly(lut, deltas).eval(delta) (plonk/vanishing_poly.rs): sum_e (in_e + b*out_e) * delta^(degree-1-e)
+// with the table zero-padded to `degree` = rows * slots entries.  One block per (lut, challenge).
+__global__ void __launch_bounds__(256)
+lut_eval_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const uint16_t* __restrict__ lut_data,
+                const int* __restrict__ lut_off, const int* __restrict__ lut_len, gl_t* __restrict__ out /*[nch][8]*/) {
+    __shared__ gl_t sm[256];
+    const int lut = blockIdx.x, ch = blockIdx.y;
+    const int len = lut_len[lut];
+    const int degree = ((len + cd.lut_slots - 1) / cd.lut_slots) * cd.lut_slots;
+    const gl_t b = pc->deltas[ch][1], delta = pc->deltas[ch][3];
+    const uint16_t* data = lut_data + 2 * (size_t)lut_off[lut];
+    const int chunk = (degree + blockDim.x - 1) / blockDim.x;
+    const int e0 = min(degree, (int)threadIdx.x * chunk), e1 = min(degree, e0 + chunk);
+    gl_t acc = 0;
+    for (int e = e0; e < e1; e++) {
+        gl_t combo = e < len ? gl_add((gl_t)data[2 * e], gl_mul(b, (gl_t)data[2 * e + 1])) : 0;
+        acc = gl_add(gl_mul(acc, delta), combo);
+    }
+    sm[threadIdx.x] = gl_mul(acc, gl_pow(delta, (uint64_t)(degree - e1)));
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) sm[threadIdx.x] = gl_add(sm[threadIdx.x], sm[threadIdx.x + d]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[ch * 8 + lut] = sm[0];
+}
+
 __global__ void __launch_bounds__(128)
-quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const p2g_gate* __restrict__ gates,
+quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ lut_evals, const p2g_gate* __restrict__ gates,
                 const gl_t* __restrict__ cs, const gl_t* __restrict__ wl, const gl_t* __restrict__ zl,
                 const gl_t* __restrict__ domain, gl_t* __restrict__ out) {
     const int logn = cd.logn, logN = logn + cd.rate_bits;
@@ -326,7 +352,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const p2g_gat
             ADD_TERM(tb + 1, gl_mul(s_init, lz[(size_t)1 * N + j]));
             ADD_TERM(tb + 2, gl_mul(s_init, z_re));
             for (int r = 0; r < cd.num_luts; r++)
-                ADD_TERM(tb + 3 + r, gl_mul(lsel[(size_t)(4 + r) * N + j], gl_sub(z_re, pc->lut_evals[c][r])));
+                ADD_TERM(tb + 3 + r, gl_mul(lsel[(size_t)(4 + r) * N + j], gl_sub(z_re, lut_evals[c * 8 + r])));
             gl_t re_cur = next_z_re;
             const int tt = tb + 4 + cd.num_luts;   // index of the first per-poly term (after RE transition at tt-1)
             for (int poly = 0; poly < cd.num_sldc; poly++) {
@@ -540,9 +566,10 @@ pow_grind_kernel(PowState st, int pos, int pow_bits, unsigned long long base, un
     const unsigned long long cand = base + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     gl_t s[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = st.s[i];
-#pragma unroll
-    for (int i = 0; i < 12; i++) if (i == pos) s[i] = cand;
+    for (int i = 0; i < 12; i++) {          // select, not an indexed store: the state stays in registers
+        const gl_t m = (gl_t)0 - (gl_t)(i == pos);
+        s[i] = (st.s[i] & ~m) | (cand & m);
+    }
     poseidon_permute(s);
     if ((s[7] >> (64 - pow_bits)) == 0) atomicMin(best, cand);
 }

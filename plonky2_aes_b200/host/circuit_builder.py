@@ -475,13 +475,18 @@ class CircuitData:
         dom = ctx.hash_no_pad_many(pad)[0]
         parts = np.concatenate([self.constants_sigmas_cap.ravel(), dom, np.array([self.degree_bits], dtype=np.uint64)])
         self.circuit_digest = ctx.hash_no_pad_many(parts[None, :])[0].copy()
+        self._gpu_circuit = self.load_handle(ctx)
+        return self
+
+    def load_handle(self, ctx):
+        """p2g_circuit_load on another context (a second stream of the same GPU, or another GPU);
+        the digest computed by load() is reused."""
         h = C.c_void_p()
         desc = self.descriptor()
-        cap = np.empty_like(self.constants_sigmas_cap)
-        ctx.check(lib.p2g_circuit_load(ctx.handle, C.byref(desc), C.byref(h), cap.ctypes.data))
+        cap = np.empty((1 << self.config.fri_config.cap_height, 4), dtype=np.uint64)
+        ctx.check(ctx.lib.p2g_circuit_load(ctx.handle, C.byref(desc), C.byref(h), cap.ctypes.data))
         assert np.array_equal(cap, self.constants_sigmas_cap)
-        self._gpu_circuit = h
-        return self
+        return h
 
     @property
     def proof_words(self):
