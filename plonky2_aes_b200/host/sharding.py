@@ -1,0 +1,88 @@
+"""Multi-GPU work split for batches of independent proofs (BASELINE config 5).
+
+The path shards by proof: rank r proves proofs r, r + world, r + 2*world, ... of the batch with
+its own GPU context(s); there is no data-path collective.  The only communication is the
+gather of results (proof words or their digests) to rank 0 and the max-over-ranks timing, both
+through torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+import threading
+
+import numpy as np
+
+
+def shard_indices(total, rank, world):
+    """proof indices owned by `rank` (round-robin so every rank gets the same count +-1)"""
+    return list(range(rank, total, world))
+
+
+def proof_checksum(proof_words):
+    """order-independent 64-bit fingerprint used to cross-check gathered proofs"""
+    a = np.ascontiguousarray(proof_words, dtype=np.uint64)
+    w = np.arange(1, a.size + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        return int(np.bitwise_xor.reduce(a * w))
+
+
+def gather_to_rank0(local, dist, rank, world):
+    """gather a list of (index, uint64 array) pairs on rank 0 -> dict index -> array"""
+    import torch
+    if world == 1:
+        return dict(local)
+    n_local = len(local)
+    width = max((len(p) for _, p in local), default=0)
+    meta = torch.tensor([n_local, width], dtype=torch.int64)
+    metas = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    n_max = max(int(m[0]) for m in metas)
+    w_max = max(int(m[1]) for m in metas)
+    buf = torch.zeros((n_max, w_max + 2), dtype=torch.int64)
+    for k, (idx, p) in enumerate(local):
+        buf[k, 0], buf[k, 1] = idx, len(p)
+        buf[k, 2:2 + len(p)] = torch.from_numpy(np.ascontiguousarray(p, dtype=np.uint64).view(np.int64))
+    bufs = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, bufs, dst=0)
+    if rank != 0:
+        return None
+    out = {}
+    for r in range(world):
+        for k in range(int(metas[r][0])):
+            idx, ln = int(bufs[r][k, 0]), int(bufs[r][k, 1])
+            out[idx] = bufs[r][k, 2:2 + ln].numpy().view(np.uint64).copy()
+    return out
+
+
+class BatchProver:
+    """Proves many witnesses of one circuit with several proofs in flight on one GPU: one p2g
+    context (stream + host thread) per in-flight proof, so the latency-bound tails of one proof
+    (tree tops, Fiat-Shamir round trips) overlap the heavy kernels of another."""
+
+    def __init__(self, data, ctxs):
+        self.data, self.ctxs = data, ctxs
+        self.handles = [data._gpu_circuit if c is data.ctx else data.load_handle(c) for c in ctxs]
+
+    def prove_many(self, wires_list, device_resident=False):
+        import ctypes as C
+        lib = self.ctxs[0].lib
+        words = self.data.proof_words
+        out = [None] * len(wires_list)
+        fn = lib.p2g_prove_dev if device_resident else lib.p2g_prove
+        errors = []
+
+        def worker(t):
+            got = C.c_size_t()
+            try:
+                for i in range(t, len(wires_list), len(self.ctxs)):
+                    w = wires_list[i]
+                    ptr = w.data_ptr() if hasattr(w, "data_ptr") else np.ascontiguousarray(w, dtype=np.uint64).ctypes.data
+                    buf = np.empty(words, dtype=np.uint64)
+                    self.ctxs[t].check(fn(self.ctxs[t].handle, self.handles[t], ptr, None, buf.ctypes.data, words, C.byref(got)))
+                    out[i] = buf[:got.value]
+            except Exception as e:       # surfaced to the caller below
+                errors.append(e)
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(len(self.ctxs))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        if errors:
+            raise errors[0]
+        return out
