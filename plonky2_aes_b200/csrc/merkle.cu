@@ -8,7 +8,11 @@
 // that are finished by a single block.
 #include "common.h"
 #include "poseidon.cuh"
+#include <stdlib.h>
 
+#ifndef POS_MINB
+#define POS_MINB 3
+#endif
 #define MERKLE_BLOCK 256
 #define MERKLE_BLOCK_LOG 8
 
@@ -32,7 +36,7 @@ __device__ __forceinline__ gl_t* level_ptr(gl_t* digests, gl_t* cap, uint32_t lo
 }
 
 template <bool COL_MAJOR>
-__global__ void __launch_bounds__(MERKLE_BLOCK, 4)
+__global__ void __launch_bounds__(MERKLE_BLOCK, POS_MINB)
 merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t leaf_len, uint32_t log_leaves,
                      uint32_t L, uint32_t levels_here, gl_t* __restrict__ digests, gl_t* __restrict__ cap) {
     __shared__ gl_t sh[MERKLE_BLOCK][4];
@@ -108,7 +112,7 @@ merkle_top_kernel(gl_t* digests, gl_t* cap, uint32_t log_leaves, uint32_t L, uin
 }
 
 // one grid-wide level (used when the level is too wide for the single-block finisher)
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, POS_MINB)
 merkle_level_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, size_t cnt) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
@@ -130,6 +134,12 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
     uint32_t block_log = 0; while ((1u << block_log) < threads) block_log++;
     uint32_t real_log = log_leaves < block_log ? log_leaves : block_log;
     uint32_t levels_here = real_log < L ? real_log : L;
+    {   // levels folded inside the leaf kernel: past 3 levels most of a block idles while it still
+        // pins its registers, so the rest of the tree is finished by the per-level / top kernels
+        static int cap_levels = -1;
+        if (cap_levels < 0) { const char* e = getenv("P2G_MERKLE_BLOCK_LEVELS"); cap_levels = e ? atoi(e) : 3; }
+        if ((int)levels_here > cap_levels) levels_here = (uint32_t)cap_levels;
+    }
     uint32_t blocks = (uint32_t)((num_leaves + threads - 1) / threads);
     if (col_major)
         merkle_leaves_kernel<true><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
@@ -151,7 +161,7 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
 }
 
 // ---- INT-pipe roofline microbenchmark: chained permutations, no memory traffic ------------
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, POS_MINB)
 poseidon_bench_kernel(gl_t* out, uint32_t iters) {
     gl_t s[12];
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;

@@ -29,6 +29,7 @@ __constant__ gl_t POSEIDON_RC_DEV[372] = {      // 30 rounds + one all-zero row 
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0
 };
 __constant__ uint32_t GL_EPS_DEV = 0xffffffffu;  // kept in constant memory so ptxas keeps h*EPS as one IMAD.WIDE
+#include "poseidon_rc_f64.inc"
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -97,27 +98,50 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
     gl_t x2 = pmul(x, x), x4 = pmul(x2, x2), x3 = pmul(x, x2);
     return pmul(x3, x4);
 }
-// s <- MDS * s + next   (next = 12 canonical constants; lazy in, lazy out)
-__device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], const gl_t* __restrict__ next) {
-    const uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    uint32_t lo[12], hi[12];
+// s <- MDS * s + RC[next_row]   (lazy in, lazy out) on the FP64 pipe.
+// The circulant coefficients are <= 41, so every partial sum of  c_i * (32-bit half)  plus a 32-bit
+// constant stays below 2^43: DFMA on integer-valued doubles is exact, and the FP64 pipe (16
+// lanes/clk/SMSP on B200, idle otherwise) co-issues with the IADD3 carry chains of the S-boxes,
+// which IMAD.WIDE does not (profiles/r1_int_pipes_microbench.jsonl: dfma+iadd3 2.08 cyc/pair,
+// imad.wide+iadd3 5.3).  Accumulators start at 2^52 + round constant, so the integer result can
+// be read straight out of the mantissa with no conversion instruction.
+__device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    const double MAGIC = 4503599627370496.0;   // 2^52
+    uint32_t al0[12], al1[12];
+    {
+        double acc[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) gl_unpack(s[i], lo[i], hi[i]);
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        uint32_t nl, nh; gl_unpack(next[r], nl, nh);
-        uint64_t al = nl, ah = nh;
+        for (int r = 0; r < 12; r++) acc[r] = POSEIDON_RCD_LO[12 * next_row + r];
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            al += (uint64_t)lo[(i + r) % 12] * C[i];
-            ah += (uint64_t)hi[(i + r) % 12] * C[i];
+            const double x = __hiloint2double(0x43300000, (int)(uint32_t)s[i]) - MAGIC;
+#pragma unroll
+            for (int r = 0; r < 12; r++) acc[r] = __fma_rn(x, C[(i - r + 12) % 12], acc[r]);
+            if (i == 0) acc[0] = __fma_rn(x, 8., acc[0]);
         }
-        if (r == 0) { al += (uint64_t)lo[0] * 8u; ah += (uint64_t)hi[0] * 8u; }
-        // value = al + ah * 2^32 with al, ah < 2^43
-        uint32_t al0, al1, ah0, ah1; gl_unpack(al, al0, al1); gl_unpack(ah, ah0, ah1);
-        uint32_t m, t;
-        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
-        s[r] = gl_fold3(al0, m, t);
+#pragma unroll
+        for (int r = 0; r < 12; r++) { al0[r] = (uint32_t)__double2loint(acc[r]); al1[r] = (uint32_t)__double2hiint(acc[r]) & 0xFFFFFu; }
+    }
+    {
+        double acc[12];
+#pragma unroll
+        for (int r = 0; r < 12; r++) acc[r] = POSEIDON_RCD_HI[12 * next_row + r];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            const double x = __hiloint2double(0x43300000, (int)(uint32_t)(s[i] >> 32)) - MAGIC;
+#pragma unroll
+            for (int r = 0; r < 12; r++) acc[r] = __fma_rn(x, C[(i - r + 12) % 12], acc[r]);
+            if (i == 0) acc[0] = __fma_rn(x, 8., acc[0]);
+        }
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            // value = al + ah * 2^32 with al, ah < 2^43
+            const uint32_t ah0 = (uint32_t)__double2loint(acc[r]), ah1 = (uint32_t)__double2hiint(acc[r]) & 0xFFFFFu;
+            uint32_t m, t;
+            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1[r]), "r"(ah0), "r"(ah1));
+            s[r] = gl_fold3(al0[r], m, t);
+        }
     }
 }
 __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonical
@@ -137,13 +161,13 @@ __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
         for (int r = 0; r < 4; r++, k++) {
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(s[i]);
-            poseidon_mds_rc(s, POSEIDON_RC_DEV + 12 * (k + 1));
+            poseidon_mds_rc(s, k + 1);
         }
         if (phase == 0) {
 #pragma unroll 1
             for (int r = 0; r < 22; r++, k++) {
                 s[0] = poseidon_sbox(s[0]);
-                poseidon_mds_rc(s, POSEIDON_RC_DEV + 12 * (k + 1));
+                poseidon_mds_rc(s, k + 1);
             }
         }
     }

@@ -16,7 +16,8 @@ class P2GError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(_HERE), "libp2gpu.so")
+    # P2G_LIB_PATH: developer override used to A/B kernel variants; the default is the in-tree build
+    return os.environ.get("P2G_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libp2gpu.so")
 
 
 class Gate(C.Structure):
