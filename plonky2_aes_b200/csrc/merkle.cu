@@ -43,51 +43,69 @@ merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t 
     const uint32_t tid = threadIdx.x;
     const size_t j = (size_t)blockIdx.x * blockDim.x + tid;
     const size_t num_leaves = (size_t)1 << log_leaves;
+    const bool leaf_ok = j < num_leaves;
     gl_t s[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = 0;
-    if (j < num_leaves) {
-        if (leaf_len <= 4) {                       // hash_or_noop
+    // One loop drives both phases so the permutation is inlined exactly once (the kernel was
+    // instruction-fetch bound with two copies): iterations [0, absorbs) are the leaf sponge,
+    // iterations [absorbs, absorbs + levels_here) fold tree levels through shared memory.
+    const uint32_t absorbs = leaf_len <= 4 ? 0 : (leaf_len + 7) / 8;
+    if (leaf_len <= 4 && leaf_ok) {                // hash_or_noop: the leaf is its own digest
 #pragma unroll
-            for (uint32_t c = 0; c < 4; c++)
-                if (c < leaf_len) s[c] = COL_MAJOR ? __ldg(data + (size_t)c * col_stride + j) : __ldg(data + j * leaf_len + c);
-        } else {
-            for (uint32_t c0 = 0; c0 < leaf_len; c0 += 8) {
+        for (uint32_t c = 0; c < 4; c++)
+            if (c < leaf_len) s[c] = COL_MAJOR ? __ldg(data + (size_t)c * col_stride + j) : __ldg(data + j * leaf_len + c);
+    }
+    if (absorbs == 0) {
+        if (leaf_ok) {
+            gl_t* d0 = level_ptr(digests, cap, log_leaves, L, 0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) d0[4 * j + i] = s[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) sh[tid][i] = s[i];
+    }
+    for (uint32_t it = 0; it < absorbs + levels_here; it++) {
+        bool active;
+        uint32_t lv = 0;
+        if (it < absorbs) {
+            active = leaf_ok;
+            if (active) {
+                const uint32_t c0 = it * 8;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     uint32_t c = c0 + i;
                     if (c < leaf_len)
                         s[i] = COL_MAJOR ? __ldg(data + (size_t)c * col_stride + j) : __ldg(data + j * leaf_len + c);
                 }
-                poseidon_permute_lazy(s);
             }
+        } else {
+            lv = it - absorbs + 1;
+            __syncthreads();
+            active = tid < (blockDim.x >> lv);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) { s[i] = sh[2 * tid][i]; s[4 + i] = sh[2 * tid + 1][i]; s[8 + i] = 0; }
+            }
+            __syncthreads();
+        }
+        if (active) poseidon_permute_lazy(s);
+        if (it + 1 == absorbs) {                   // leaf digest complete
 #pragma unroll
             for (int i = 0; i < 4; i++) s[i] = gl_canon(s[i]);
-        }
-        gl_t* d0 = level_ptr(digests, cap, log_leaves, L, 0);
+            if (leaf_ok) {
+                gl_t* d0 = level_ptr(digests, cap, log_leaves, L, 0);
 #pragma unroll
-        for (int i = 0; i < 4; i++) d0[4 * j + i] = s[i];
-    }
+                for (int i = 0; i < 4; i++) d0[4 * j + i] = s[i];
+            }
 #pragma unroll
-    for (int i = 0; i < 4; i++) sh[tid][i] = s[i];
-    __syncthreads();
-    // fold levels inside the block
-    for (uint32_t lv = 1; lv <= levels_here; lv++) {
-        uint32_t active = blockDim.x >> lv;
-        gl_t l[4], r[4], o[4];
-        if (tid < active) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) { l[i] = sh[2 * tid][i]; r[i] = sh[2 * tid + 1][i]; }
-            poseidon_two_to_one(l, r, o);
-        }
-        __syncthreads();
-        if (tid < active) {
+            for (int i = 0; i < 4; i++) sh[tid][i] = s[i];
+        } else if (it >= absorbs && active) {
             size_t node = ((size_t)blockIdx.x * blockDim.x >> lv) + tid;
             gl_t* d = level_ptr(digests, cap, log_leaves, L, lv);
 #pragma unroll
-            for (int i = 0; i < 4; i++) { sh[tid][i] = o[i]; d[4 * node + i] = o[i]; }
+            for (int i = 0; i < 4; i++) { gl_t v = gl_canon(s[i]); sh[tid][i] = v; d[4 * node + i] = v; }
         }
-        __syncthreads();
     }
 }
 
