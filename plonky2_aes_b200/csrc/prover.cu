@@ -301,12 +301,14 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
 
     // ---- Z, partial products, lookup polys ----
-    gl_t* d_zs;
+    gl_t *d_zs, *d_rowprod;
     if ((rc = ctx_alloc(ctx, &d_zs, (size_t)zs_cols * n))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_rowprod, (size_t)nch * n))) return rc;
     {
         dim3 grid((unsigned)((n + 127) / 128), nch);
-        P2G_COUNT_LAUNCH(1); zs_chunk_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_sigmas, C->d_subgroup, d_zs);
-        P2G_COUNT_LAUNCH(1); zs_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_zs);
+        P2G_COUNT_LAUNCH(1); zs_chunk_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_sigmas, C->d_subgroup, d_zs, d_rowprod);
+        P2G_COUNT_LAUNCH(1); zs_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_rowprod);
+        P2G_COUNT_LAUNCH(1); zs_apply_kernel<<<grid, 128, 0, st>>>(cd, d_rowprod, d_zs);
         if (has_lookup) {
             P2G_COUNT_LAUNCH(1); lookup_rows_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_row_kind, d_zs);
             P2G_COUNT_LAUNCH(1); lookup_scan_kernel<<<nch, 1024, 0, st>>>(cd, d_pc, C->d_row_kind, d_zs);
@@ -320,7 +322,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     tm.mark();
     if ((rc = commit_dev(ctx, d_zs, zs_cols, logn, cd.rate_bits, d.cap_height, true, &zb, true))) return rc;
-    ctx_free(ctx, d_zs);
+    ctx_free(ctx, d_zs); ctx_free(ctx, d_rowprod);
     tm.mark();
     ch.observe_many(zb->cap_host.data(), capw);
     // pc_host (pinned) was consumed by the H2D copy above once commit_dev synchronised

@@ -82,7 +82,8 @@ struct CircuitDev {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 zs_chunk_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ wires,
-                const gl_t* __restrict__ sigmas, const gl_t* __restrict__ subgroup, gl_t* __restrict__ zs) {
+                const gl_t* __restrict__ sigmas, const gl_t* __restrict__ subgroup, gl_t* __restrict__ zs,
+                gl_t* __restrict__ rowprod /*[nch][n]*/) {
     const size_t n = (size_t)1 << cd.logn;
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int ch = blockIdx.y;
@@ -108,45 +109,48 @@ zs_chunk_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
 #pragma unroll
     for (int ck = 0; ck < 16; ck++) if (ck < nchunks) { pre[ck] = acc; acc = gl_mul(acc, dens[ck]); }
     gl_t inv = gl_inv(acc);
+    gl_t rp = inv;                       // row quotient = prod(nums) / prod(dens)
 #pragma unroll
     for (int ck = 15; ck >= 0; ck--) if (ck < nchunks) {
         gl_t q = gl_mul(nums[ck], gl_mul(inv, pre[ck]));
         inv = gl_mul(inv, dens[ck]);
+        rp = gl_mul(rp, nums[ck]);
         int col = ck < cd.num_prods ? cd.nch + ch * cd.num_prods + ck : ch;
         zs[(size_t)col * n + r] = q;
     }
+    rowprod[(size_t)ch * n + r] = rp;
 }
 
-// step 2: Z(g^r) = prod_{r' < r} rowquotient(r'), partial products = Z * running chunk products.
-// One block per challenge; each thread owns a contiguous run of rows.
+// step 2: exclusive prefix product of the row quotients, one block per challenge
+// (in place: rowprod[r] <- Z(g^r), Z(1) = 1)
 __global__ void __launch_bounds__(1024)
-zs_scan_kernel(CircuitDev cd, gl_t* __restrict__ zs) {
+zs_scan_kernel(CircuitDev cd, gl_t* __restrict__ rowprod) {
     __shared__ Aff sm[32];
     const size_t n = (size_t)1 << cd.logn;
-    const int ch = blockIdx.x, nchunks = cd.num_prods + 1;
+    gl_t* P = rowprod + (size_t)blockIdx.x * n;
     const size_t per = (n + blockDim.x - 1) / blockDim.x;
     const size_t r0 = min(n, (size_t)threadIdx.x * per), r1 = min(n, r0 + per);
-    gl_t* Z = zs + (size_t)ch * n;
-    gl_t* PP = zs + ((size_t)cd.nch + (size_t)ch * cd.num_prods) * n;
     Aff mine = aff_id();
-    for (size_t r = r0; r < r1; r++) {
-        gl_t p = Z[r];
-        for (int ck = 0; ck < cd.num_prods; ck++) p = gl_mul(p, PP[(size_t)ck * n + r]);
-        mine.a = gl_mul(mine.a, p);
-    }
+    for (size_t r = r0; r < r1; r++) mine.a = gl_mul(mine.a, P[r]);
     Aff pre = block_scan_exclusive(mine, sm);
-    gl_t z = pre.a;   // Z at row r0 (Z(1) = 1)
-    for (size_t r = r0; r < r1; r++) {
-        gl_t q_last = Z[r];
-        gl_t accp = z;
-        for (int ck = 0; ck < cd.num_prods; ck++) {
-            accp = gl_mul(accp, PP[(size_t)ck * n + r]);
-            PP[(size_t)ck * n + r] = accp;
-        }
-        Z[r] = z;
-        z = gl_mul(accp, q_last);
+    gl_t z = pre.a;
+    for (size_t r = r0; r < r1; r++) { gl_t q = P[r]; P[r] = z; z = gl_mul(z, q); }
+}
+// step 3: per row, Z and the running partial products  Z * chunk_0 * ... * chunk_t
+__global__ void __launch_bounds__(128)
+zs_apply_kernel(CircuitDev cd, const gl_t* __restrict__ rowprod, gl_t* __restrict__ zs) {
+    const size_t n = (size_t)1 << cd.logn;
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (r >= n) return;
+    gl_t z = rowprod[(size_t)ch * n + r];
+    gl_t* PP = zs + ((size_t)cd.nch + (size_t)ch * cd.num_prods) * n;
+    gl_t acc = z;
+    for (int ck = 0; ck < cd.num_prods; ck++) {
+        acc = gl_mul(acc, PP[(size_t)ck * n + r]);
+        PP[(size_t)ck * n + r] = acc;
     }
-    (void)nchunks;
+    zs[(size_t)ch * n + r] = z;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -176,11 +180,19 @@ lookup_rows_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t
         gl_t re = 0;
         for (int k = 0; k < cd.num_sldc; k++) {
             int s0 = k * cd.lut_degree, s1 = min(s0 + cd.lut_degree, cd.lut_slots);
+            gl_t den[8], pre[8], mult[8];
+            gl_t acc = 1;
             for (int s = s0; s < s1; s++) {
-                gl_t in = wires[(size_t)(3 * s) * n + r], o = wires[(size_t)(3 * s + 1) * n + r], m = wires[(size_t)(3 * s + 2) * n + r];
+                gl_t in = wires[(size_t)(3 * s) * n + r], o = wires[(size_t)(3 * s + 1) * n + r];
+                mult[s - s0] = wires[(size_t)(3 * s + 2) * n + r];
                 re = gl_add(gl_mul(re, ddelta), gl_add(in, gl_mul(db, o)));
-                gl_t den = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
-                cum = gl_add(cum, gl_mul(m, gl_inv(den)));
+                den[s - s0] = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
+                pre[s - s0] = acc; acc = gl_mul(acc, den[s - s0]);
+            }
+            gl_t inv = gl_inv(acc);         // one inversion per slot group (Montgomery's trick)
+            for (int s = s1 - 1; s >= s0; s--) {
+                cum = gl_add(cum, gl_mul(mult[s - s0], gl_mul(inv, pre[s - s0])));
+                inv = gl_mul(inv, den[s - s0]);
             }
             base[(size_t)(k + 1) * n + r] = cum;
         }
