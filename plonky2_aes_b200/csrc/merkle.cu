@@ -142,39 +142,87 @@ merkle_level_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, size_t
     for (int i = 0; i < 4; i++) dst[4 * t + i] = o[i];
 }
 
+// one tree level, two nodes per warp (12 lanes each): the low-latency path for narrow levels
+__global__ void __launch_bounds__(256)
+merkle_level_coop_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, uint32_t cnt) {
+    const uint32_t lane = threadIdx.x & 31, l = lane & 15, g = lane >> 4;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t node = warp * 2 + g;
+#if defined(__CUDA_ARCH__)
+    gl_t x = 0;
+    if (node < cnt && l < 8) x = src[8 * (size_t)node + l];       // [left digest | right digest]
+    x = poseidon_coop(x, l, g << 4, POSEIDON_RC_GLOBAL);
+    if (node < cnt && l < 4) dst[4 * (size_t)node + l] = gl_canon(x);
+#else
+    (void)node; (void)l; (void)g; (void)src; (void)dst;
+#endif
+}
+// row-major leaves hashed cooperatively (FRI layers with few leaves): two leaves per warp
+__global__ void __launch_bounds__(256)
+merkle_leaves_coop_kernel(const gl_t* __restrict__ data, uint32_t leaf_len, uint32_t cnt, gl_t* __restrict__ dst) {
+    const uint32_t lane = threadIdx.x & 31, l = lane & 15, g = lane >> 4;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t leaf = warp * 2 + g;
+#if defined(__CUDA_ARCH__)
+    const bool ok = leaf < cnt;
+    gl_t x = 0;
+    for (uint32_t c0 = 0; c0 < leaf_len; c0 += 8) {
+        if (ok && l < 8 && c0 + l < leaf_len) x = data[(size_t)leaf * leaf_len + c0 + l];
+        x = poseidon_coop(x, l, g << 4, POSEIDON_RC_GLOBAL);
+    }
+    if (ok && l < 4) dst[4 * (size_t)leaf + l] = gl_canon(x);
+#else
+    (void)leaf; (void)l; (void)g; (void)data; (void)dst; (void)leaf_len;
+#endif
+}
+
 int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t leaf_len, uint32_t log_leaves,
                  uint32_t cap_height, gl_t* digests, gl_t* cap, cudaStream_t st) {
     if (cap_height > log_leaves) return -2;
     const uint32_t L = log_leaves - cap_height;
     const size_t num_leaves = (size_t)1 << log_leaves;
-    uint32_t threads = num_leaves < MERKLE_BLOCK ? (uint32_t)num_leaves : MERKLE_BLOCK;
-    if (threads < 32) threads = 32;   // keep full warps; surplus threads hash nothing
-    uint32_t block_log = 0; while ((1u << block_log) < threads) block_log++;
-    uint32_t real_log = log_leaves < block_log ? log_leaves : block_log;
-    uint32_t levels_here = real_log < L ? real_log : L;
-    {   // levels folded inside the leaf kernel: past 3 levels most of a block idles while it still
-        // pins its registers, so the rest of the tree is finished by the per-level / top kernels
-        static int cap_levels = -1;
-        if (cap_levels < 0) { const char* e = getenv("P2G_MERKLE_BLOCK_LEVELS"); cap_levels = e ? atoi(e) : 3; }
-        if ((int)levels_here > cap_levels) levels_here = (uint32_t)cap_levels;
+    const uint32_t COOP_MAX = 4096;     // levels (or leaf sets) this narrow use the 12-lane permutation
+    uint32_t lv;
+    if (!col_major && leaf_len > 4 && num_leaves <= COOP_MAX) {
+        gl_t* d0 = L == 0 ? cap : digests;
+        uint32_t warps = (uint32_t)((num_leaves + 1) / 2);
+        merkle_leaves_coop_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(data, leaf_len, (uint32_t)num_leaves, d0);
+        P2G_COUNT_LAUNCH(1);
+        lv = 0;
+    } else {
+        uint32_t threads = num_leaves < MERKLE_BLOCK ? (uint32_t)num_leaves : MERKLE_BLOCK;
+        if (threads < 32) threads = 32;   // keep full warps; surplus threads hash nothing
+        uint32_t block_log = 0; while ((1u << block_log) < threads) block_log++;
+        uint32_t real_log = log_leaves < block_log ? log_leaves : block_log;
+        uint32_t levels_here = real_log < L ? real_log : L;
+        {   // levels folded inside the leaf kernel: past 3 levels most of a block idles while it still
+            // pins its registers, so the rest of the tree is finished by the per-level kernels
+            static int cap_levels = -1;
+            if (cap_levels < 0) { const char* e = getenv("P2G_MERKLE_BLOCK_LEVELS"); cap_levels = e ? atoi(e) : 3; }
+            if ((int)levels_here > cap_levels) levels_here = (uint32_t)cap_levels;
+        }
+        uint32_t blocks = (uint32_t)((num_leaves + threads - 1) / threads);
+        if (col_major)
+            merkle_leaves_kernel<true><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
+        else
+            merkle_leaves_kernel<false><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
+        P2G_COUNT_LAUNCH(1);
+        lv = levels_here;
     }
-    uint32_t blocks = (uint32_t)((num_leaves + threads - 1) / threads);
-    if (col_major)
-        merkle_leaves_kernel<true><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
-    else
-        merkle_leaves_kernel<false><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
-    P2G_COUNT_LAUNCH(1);
-    uint32_t lv = levels_here;
-    // wide levels: one launch each until <= 2048 nodes remain, then a single block finishes
-    while (lv < L && ((size_t)1 << (log_leaves - lv - 1)) > 2048) {
+    // remaining levels, one launch each: thread-per-node while the level is wide, 12-lane form below
+    while (lv < L) {
         size_t cnt = (size_t)1 << (log_leaves - lv - 1);
         const gl_t* src = digests + merkle_level_offset(log_leaves, lv);
         gl_t* dst = (lv + 1 >= L) ? cap : digests + merkle_level_offset(log_leaves, lv + 1);
-        merkle_level_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(src, dst, cnt);
+        if (cnt > COOP_MAX) {
+            merkle_level_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(src, dst, cnt);
+        } else {
+            uint32_t warps = (uint32_t)((cnt + 1) / 2);
+            merkle_level_coop_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(src, dst, (uint32_t)cnt);
+        }
         P2G_COUNT_LAUNCH(1);
         lv++;
     }
-    if (lv < L) { merkle_top_kernel<<<1, 1024, 0, st>>>(digests, cap, log_leaves, L, lv); P2G_COUNT_LAUNCH(1); }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

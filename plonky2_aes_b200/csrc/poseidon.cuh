@@ -28,6 +28,10 @@ __constant__ gl_t POSEIDON_RC_DEV[372] = {      // 30 rounds + one all-zero row 
 #include "poseidon_rc.inc"
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0
 };
+__device__ gl_t POSEIDON_RC_GLOBAL[372] = {     // same table in global memory for per-lane reads
+#include "poseidon_rc.inc"
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0
+};
 __constant__ uint32_t GL_EPS_DEV = 0xffffffffu;  // kept in constant memory so ptxas keeps h*EPS as one IMAD.WIDE
 #include "poseidon_rc_f64.inc"
 #endif
@@ -176,6 +180,40 @@ __device__ __forceinline__ void poseidon_permute(gl_t s[12]) {
     poseidon_permute_lazy(s);
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+}
+// ------------------------------------------------------------------------------------------
+// Low-latency form: one permutation spread over 12 lanes of a 16-lane group (2 per warp).
+// Lane l holds state word l.  Every round costs one S-box + 22 shuffles + 24 IMAD.WIDE per lane
+// instead of 12 S-boxes + a 144-term MDS per thread, so the dependent chain of a permutation is
+// ~6x shorter.  Used where a Merkle level has too few nodes to fill the GPU (tree tops, FRI
+// layers): there latency, not throughput, is the cost.  rc: global-memory copy of the constants
+// (per-lane addresses would serialise in the constant cache).
+__device__ __forceinline__ gl_t poseidon_coop(gl_t x, uint32_t l, uint32_t group_base, const gl_t* __restrict__ rc) {
+    const uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    const uint32_t lc = l < 12 ? l : 0;
+    x = gl_add_lazy_dev(x, __ldg(rc + lc));
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+        const bool full = r < 4 || r >= 26;
+        gl_t y = poseidon_sbox(x);
+        if (full || l == 0) x = y;
+        uint32_t lo, hi; gl_unpack(x, lo, hi);
+        uint32_t nl, nh; gl_unpack(__ldg(rc + 12 * (r + 1) + lc), nl, nh);     // row 30 is zero
+        uint64_t al = nl, ah = nh;
+        al += (uint64_t)lo * C[0]; ah += (uint64_t)hi * C[0];
+        if (l == 0) { al += (uint64_t)lo * 8u; ah += (uint64_t)hi * 8u; }
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+            const uint32_t src = group_base + (lc + i >= 12 ? lc + i - 12 : lc + i);
+            const uint32_t vl = __shfl_sync(0xffffffffu, lo, src), vh = __shfl_sync(0xffffffffu, hi, src);
+            al += (uint64_t)vl * C[i]; ah += (uint64_t)vh * C[i];
+        }
+        uint32_t al0, al1, ah0, ah1; gl_unpack(al, al0, al1); gl_unpack(ah, ah0, ah1);
+        uint32_t m, t;
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
+        x = gl_fold3(al0, m, t);
+    }
+    return x;
 }
 #else
 // ------------------------------------------------------------------------------------------
