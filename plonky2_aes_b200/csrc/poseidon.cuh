@@ -78,6 +78,18 @@ __device__ __forceinline__ void pmul128(gl_t a, gl_t b, uint32_t& l0, uint32_t& 
         : "=&r"(l1), "=&r"(h0), "=&r"(h1)
         : "r"(c0), "r"(m1l), "r"(p11l), "r"(m1h), "r"(p11h), "r"(m2l), "r"(m2h));
 }
+// a^2: the cross product a0*a1 is computed once and added twice (one IMAD.WIDE fewer)
+__device__ __forceinline__ gl_t psqr(gl_t a) {
+    uint32_t a0, a1; gl_unpack(a, a0, a1);
+    uint32_t l0, c0, ml, mh, p11l, p11h;
+    gl_unpack(gl_mulw(a0, a0), l0, c0); gl_unpack(gl_mulw(a0, a1), ml, mh); gl_unpack(gl_mulw(a1, a1), p11l, p11h);
+    uint32_t l1, h0, h1;
+    asm("add.cc.u32 %0, %3, %4;\n\taddc.cc.u32 %1, %5, %6;\n\taddc.u32 %2, %7, 0;\n\t"
+        "add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.u32 %2, %2, 0;"
+        : "=&r"(l1), "=&r"(h0), "=&r"(h1)
+        : "r"(c0), "r"(ml), "r"(p11l), "r"(mh), "r"(p11h));
+    return gl_fold4(l0, l1, h0, h1);
+}
 // any u64 * any u64 -> lazy residue (about 21 SASS instructions, 5 of them IMAD.WIDE)
 __device__ __forceinline__ gl_t pmul(gl_t a, gl_t b) {
     uint32_t l0, l1, h0, h1; pmul128(a, b, l0, l1, h0, h1);
@@ -99,7 +111,7 @@ __device__ __forceinline__ void acc_mul(Acc160& A, gl_t a, gl_t b) {
 }
 __device__ __forceinline__ gl_t acc_fold(const Acc160& A) { return gl_fold5(A.w[0], A.w[1], A.w[2], A.w[3], A.w[4]); }
 __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
-    gl_t x2 = pmul(x, x), x4 = pmul(x2, x2), x3 = pmul(x, x2);
+    gl_t x2 = psqr(x), x4 = psqr(x2), x3 = pmul(x, x2);
     return pmul(x3, x4);
 }
 // s <- MDS * s + RC[next_row]   (lazy in, lazy out) on the FP64 pipe.
@@ -112,6 +124,9 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 __device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
     const double MAGIC = 4503599627370496.0;   // 2^52
+    // u32 -> f64 with I2F (conversion pipe) rather than the magic-number DADD: measured +4.5 %
+#define POS_CVT(u) ((double)(u))
+    (void)MAGIC;
     uint32_t al0[12], al1[12];
     {
         double acc[12];
@@ -119,7 +134,7 @@ __device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
         for (int r = 0; r < 12; r++) acc[r] = POSEIDON_RCD_LO[12 * next_row + r];
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            const double x = __hiloint2double(0x43300000, (int)(uint32_t)s[i]) - MAGIC;
+            const double x = POS_CVT((uint32_t)s[i]);
 #pragma unroll
             for (int r = 0; r < 12; r++) acc[r] = __fma_rn(x, C[(i - r + 12) % 12], acc[r]);
             if (i == 0) acc[0] = __fma_rn(x, 8., acc[0]);
@@ -133,7 +148,7 @@ __device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
         for (int r = 0; r < 12; r++) acc[r] = POSEIDON_RCD_HI[12 * next_row + r];
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            const double x = __hiloint2double(0x43300000, (int)(uint32_t)(s[i] >> 32)) - MAGIC;
+            const double x = POS_CVT((uint32_t)(s[i] >> 32));
 #pragma unroll
             for (int r = 0; r < 12; r++) acc[r] = __fma_rn(x, C[(i - r + 12) % 12], acc[r]);
             if (i == 0) acc[0] = __fma_rn(x, 8., acc[0]);
