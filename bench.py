@@ -119,7 +119,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, help="proofs in flight per GPU (one p2g context + host thread each)")
+    ap.add_argument("--streams", type=int, default=3, help="proofs in flight per GPU (one p2g context + host thread each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,7 +207,7 @@ def main():
     ms_dev = timed(step_device, args.steps)
     launches = lib.p2g_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(args.warmup):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     total_proofs = B * args.steps * world

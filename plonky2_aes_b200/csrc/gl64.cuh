@@ -56,12 +56,61 @@ GL_HD void gl_mul_wide(gl_t a, gl_t b, gl_t& lo, gl_t& hi) {
     lo = (gl_t)x; hi = (gl_t)(x >> 64);
 #endif
 }
+#if defined(__CUDACC__)
+__constant__ uint32_t GL_EPS_DEV = 0xffffffffu;  // kept in constant memory so ptxas keeps h*EPS as one IMAD.WIDE
+#endif
+#if defined(__CUDA_ARCH__)
+// ---- device multiply on 32-bit halves (the 64-bit mul.hi of the compiler costs 13 issue cycles) ----
+__device__ __forceinline__ void gl_unpack(gl_t x, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
+__device__ __forceinline__ gl_t gl_pack(uint32_t lo, uint32_t hi) { gl_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ gl_t gl_mulw(uint32_t a, uint32_t b) { gl_t r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
+
+// (l1:l0) + h0*2^64 -> lazy residue:  one IMAD.WIDE, then +EPS if the 64-bit sum wrapped
+// (h0*EPS <= 2^64 - 2^33 + 1, so a wrap always lowers the high word: one 32-bit compare)
+__device__ __forceinline__ void gl_fold3w(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t& w0, uint32_t& w1) {
+    gl_t v;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(v) : "r"(h0), "r"(GL_EPS_DEV), "l"(gl_pack(l0, l1)));
+    uint32_t v0, v1; gl_unpack(v, v0, v1);
+    uint32_t c = v1 < l1 ? 0xffffffffu : 0u;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(w0), "=&r"(w1) : "r"(v0), "r"(c), "r"(v1));
+}
+__device__ __forceinline__ gl_t gl_fold3(uint32_t l0, uint32_t l1, uint32_t h0) {
+    uint32_t w0, w1; gl_fold3w(l0, l1, h0, w0, w1);
+    return gl_pack(w0, w1);
+}
+// (l1:l0) + h0*2^64 + (h2:h1)*2^96 -> lazy residue  (2^96 = -1: subtract (h2:h1), -EPS on borrow;
+// h2 is the small overflow word of multi-term accumulations, 2^128 = -2^32)
+__device__ __forceinline__ gl_t gl_fold5(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t h1, uint32_t h2) {
+    uint32_t w0, w1, m; gl_fold3w(l0, l1, h0, w0, w1);
+    asm("sub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;"
+        : "+r"(w0), "+r"(w1), "=&r"(m) : "r"(h1), "r"(h2));
+    return gl_pack(w0, w1);
+}
+__device__ __forceinline__ gl_t gl_fold4(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t h1) { return gl_fold5(l0, l1, h0, h1, 0); }
+// 128-bit product of two u64 as four 32-bit words
+__device__ __forceinline__ void pmul128(gl_t a, gl_t b, uint32_t& l0, uint32_t& l1, uint32_t& h0, uint32_t& h1) {
+    uint32_t a0, a1, b0, b1; gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
+    uint32_t c0, m1l, m1h, m2l, m2h, p11l, p11h;
+    gl_unpack(gl_mulw(a0, b0), l0, c0); gl_unpack(gl_mulw(a0, b1), m1l, m1h);
+    gl_unpack(gl_mulw(a1, b0), m2l, m2h); gl_unpack(gl_mulw(a1, b1), p11l, p11h);
+    asm("add.cc.u32 %0, %3, %4;\n\taddc.cc.u32 %1, %5, %6;\n\taddc.u32 %2, %7, 0;\n\t"
+        "add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %9;\n\taddc.u32 %2, %2, 0;"
+        : "=&r"(l1), "=&r"(h0), "=&r"(h1)
+        : "r"(c0), "r"(m1l), "r"(p11l), "r"(m1h), "r"(p11h), "r"(m2l), "r"(m2h));
+}
+__device__ __forceinline__ gl_t gl_mul_lazy(gl_t a, gl_t b) {
+    uint32_t l0, l1, h0, h1; pmul128(a, b, l0, l1, h0, h1);
+    return gl_fold4(l0, l1, h0, h1);
+}
+#else
 // any u64 * any u64 -> lazy residue
 GL_HD gl_t gl_mul_lazy(gl_t a, gl_t b) {
     gl_t lo, hi;
     gl_mul_wide(a, b, lo, hi);
     return gl_reduce128_lazy(lo, hi);
 }
+#endif
 // any * any -> canonical
 GL_HD gl_t gl_mul(gl_t a, gl_t b) { return gl_canon(gl_mul_lazy(a, b)); }
 GL_HD gl_t gl_sqr(gl_t a) { return gl_mul(a, a); }
