@@ -19,10 +19,15 @@ extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     memset(&ctx->transcript, 0, sizeof(ctx->transcript));
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    {
+        cudaMemPoolProps props; memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) { cudaStreamDestroy(ctx->st); delete ctx; return P2G_E_CUDA; }
         uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     ctx->pinned_words = 1 << 20;
     if (cudaMallocHost(&ctx->pinned, ctx->pinned_words * sizeof(gl_t)) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
@@ -35,6 +40,7 @@ extern "C" void p2g_ctx_destroy(p2g_ctx* ctx) {
     cudaStreamSynchronize(ctx->st);
     for (auto& kv : ctx->plans) ntt_plan_free(&kv.second);
     cudaFreeHost(ctx->pinned);
+    cudaMemPoolDestroy(ctx->pool);
     cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -54,7 +60,7 @@ int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan
     return P2G_OK;
 }
 int ctx_alloc(p2g_ctx* ctx, gl_t** p, size_t words) {
-    CU(cudaMallocAsync((void**)p, (words ? words : 1) * sizeof(gl_t), ctx->st));
+    CU(cudaMallocFromPoolAsync((void**)p, (words ? words : 1) * sizeof(gl_t), ctx->pool, ctx->st));
     return P2G_OK;
 }
 void ctx_free(p2g_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->st); }

@@ -25,6 +25,8 @@ struct ProveScratch;  // prover.cu
 struct p2g_ctx {
     int device;
     cudaStream_t st;
+    cudaMemPool_t pool;     // private pool: blocks freed on this stream are never handed to another
+                            // context's stream, so proofs in flight on one GPU stay independent
     std::string err;
     std::map<std::tuple<int, int, int>, NttPlan> plans;
     gl_t* pinned; size_t pinned_words;     // small pinned staging buffer for D2H results

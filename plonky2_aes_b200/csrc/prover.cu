@@ -166,15 +166,15 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
             for (int r = last_lu; r < last_lut; r++) kind[r] = 1;
             for (int r = last_lut; r <= first_lut; r++) kind[r] = 2;
         }
-        CU(cudaMallocAsync((void**)&C->d_row_kind, n, ctx->st));
-        CU(cudaMallocAsync((void**)&C->d_gates, sizeof(p2g_gate) * std::max(1, d.num_gates), ctx->st));
+        CU(cudaMallocFromPoolAsync((void**)&C->d_row_kind, n, ctx->pool, ctx->st));
+        CU(cudaMallocFromPoolAsync((void**)&C->d_gates, sizeof(p2g_gate) * std::max(1, d.num_gates), ctx->pool, ctx->st));
         CU(cudaMemcpyAsync(C->d_row_kind, kind.data(), n, cudaMemcpyHostToDevice, ctx->st));
         CU(cudaMemcpyAsync(C->d_gates, C->gates.data(), sizeof(p2g_gate) * d.num_gates, cudaMemcpyHostToDevice, ctx->st));
         std::vector<int> off(8, 0), len(8, 0);
         { int t = 0; for (int l = 0; l < d.num_luts; l++) { off[l] = t; len[l] = d.lut_lens[l]; t += d.lut_lens[l]; } }
-        CU(cudaMallocAsync((void**)&C->d_lut_data, std::max<size_t>(4, 4 * lut_total), ctx->st));
-        CU(cudaMallocAsync((void**)&C->d_lut_off, 8 * sizeof(int), ctx->st));
-        CU(cudaMallocAsync((void**)&C->d_lut_len, 8 * sizeof(int), ctx->st));
+        CU(cudaMallocFromPoolAsync((void**)&C->d_lut_data, std::max<size_t>(4, 4 * lut_total), ctx->pool, ctx->st));
+        CU(cudaMallocFromPoolAsync((void**)&C->d_lut_off, 8 * sizeof(int), ctx->pool, ctx->st));
+        CU(cudaMallocFromPoolAsync((void**)&C->d_lut_len, 8 * sizeof(int), ctx->pool, ctx->st));
         CU(cudaMemcpyAsync(C->d_lut_data, C->lut_data.data(), 4 * lut_total, cudaMemcpyHostToDevice, ctx->st));
         CU(cudaMemcpyAsync(C->d_lut_off, off.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
         CU(cudaMemcpyAsync(C->d_lut_len, len.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
@@ -292,7 +292,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     if (has_lookup) for (int i = 0; i < nch; i++) pc_host->delta_pow_slots[i] = gl_pow(pc_host->deltas[i][3], cd.lut_slots);
     ProofConsts* d_pc;
-    CU(cudaMallocAsync((void**)&d_pc, sizeof(ProofConsts), st));
+    CU(cudaMallocFromPoolAsync((void**)&d_pc, sizeof(ProofConsts), ctx->pool, st));
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
     gl_t* d_lut_evals;
     if ((rc = ctx_alloc(ctx, &d_lut_evals, MAX_CH * 8))) return rc;
@@ -379,7 +379,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         for (int i = zpp; i < zs_cols; i++) plist[k++] = oracles[2]->coeffs + (size_t)i * n;
     }
     const gl_t** d_plist; gl_t *d_zp, *d_open;
-    CU(cudaMallocAsync((void**)&d_plist, plist.size() * sizeof(gl_t*), st));
+    CU(cudaMallocFromPoolAsync((void**)&d_plist, plist.size() * sizeof(gl_t*), ctx->pool, st));
     CU(cudaMemcpyAsync(d_plist, plist.data(), plist.size() * sizeof(gl_t*), cudaMemcpyHostToDevice, st));
     if ((rc = ctx_alloc(ctx, &d_zp, 4 * n))) return rc;
     if ((rc = ctx_alloc(ctx, &d_open, 2 * (size_t)(tot0 + tot1)))) return rc;
@@ -510,7 +510,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         const int pos = ch.in_len;
         for (int i = 0; i < pos; i++) ps.s[i] = ch.in_buf[i];
         unsigned long long* d_best;
-        CU(cudaMallocAsync((void**)&d_best, 8, st));
+        CU(cudaMallocFromPoolAsync((void**)&d_best, 8, ctx->pool, st));
         const unsigned long long WIN = 1ull << 18;   // expected hit within 2^16 candidates; P(miss) = e^-4
         bool found = false;
         for (unsigned long long base = 0; !found && base < (1ull << 30); base += WIN) {
@@ -556,8 +556,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         }
     }
     GatherTree* d_gt; unsigned long long* d_qidx; gl_t* d_q;
-    CU(cudaMallocAsync((void**)&d_gt, gt.size() * sizeof(GatherTree), st));
-    CU(cudaMallocAsync((void**)&d_qidx, nq * 8, st));
+    CU(cudaMallocFromPoolAsync((void**)&d_gt, gt.size() * sizeof(GatherTree), ctx->pool, st));
+    CU(cudaMallocFromPoolAsync((void**)&d_qidx, nq * 8, ctx->pool, st));
     if ((rc = ctx_alloc(ctx, &d_q, rec * nq))) return rc;
     CU(cudaMemcpyAsync(d_gt, gt.data(), gt.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_qidx, qidx.data(), nq * 8, cudaMemcpyHostToDevice, st));
@@ -630,7 +630,7 @@ extern "C" int32_t p2g_pow_grind(p2g_ctx* ctx, const uint64_t state[12], uint32_
     CU(cudaSetDevice(ctx->device));
     PowState ps; memcpy(ps.s, state, sizeof(ps.s));
     unsigned long long* d_best;
-    CU(cudaMallocAsync((void**)&d_best, 8, ctx->st));
+    CU(cudaMallocFromPoolAsync((void**)&d_best, 8, ctx->pool, ctx->st));
     const unsigned long long WIN = 1ull << 20;
     for (unsigned long long base = 0; base < (1ull << 44); base += WIN) {
         CU(cudaMemsetAsync(d_best, 0xFF, 8, ctx->st));
