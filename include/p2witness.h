@@ -19,7 +19,7 @@ enum { P2W_OP_ARITH = 0,   /* s0 = c0*s1*s2 + c1*s3                         (Ari
        P2W_OP_LOOKUP = 1,  /* s0 = lut[s4 as lut index][value(s1)]          (LookupGenerator)          */
        P2W_OP_EQ = 2,      /* s0 = (s2 == s3), s1 = (s2 - s3)^-1 or 0       (EqualityGenerator)        */
        P2W_OP_CONST = 3,   /* s0 = c0                                        (ConstantGate generator)   */
-       P2W_OP_POSEIDON = 4 /* s0..: reserved */ };
+       P2W_OP_POSEIDON = 4 /* s0 = index into poseidon_rows: PoseidonGate generator (gates/poseidon.rs) */ };
 
 #define P2W_E_CONFLICT (-10)  /* a partition was set twice with different values */
 #define P2W_E_LOOKUP (-11)    /* looked-up value is not a key of the table */
@@ -46,6 +46,9 @@ typedef struct {
     const int32_t* lookup_slots;    /* concatenated input slots */
     const int32_t* lookup_padding;  /* [num_luts] */
     const int64_t* mult_pos;        /* concatenated, one per LUT entry */
+    /* PoseidonGate rows: [num_poseidon][25] = row, 12 input slots, 12 output slots */
+    uint32_t num_poseidon;
+    const int32_t* poseidon_rows;
 } p2w_program_desc;
 
 typedef struct p2w_program p2w_program;

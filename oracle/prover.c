@@ -19,6 +19,12 @@
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 #define STAGE(name) do { if (timing) { double t_ = now_s(); fprintf(stderr, "[oracle] %-18s %.3f s\n", name, t_ - t_last); t_last = t_; } } while (0)
 
+/* constants the PoseidonGate constraints need (same tables as core.c) */
+static const gl_t VAN_RC[360] = {
+#include "poseidon_rc.inc"
+};
+static const gl_t VAN_MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+#include "poseidon_fast.inc"
 /* ---- two instantiations of the vanishing-polynomial evaluator ---- */
 #define VNAME(x) vb_##x
 #define FT gl_t

@@ -39,7 +39,7 @@ static void VNAME(eval)(const VNAME(ctx)* v, FT x, FT l0x, const FT* consts, con
     const int lut_degree = has_lookup ? (lut_slots + num_sldc - 1) / num_sldc : 0;
     const int n_lookup_terms = has_lookup ? 4 + c->num_luts + 2 * num_sldc : 0;
     const int nterms = nch + nch * (num_prods + 1) + nch * n_lookup_terms + c->num_gate_constraints;
-    FT terms[512];
+    FT terms[640];
     int t = 0;
     /* Z(x) - 1 terms */
     for (int i = 0; i < nch; i++) terms[t++] = F_MUL(l0x, F_SUBB(zs[i], 1));
@@ -130,6 +130,57 @@ static void VNAME(eval)(const VNAME(ctx)* v, FT x, FT l0x, const FT* consts, con
             case ORC_GATE_PUBLIC_INPUT:
                 for (int k = 0; k < 4; k++) gc[k] = F_ADD(gc[k], F_MUL(f, F_SUBB(wires[k], v->pi_hash[k])));
                 break;
+            case ORC_GATE_POSEIDON: {
+                /* gates/poseidon.rs eval_unfiltered: wires 0..11 input, 12..23 output, 24 swap, 25..28 delta,
+                 * 29..64 full-round S-box inputs (rounds 1..3), 65..86 partial S-box inputs, 87..134 second
+                 * full rounds; the partial rounds are constrained in their sparse form */
+                FT st[12]; int k = 0;
+                FT swap = wires[24];
+                gc[k] = F_ADD(gc[k], F_MUL(f, F_MUL(swap, F_SUBB(swap, 1)))); k++;
+                for (int i = 0; i < 4; i++) {
+                    FT d = wires[25 + i];
+                    gc[k] = F_ADD(gc[k], F_MUL(f, F_SUB(F_MUL(swap, F_SUB(wires[i + 4], wires[i])), d))); k++;
+                    st[i] = F_ADD(wires[i], d); st[i + 4] = F_SUB(wires[i + 4], d);
+                }
+                for (int i = 8; i < 12; i++) st[i] = wires[i];
+#define PG_SBOX(x) do { FT x2_ = F_MUL(x, x), x4_ = F_MUL(x2_, x2_), x3_ = F_MUL(x, x2_); x = F_MUL(x3_, x4_); } while (0)
+#define PG_MDS() do { FT o_[12]; for (int r_ = 0; r_ < 12; r_++) { FT a_ = F_ZERO; for (int i_ = 0; i_ < 12; i_++) a_ = F_ADD(a_, F_MULB(st[(i_ + r_) % 12], VAN_MDS_CIRC[i_])); \
+                      if (r_ == 0) a_ = F_ADD(a_, F_MULB(st[0], 8)); o_[r_] = a_; } for (int r_ = 0; r_ < 12; r_++) st[r_] = o_[r_]; } while (0)
+                for (int r = 0; r < 4; r++) {
+                    for (int i = 0; i < 12; i++) st[i] = F_ADDB(st[i], VAN_RC[12 * r + i]);
+                    if (r != 0) for (int i = 0; i < 12; i++) {
+                        FT in = wires[29 + 12 * (r - 1) + i];
+                        gc[k] = F_ADD(gc[k], F_MUL(f, F_SUB(st[i], in))); k++; st[i] = in;
+                    }
+                    for (int i = 0; i < 12; i++) PG_SBOX(st[i]);
+                    PG_MDS();
+                }
+                for (int i = 0; i < 12; i++) st[i] = F_ADDB(st[i], PFAST_FIRST_C[i]);
+                { FT t_[11]; for (int r = 0; r < 11; r++) { FT a = F_ZERO; for (int cc = 0; cc < 11; cc++) a = F_ADD(a, F_MULB(st[cc + 1], PFAST_INIT[r * 11 + cc])); t_[r] = a; }
+                  for (int r = 0; r < 11; r++) st[r + 1] = t_[r]; }
+                for (int r = 0; r < 22; r++) {
+                    FT in = wires[65 + r];
+                    gc[k] = F_ADD(gc[k], F_MUL(f, F_SUB(st[0], in))); k++;
+                    st[0] = in; PG_SBOX(st[0]);
+                    st[0] = F_ADDB(st[0], PFAST_K[r]);
+                    FT s0 = F_MULB(st[0], 25);
+                    for (int j = 0; j < 11; j++) s0 = F_ADD(s0, F_MULB(st[j + 1], PFAST_VROW[r * 11 + j]));
+                    for (int j = 0; j < 11; j++) st[j + 1] = F_ADD(st[j + 1], F_MULB(st[0], PFAST_WCOL[r * 11 + j]));
+                    st[0] = s0;
+                }
+                for (int r = 0; r < 4; r++) {
+                    for (int i = 0; i < 12; i++) st[i] = F_ADDB(st[i], VAN_RC[12 * (26 + r) + i]);
+                    for (int i = 0; i < 12; i++) {
+                        FT in = wires[87 + 12 * r + i];
+                        gc[k] = F_ADD(gc[k], F_MUL(f, F_SUB(st[i], in))); k++; st[i] = in;
+                    }
+                    for (int i = 0; i < 12; i++) PG_SBOX(st[i]);
+                    PG_MDS();
+                }
+                for (int i = 0; i < 12; i++) { gc[k] = F_ADD(gc[k], F_MUL(f, F_SUB(st[i], wires[12 + i]))); k++; }
+#undef PG_SBOX
+#undef PG_MDS
+                break; }
             default: break;
             }
         }

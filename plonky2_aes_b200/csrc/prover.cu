@@ -94,7 +94,7 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
         ctx->err = "unsupported circuit configuration"; return P2G_E_BADARG;
     }
     for (int g = 0; g < d.num_gates; g++)
-        if (d.gates[g].kind == P2G_GATE_POSEIDON) { ctx->err = "PoseidonGate constraints are not implemented yet"; return P2G_E_BADARG; }
+        if (d.gates[g].kind < P2G_GATE_NOOP || d.gates[g].kind > P2G_GATE_POSEIDON) { ctx->err = "unknown gate kind"; return P2G_E_BADARG; }
     CU(cudaSetDevice(ctx->device));
     p2g_circuit* C = new p2g_circuit();
     C->d = d;
@@ -118,7 +118,7 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
     cd.zs_cols = cd.nch * (1 + cd.num_prods + cd.nlp);
     if (cd.lut_degree > 8) { delete C; ctx->err = "lut_degree > 8"; return P2G_E_BADARG; }
     int nterms = cd.nch + cd.nch * (cd.num_prods + 1) + (cd.num_luts ? cd.nch * (4 + cd.num_luts + 2 * cd.num_sldc) : 0) + cd.num_gate_constraints;
-    if (nterms > 160) { delete C; ctx->err = "too many vanishing terms"; return P2G_E_BADARG; }
+    if (nterms > 256) { delete C; ctx->err = "too many vanishing terms"; return P2G_E_BADARG; }
     C->proof_words = proof_len(d);
     const size_t n = (size_t)1 << cd.logn, N = n << cd.rate_bits;
     const int logN = cd.logn + cd.rate_bits;
@@ -329,7 +329,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     for (int i = 0; i < nch; i++) {
         pc_host->alphas[i] = ch.get();
         gl_t p = 1;
-        for (int k = 0; k < 160; k++) { pc_host->alpha_pows[i][k] = p; p = gl_mul(p, pc_host->alphas[i]); }
+        for (int k = 0; k < 256; k++) { pc_host->alpha_pows[i][k] = p; p = gl_mul(p, pc_host->alphas[i]); }
     }
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
 

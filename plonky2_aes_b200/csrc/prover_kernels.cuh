@@ -63,7 +63,7 @@ struct ProofConsts {
     gl_t beta_kis[MAX_CH][MAX_ROUTED];      // beta_c * k_j
     gl_t k_is[MAX_ROUTED];
     gl_t pi_hash[4];
-    gl_t alpha_pows[MAX_CH][160];           // alpha_c^k for the reduce_with_powers of the vanishing terms
+    gl_t alpha_pows[MAX_CH][256];           // alpha_c^k for the reduce_with_powers of the vanishing terms
     gl_t zh[16], zh_inv[16];                // Z_H on coset s (natural coset index), and inverse
     gl_t delta_pow_slots[MAX_CH];           // delta^(num_lut_slots)
 };
@@ -262,6 +262,58 @@ lookup_scan_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const uint
 // = same coset block, position bitrev(k + 1).  The result is scattered to natural order inside
 // each coset block so the inverse NTT that follows can take natural input.
 // ---------------------------------------------------------------------------------------------
+#define PFAST_QUAL __constant__
+#include "poseidon_fast.inc"
+#undef PFAST_QUAL
+
+// PoseidonGate::eval_unfiltered (gates/poseidon.rs): 123 constraints, evaluated in their upstream
+// order and handed to `emit(k, value)`.  Wires: 0..11 input, 12..23 output, 24 swap, 25..28 delta,
+// 29..64 / 65..86 / 87..134 the S-box inputs of the first full, the partial (sparse form) and the
+// last full rounds.  Rare path (only circuits with Poseidon rows), kept out of line.
+template <typename Emit>
+__device__ __noinline__ void poseidon_gate_constraints(const gl_t* __restrict__ wl, size_t N, size_t j, Emit emit) {
+#if defined(__CUDA_ARCH__)
+    auto W = [&](int c) { return wl[(size_t)c * N + j]; };
+    gl_t st[12]; int k = 0;
+    const gl_t swap = W(24);
+    emit(k++, gl_mul(swap, gl_sub(swap, 1)));
+    for (int i = 0; i < 4; i++) {
+        gl_t d = W(25 + i), a = W(i), b = W(i + 4);
+        emit(k++, gl_sub(gl_mul(swap, gl_sub(b, a)), d));
+        st[i] = gl_add(a, d); st[i + 4] = gl_sub(b, d);
+    }
+    for (int i = 8; i < 12; i++) st[i] = W(i);
+    for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC_DEV[i]);
+    for (int r = 0; r < 4; r++) {
+        if (r != 0) for (int i = 0; i < 12; i++) { gl_t in = W(29 + 12 * (r - 1) + i); emit(k++, gl_sub(gl_canon(st[i]), in)); st[i] = in; }
+        for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
+        poseidon_mds_rc(st, r < 3 ? r + 1 : 30);           // next round constants; none before the partial rounds
+    }
+    for (int i = 0; i < 12; i++) st[i] = gl_add(gl_canon(st[i]), PFAST_FIRST_C[i]);
+    {
+        gl_t t[11];
+        for (int r = 0; r < 11; r++) { gl_t a = 0; for (int c = 0; c < 11; c++) a = gl_add(a, gl_mul(st[c + 1], PFAST_INIT[r * 11 + c])); t[r] = a; }
+        for (int r = 0; r < 11; r++) st[r + 1] = t[r];
+    }
+    for (int r = 0; r < 22; r++) {
+        gl_t in = W(65 + r);
+        emit(k++, gl_sub(st[0], in));
+        st[0] = gl_add(gl_canon(poseidon_sbox(in)), PFAST_K[r]);
+        gl_t s0 = gl_mul(st[0], 25);
+        for (int q = 0; q < 11; q++) s0 = gl_add(s0, gl_mul(st[q + 1], PFAST_VROW[r * 11 + q]));
+        for (int q = 0; q < 11; q++) st[q + 1] = gl_add(st[q + 1], gl_mul(st[0], PFAST_WCOL[r * 11 + q]));
+        st[0] = s0;
+    }
+    for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], POSEIDON_RC_DEV[12 * 26 + i]);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) { gl_t in = W(87 + 12 * r + i); emit(k++, gl_sub(gl_canon(st[i]), in)); st[i] = in; }
+        for (int i = 0; i < 12; i++) st[i] = poseidon_sbox(st[i]);
+        poseidon_mds_rc(st, 27 + r);                          // rows 27..29, then 30 = zero
+    }
+    for (int i = 0; i < 12; i++) emit(k++, gl_sub(gl_canon(st[i]), W(12 + i)));
+#endif
+}
+
 __device__ __forceinline__ gl_t gate_filter(int row, int gs, int ge, gl_t s, bool many) {
     gl_t f = 1;
     for (int i = gs; i < ge; i++) if (i != row) f = gl_mul(f, gl_sub((gl_t)i, s));
@@ -413,8 +465,9 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
     {
         const gl_t* gconst = cs + (size_t)(cd.num_sel + cd.num_lsel) * N;
         const bool many = cd.num_sel > 1;
-        gl_t f_arith = 0, f_const = 0, f_pi = 0;
+        gl_t f_arith = 0, f_const = 0, f_pi = 0, f_pos = 0;
         int arith_ops = 0, nconst = 0;
+        bool has_poseidon = false;
         for (int g = 0; g < cd.num_gates; g++) {
             const p2g_gate G = gates[g];
             if (G.num_constraints == 0) continue;
@@ -422,9 +475,11 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             if (G.kind == P2G_GATE_ARITHMETIC) { f_arith = f; arith_ops = G.param0; }
             else if (G.kind == P2G_GATE_CONSTANT) { f_const = f; nconst = G.param0; }
             else if (G.kind == P2G_GATE_PUBLIC_INPUT) f_pi = f;
+            else if (G.kind == P2G_GATE_POSEIDON) { f_pos = f; has_poseidon = true; }
         }
         const gl_t c0 = cd.num_consts > 0 ? gconst[j] : 0, c1 = cd.num_consts > 1 ? gconst[N + j] : 0;
-        for (int k = 0; k < cd.num_gate_constraints; k++) {
+        // contribution of the cheap gates to constraint slot k
+        auto small_gates = [&](int k) -> gl_t {
             gl_t v = 0;
             if (k < arith_ops) {
                 gl_t m0 = wl[(size_t)(4 * k) * N + j], m1 = wl[(size_t)(4 * k + 1) * N + j];
@@ -434,7 +489,19 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             }
             if (k < nconst) v = gl_add(v, gl_mul(f_const, gl_sub(k == 0 ? c0 : c1, wl[(size_t)k * N + j])));
             if (k < 4 && f_pi) v = gl_add(v, gl_mul(f_pi, gl_sub(wl[(size_t)k * N + j], pc->pi_hash[k])));
-            ADD_TERM(t + k, v);
+            return v;
+        };
+        if (has_poseidon) {
+            gl_t a0 = acc[0], a1 = acc[1];
+            const int tbase = t;
+            poseidon_gate_constraints(wl, N, j, [&](int k, gl_t cval) {
+                gl_t v = gl_add(gl_mul(f_pos, cval), small_gates(k));
+                a0 = gl_add(a0, gl_mul(v, pc->alpha_pows[0][tbase + k]));
+                if (nch > 1) a1 = gl_add(a1, gl_mul(v, pc->alpha_pows[1][tbase + k]));
+            });
+            acc[0] = a0; acc[1] = a1;
+        } else {
+            for (int k = 0; k < cd.num_gate_constraints; k++) ADD_TERM(t + k, small_gates(k));
         }
     }
 #undef ADD_TERM

@@ -6,6 +6,52 @@
 #include <string.h>
 #include <stdlib.h>
 
+static const uint64_t W_RC[360] = {
+#include "poseidon_rc.inc"
+};
+#include "poseidon_fast.inc"
+static inline uint64_t w_sbox(uint64_t x) { uint64_t x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x, x2); return gl_mul(x3, x4); }
+static inline void w_mds(uint64_t s[12]) {
+    static const uint64_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint64_t o[12];
+    for (int r = 0; r < 12; r++) {
+        unsigned __int128 acc = 0;
+        for (int i = 0; i < 12; i++) acc += (unsigned __int128)s[(i + r) % 12] * C[i];
+        if (r == 0) acc += (unsigned __int128)s[0] * 8;
+        o[r] = gl_canon(gl_reduce128_lazy((uint64_t)acc, (uint64_t)(acc >> 64)));
+    }
+    memcpy(s, o, sizeof(o));
+}
+// PoseidonGate generator with swap = 0: fills wires 12..134 of the row (trace[c - 12]) and returns the output state
+static void w_poseidon_gate(const uint64_t in[12], uint64_t trace[123]) {
+    uint64_t st[12]; memcpy(st, in, sizeof(st));
+    memset(trace, 0, 123 * sizeof(uint64_t));           // swap (24) and deltas (25..28) are zero
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], W_RC[12 * r + i]);
+        if (r != 0) for (int i = 0; i < 12; i++) trace[29 + 12 * (r - 1) + i - 12] = st[i];
+        for (int i = 0; i < 12; i++) st[i] = w_sbox(st[i]);
+        w_mds(st);
+    }
+    for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], PFAST_FIRST_C[i]);
+    { uint64_t t[11]; for (int r = 0; r < 11; r++) { uint64_t a = 0; for (int c = 0; c < 11; c++) a = gl_add(a, gl_mul(st[c + 1], PFAST_INIT[r * 11 + c])); t[r] = a; }
+      for (int r = 0; r < 11; r++) st[r + 1] = t[r]; }
+    for (int r = 0; r < 22; r++) {
+        trace[65 + r - 12] = st[0];
+        st[0] = gl_add(w_sbox(st[0]), PFAST_K[r]);
+        uint64_t s0 = gl_mul(st[0], 25);
+        for (int j = 0; j < 11; j++) s0 = gl_add(s0, gl_mul(st[j + 1], PFAST_VROW[r * 11 + j]));
+        for (int j = 0; j < 11; j++) st[j + 1] = gl_add(st[j + 1], gl_mul(st[0], PFAST_WCOL[r * 11 + j]));
+        st[0] = s0;
+    }
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], W_RC[12 * (26 + r) + i]);
+        for (int i = 0; i < 12; i++) trace[87 + 12 * r + i - 12] = st[i];
+        for (int i = 0; i < 12; i++) st[i] = w_sbox(st[i]);
+        w_mds(st);
+    }
+    for (int i = 0; i < 12; i++) trace[i] = st[i];         // outputs, wires 12..23
+}
+
 struct p2w_program {
     p2w_program_desc d;
     std::vector<int32_t> ops; std::vector<uint64_t> op_consts;
@@ -15,6 +61,7 @@ struct p2w_program {
     std::vector<int64_t> fixed_pos; std::vector<uint64_t> fixed_val;
     std::vector<int32_t> lookup_counts, lookup_slots, lookup_padding, lookup_off;
     std::vector<int64_t> mult_pos;
+    std::vector<int32_t> poseidon_rows;
 };
 
 extern "C" int32_t p2w_program_create(const p2w_program_desc* d, p2w_program** out) {
@@ -42,6 +89,7 @@ extern "C" int32_t p2w_program_create(const p2w_program_desc* d, p2w_program** o
     for (uint32_t i = 0; i < d->num_luts; i++) { p->lookup_off.push_back((int32_t)totl); totl += d->lookup_counts[i]; }
     p->lookup_slots.assign(d->lookup_slots, d->lookup_slots + totl);
     p->mult_pos.assign(d->mult_pos, d->mult_pos + tot);
+    if (d->num_poseidon) p->poseidon_rows.assign(d->poseidon_rows, d->poseidon_rows + (size_t)25 * d->num_poseidon);
     *out = p;
     return 0;
 }
@@ -58,6 +106,7 @@ extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, c
     const p2w_program_desc& d = p->d;
     std::vector<uint64_t> val(d.num_slots, 0);
     std::vector<uint8_t> has(d.num_slots, 0);
+    std::vector<uint64_t> ptrace((size_t)123 * d.num_poseidon);
     int rc;
     for (uint32_t i = 0; i < num_inputs; i++) {
         if (in_slots[i] < 0 || (uint32_t)in_slots[i] >= d.num_slots || in_vals[i] >= GL_P) return P2W_E_BADARG;
@@ -90,6 +139,15 @@ extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, c
         case P2W_OP_CONST:
             if ((rc = set_slot(val, has, op[1], oc[0]))) return rc;
             break;
+        case P2W_OP_POSEIDON: {
+            if (op[1] < 0 || (uint32_t)op[1] >= d.num_poseidon) return P2W_E_BADARG;
+            const int32_t* pr = p->poseidon_rows.data() + (size_t)25 * op[1];
+            uint64_t in[12];
+            for (int i = 0; i < 12; i++) { if (!has[pr[1 + i]]) return P2W_E_UNSET; in[i] = val[pr[1 + i]]; }
+            uint64_t* tr = ptrace.data() + (size_t)123 * op[1];
+            w_poseidon_gate(in, tr);
+            for (int i = 0; i < 12; i++) if ((rc = set_slot(val, has, pr[13 + i], tr[i]))) return rc;
+            break; }
         default: return P2W_E_BADARG;
         }
     }
@@ -97,6 +155,10 @@ extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, c
     const int32_t* ws = p->wire_slot.data();
     for (size_t i = 0; i < cells; i++) wires[i] = ws[i] >= 0 ? val[ws[i]] : 0;
     for (uint32_t i = 0; i < d.num_fixed; i++) wires[p->fixed_pos[i]] = p->fixed_val[i];
+    for (uint32_t k = 0; k < d.num_poseidon; k++) {       // internal wires of every PoseidonGate row
+        const size_t row = (size_t)p->poseidon_rows[(size_t)25 * k];
+        for (int c = 24; c < 135; c++) wires[(size_t)c * n + row] = ptrace[(size_t)123 * k + c - 12];
+    }
     // set_lookup_wires: multiplicities
     for (uint32_t l = 0; l < d.num_luts; l++) {
         std::vector<uint64_t> mult(p->lut_lens[l], 0);

@@ -32,9 +32,10 @@ GATE_META = {
     GATE_CONSTANT: (1, "ConstantGate { num_consts: 2 }"),
     GATE_PUBLIC_INPUT: (1, "PublicInputGate"),
     GATE_ARITHMETIC: (3, "ArithmeticGate { num_ops: 20 }"),
+    GATE_POSEIDON: (7, "PoseidonGate(PhantomData<GoldilocksField>)<WIDTH=12>"),
 }
 UNUSED_SELECTOR = (1 << 32) - 1
-OP_ARITH, OP_LOOKUP, OP_EQ, OP_CONST = 0, 1, 2, 3
+OP_ARITH, OP_LOOKUP, OP_EQ, OP_CONST, OP_POSEIDON = 0, 1, 2, 3, 4
 
 
 @dataclass
@@ -106,6 +107,7 @@ class CircuitBuilder:
         self.luts = []             # list of list[(inp, out)]
         self.lut_to_lookups = []   # per LUT: [(inp target, out target)]
         self.public_inputs = []
+        self.poseidon_rows = []    # (row, [12 input wire targets], [12 output wire targets])
         self.ops_per_arith_row = self.config.num_routed_wires // 4
 
     # ---- targets -----------------------------------------------------------------------
@@ -233,6 +235,37 @@ class CircuitBuilder:
         self.connect(not_equal.target, not_equal_check)
         self.connect(diff_normalized, zero)
         return equal
+
+    # ---- Poseidon (gadgets/hash.rs: permute / hash_n_to_hash_no_pad) ----------------------------
+    def permute(self, state):
+        """One PoseidonGate row (swap wire tied to zero); returns the 12 output wire targets."""
+        assert len(state) == 12
+        row = self.add_gate(GATE_POSEIDON)
+        self.connect(self.zero(), wire(row, 24))
+        ins = [wire(row, i) for i in range(12)]
+        outs = [wire(row, 12 + i) for i in range(12)]
+        for t, w in zip(state, ins):
+            self.connect(t, w)
+        self.ops.append((OP_POSEIDON, len(self.poseidon_rows), 0, 0, 0, 0, 0, 0))
+        self.poseidon_rows.append((row, ins, outs))
+        return outs
+
+    def hash_n_to_m_no_pad(self, inputs, m):
+        state = [self.zero()] * 12
+        for k in range(0, len(inputs), 8):
+            chunk = inputs[k:k + 8]
+            state = list(chunk) + state[len(chunk):]
+            state = self.permute(state)
+        out = []
+        while True:
+            for t in state[:8]:
+                out.append(t)
+                if len(out) == m:
+                    return out
+            state = self.permute(state)
+
+    def hash_n_to_hash_no_pad(self, inputs):
+        return self.hash_n_to_m_no_pad(inputs, 4)
 
     # ---- lookups (gadgets/lookup.rs) ---------------------------------------------------------
     def add_lookup_table_from_pairs(self, pairs):
@@ -412,7 +445,7 @@ class CircuitData:
         self.gate_kinds = kinds
         gate_arr = (ffi.Gate * len(kinds))()
         ncons = {GATE_NOOP: 0, GATE_LOOKUP: 0, GATE_LOOKUP_TABLE: 0, GATE_CONSTANT: cfg.num_constants,
-                 GATE_PUBLIC_INPUT: 4, GATE_ARITHMETIC: b.ops_per_arith_row}
+                 GATE_PUBLIC_INPUT: 4, GATE_ARITHMETIC: b.ops_per_arith_row, GATE_POSEIDON: 123}
         for i, k in enumerate(kinds):
             s, e = groups[sel_of[i]]
             gate_arr[i] = ffi.Gate(k, sel_of[i], s, e, ncons[k], b.ops_per_arith_row if k == GATE_ARITHMETIC else cfg.num_constants)
@@ -510,6 +543,9 @@ class CircuitData:
         prog[:, 0] = kinds
         prog[:, 1] = slots(ops[:, 1])
         prog[:, 2] = slots(ops[:, 2])
+        mp = kinds == OP_POSEIDON
+        prog[mp, 1] = ops[mp, 1]            # index into the PoseidonGate row table, not a target
+        prog[mp, 2] = 0
         for col in (3, 4):
             m = (kinds == OP_ARITH) | (kinds == OP_EQ)
             prog[m, col] = slots(ops[m, col])
@@ -525,7 +561,7 @@ class CircuitData:
         ws = so[nv + wt].astype(np.int32)
         counts = np.bincount(so, minlength=self.num_slots)
         written = np.zeros(self.num_slots, dtype=bool)
-        written[prog[:, 1]] = True
+        written[prog[~mp, 1]] = True
         written[prog[kinds == OP_EQ, 2]] = True
         self._written = written
         self._w_wire_slot = np.ascontiguousarray(ws)
@@ -537,6 +573,9 @@ class CircuitData:
         self._w_lookup_slots = slots(ls).astype(np.int32) if ls else np.zeros(1, dtype=np.int32)
         self._w_lookup_padding = np.array([r[3] for r in lookup_rows] or [0], dtype=np.int32)
         self._w_mult_pos = np.array([c * n + r for row in lookup_rows for (r, c) in row[4]] or [0], dtype=np.int64)
+        pr = [[row] + [int(v) for v in slots(ins)] + [int(v) for v in slots(outs)] for (row, ins, outs) in b.poseidon_rows]
+        self._w_poseidon = np.array(pr or [[0] * 25], dtype=np.int32)
+        self._w_num_poseidon = len(pr)
         self._w_lut_lens = np.array([len(l) for l in b.luts] or [0], dtype=np.int32)
         self._w_lut_data = np.array([v for l in b.luts for pr in l for v in pr] or [0], dtype=np.uint16)
         self._wprog = None
@@ -560,13 +599,13 @@ class CircuitData:
                             ("num_wires", C.c_uint32), ("log_n", C.c_uint32), ("wire_slot", C.c_void_p),
                             ("num_fixed", C.c_uint32), ("fixed_pos", C.c_void_p), ("fixed_val", C.c_void_p),
                             ("lookup_counts", C.c_void_p), ("lookup_slots", C.c_void_p), ("lookup_padding", C.c_void_p),
-                            ("mult_pos", C.c_void_p)]
+                            ("mult_pos", C.c_void_p), ("num_poseidon", C.c_uint32), ("poseidon_rows", C.c_void_p)]
             d = Desc(self.num_slots, len(self._w_ops), self._w_ops.ctypes.data, self._w_consts.ctypes.data,
                      len(self.luts), self._w_lut_lens.ctypes.data, self._w_lut_data.ctypes.data,
                      NUM_WIRES, self.degree_bits, self._w_wire_slot.ctypes.data,
                      self._w_num_fixed, self._w_fixed_pos.ctypes.data, self._w_fixed_val.ctypes.data,
                      self._w_lookup_counts.ctypes.data, self._w_lookup_slots.ctypes.data, self._w_lookup_padding.ctypes.data,
-                     self._w_mult_pos.ctypes.data)
+                     self._w_mult_pos.ctypes.data, self._w_num_poseidon, self._w_poseidon.ctypes.data)
             self._wlib = self._witness_lib()
             h = C.c_void_p()
             rc = self._wlib.p2w_program_create(C.byref(d), C.byref(h))

@@ -76,3 +76,30 @@ def gcm_inputs(tg, seed, count):
         ct, tagv = native.gcm_encrypt(key, nonce, pt)
         rows.append(tg.input_values(key, nonce, pt, ct, tagv))
     return np.array(rows, dtype=np.uint64)
+
+
+@functools.lru_cache(maxsize=None)
+def feistel_poseidon(nr=32, half=4, key_len=4, seed=7):
+    """feistel_poseidon_check (/root/reference/feistel/src/circuit.rs:113-153): NR=32 rounds,
+    Poseidon round function, seeded instead of thread_rng inputs"""
+    from plonky2_aes_b200.host.gadgets import feistel, poseidon_native
+    b = CircuitBuilder()
+    st = feistel.add_feistel_state_target(b, 2 * half)
+    ks = [b.add_virtual_targets(key_len) for _ in range(nr)]
+    out = feistel.feistel_cipher_target(b, st, ks, lambda bb, t: bb.hash_n_to_hash_no_pad(t))
+    data = b.build()
+    rng = np.random.default_rng(seed)
+    P = 0xFFFFFFFF00000001
+    state = [int(v) for v in rng.integers(0, P, size=2 * half, dtype=np.uint64)]
+    keys = [[int(v) for v in rng.integers(0, P, size=key_len, dtype=np.uint64)] for _ in range(nr)]
+    exp = feistel.feistel_cipher(state, keys, poseidon_native.hash_n_to_hash_no_pad)
+    assert feistel.feistel_inv_cipher(exp, keys[::-1], poseidon_native.hash_n_to_hash_no_pad) == state
+    pw = PartialWitness()
+    for t, v in zip(st, state):
+        pw.set_target(t, v)
+    for kt, kv in zip(ks, keys):
+        for t, v in zip(kt, kv):
+            pw.set_target(t, v)
+    for t, v in zip(out, exp):
+        pw.set_target(t, v)
+    return data, data.generate_witness(pw), (st, ks, out, state, keys, exp)

@@ -78,6 +78,12 @@ def test_aes_gcm_256_tag_c2(gpu_ctx, oracle):
     _check(gpu_ctx, oracle, data, wires).free()
 
 
+def test_feistel_poseidon_gate(gpu_ctx, oracle):
+    """config 3 (Feistel half): PoseidonGate constraints in the quotient kernel, two selector groups."""
+    data, wires, _ = circuits.feistel_poseidon()
+    _check(gpu_ctx, oracle, data, wires).free()
+
+
 def test_stage_helpers(gpu_ctx, oracle):
     rng = np.random.default_rng(3)
     # proof-of-work grind: lowest nonce

@@ -94,3 +94,26 @@ def test_aes_gcm_tag_circuit(oracle):
     assert np.array_equal(many[1], data.generate_witness(pw))
     assert oc.verify(oc.prove(many[2])) == 0
     oc.free()
+
+
+def test_feistel_poseidon_circuit(oracle):
+    """config 3 (Feistel half): 32 PoseidonGate rows — feistel_poseidon_check,
+    /root/reference/feistel/src/circuit.rs:113-153, and the native round trip lib.rs:98-120."""
+    data, wires, (st, ks, out, state, keys, exp) = circuits.feistel_poseidon()
+    assert data.num_selectors == 2 and data.num_gate_constraints == 123
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    assert oc.verify(oc.prove(wires)) == 0
+    # wrong expected output is refused by the witness generator (prove() -> Err)
+    pw = PartialWitness()
+    for t, v in zip(st, state):
+        pw.set_target(t, v)
+    for kt, kv in zip(ks, keys):
+        for t, v in zip(kt, kv):
+            pw.set_target(t, v)
+    pw.set_target(out[0], (exp[0] + 1) % P)
+    with pytest.raises(ValueError):
+        data.generate_witness(pw)
+    # a forged S-box wire inside a PoseidonGate row is caught by the verifier
+    w2 = wires.copy(); w2[70, 3] ^= 1
+    assert oc.verify(oc.prove(w2)) == -20
+    oc.free()
