@@ -117,3 +117,20 @@ def test_feistel_poseidon_circuit(oracle):
     w2 = wires.copy(); w2[70, 3] ^= 1
     assert oc.verify(oc.prove(w2)) == -20
     oc.free()
+
+
+def test_proof_views_and_byte_round_trip(oracle):
+    from plonky2_aes_b200.host.proof import Proof
+    data, wires, _ = circuits.aes_gcm(13, True)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    words, tr, _, _ = oc.prove(wires, debug=True)
+    pr = Proof(words, data.descriptor())
+    assert pr.pow_witness == tr.pow_witness
+    assert pr["wires_cap"].size == 64 and pr["openings.wires"].size == 270
+    assert int(pr["fri.query[0].initial[1].path_len"][0]) == data.degree_bits + 3 - 4
+    raw = pr.to_bytes()
+    n_paths = data.config.fri_config.num_query_rounds * (4 + len(data.reduction_arity_bits))
+    assert len(raw) == 8 * (len(words) - n_paths) + n_paths
+    back = Proof.from_bytes(raw, data.descriptor())
+    assert np.array_equal(back.words, words) and oc.verify(back.words) == 0
+    oc.free()
