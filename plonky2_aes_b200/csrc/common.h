@@ -21,7 +21,8 @@ enum { NTT_KIND_LDE = 0, NTT_KIND_INV = 1 };
 struct NttPlan {
     int kind, log_n, log_m, log_r, log_variants;
     gl_t* T;    // [variants][R][R][M]
-    gl_t* tw;   // w_M^k (forward) or w_M^-k (inverse), k < M/2
+    gl_t* tw;   // per-pass compact twiddle tables (forward or inverse roots), tw_words entries
+    int tw_words;
 };
 int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream_t st);
 void ntt_plan_free(NttPlan* plan);

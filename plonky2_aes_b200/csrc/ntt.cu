@@ -21,6 +21,8 @@ __device__ __forceinline__ uint32_t smpad(uint32_t i) { return i + (i >> 4); }
 
 // K butterfly stages on 2^K register-resident points.  DIF: (a,b) -> (a+b, (a-b)*w).
 // log_b = log2 of the block size at the first stage of this pass.
+// tw: this pass's twiddles in shared memory, tw[p] = w_B^p for p < B/2 (B = block size at the
+// first stage of the pass); stage u needs w_{B>>u}^p = tw[p << u].
 template <int K>
 __device__ __forceinline__ void dif_pass(gl_t* sm, int log_m, int log_b, const gl_t* __restrict__ tw,
                                          uint32_t tid, uint32_t nthreads) {
@@ -37,12 +39,11 @@ __device__ __forceinline__ void dif_pass(gl_t* sm, int log_m, int log_b, const g
 #pragma unroll
         for (int u = 0; u < K; u++) {
             const int half = E >> (u + 1);            // in units of i
-            const int tw_shift = log_m - (log_b - u); // twiddle index scale: M / B_u
 #pragma unroll
             for (int i = 0; i < E; i++) {
                 if ((i & half) == 0) {
                     uint32_t p = lowpos + ((uint32_t)(i & (half - 1)) << log_s);  // position of the lower point in its block
-                    gl_t w = __ldg(tw + ((size_t)p << tw_shift));
+                    gl_t w = tw[p << u];
                     gl_t x = a[i], y = a[i + half];
                     a[i] = gl_add(x, y);
                     a[i + half] = gl_mul(gl_sub(x, y), w);
@@ -66,6 +67,16 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const gl_t* x = in + (size_t)col * in_stride;
     const gl_t* Tq = T + ((size_t)(variant * R + q) << log_n);   // [k][t]
+    // per-pass twiddle tables live behind the data in shared memory (global/L2 twiddle loads were
+    // the dominant stall of this kernel: long_scoreboard 3.0 per issue, profiles/)
+    gl_t* tws = sm + M + (M >> 4) + 1;
+    {
+        uint32_t total = 0;
+        int lb = log_m, rem0 = log_m & 3;
+        if (rem0) { total += 1u << (lb - 1); lb -= rem0; }
+        while (lb > 0) { total += 1u << (lb - 1); lb -= 4; }
+        for (uint32_t i = tid; i < total; i += nth) tws[i] = __ldg(tw + i);
+    }
 
     // load + fold: y[t] = sum_k x[t + kM] * T[k][t]
     for (uint32_t t = tid; t < M; t += nth) {
@@ -78,11 +89,16 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
 
     int log_b = log_m;
     int rem = log_m & 3;
-    if (rem == 1) { dif_pass<1>(sm, log_m, log_b, tw, tid, nth); log_b -= 1; __syncthreads(); }
-    else if (rem == 2) { dif_pass<2>(sm, log_m, log_b, tw, tid, nth); log_b -= 2; __syncthreads(); }
-    else if (rem == 3) { dif_pass<3>(sm, log_m, log_b, tw, tid, nth); log_b -= 3; __syncthreads(); }
+    const gl_t* twp = tws;
+    if (rem) {
+        if (rem == 1) dif_pass<1>(sm, log_m, log_b, twp, tid, nth);
+        else if (rem == 2) dif_pass<2>(sm, log_m, log_b, twp, tid, nth);
+        else dif_pass<3>(sm, log_m, log_b, twp, tid, nth);
+        twp += 1u << (log_b - 1); log_b -= rem; __syncthreads();
+    }
     while (log_b > 0) {
-        dif_pass<4>(sm, log_m, log_b, tw, tid, nth);
+        dif_pass<4>(sm, log_m, log_b, twp, tid, nth);
+        twp += 1u << (log_b - 1);
         log_b -= 4;
         __syncthreads();
     }
@@ -120,7 +136,21 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
             for (size_t j = 0; j < n; j++) { dst[j] = x; x = gl_mul(x, base); }
         }
     }
-    { gl_t x = 1; for (size_t k = 0; k < M / 2; k++) { tw[k] = x; x = gl_mul(x, wm); } if (M / 2 == 0) tw[0] = 1; }
+    {   // per-pass compact twiddle tables, in pass order: w_B^p, p < B/2
+        tw.clear();
+        int lb = plan->log_m, rem0 = plan->log_m & 3;
+        auto push = [&](int logb) {
+            gl_t wb = gl_root_of_unity(logb);
+            if (kind == NTT_KIND_INV) wb = gl_inv(wb);
+            gl_t x = 1;
+            for (size_t k = 0; k < ((size_t)1 << (logb - 1)); k++) { tw.push_back(x); x = gl_mul(x, wb); }
+        };
+        if (rem0) { push(lb); lb -= rem0; }
+        while (lb > 0) { push(lb); lb -= 4; }
+        if (tw.empty()) tw.push_back(1);
+        plan->tw_words = (int)tw.size();
+        (void)wm;
+    }
     if (cudaMalloc(&plan->T, T.size() * sizeof(gl_t)) != cudaSuccess) return -1;
     if (cudaMalloc(&plan->tw, tw.size() * sizeof(gl_t)) != cudaSuccess) return -1;
     if (cudaMemcpyAsync(plan->T, T.data(), T.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
@@ -134,9 +164,9 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
                int ncols, int out_mode, cudaStream_t st) {
     static bool attr_set = false;
     const size_t M = (size_t)1 << plan->log_m;
-    size_t smem = (M + (M >> 4) + 1) * sizeof(gl_t);
+    size_t smem = (M + (M >> 4) + 1 + (size_t)plan->tw_words) * sizeof(gl_t);
     if (!attr_set) {
-        if (cudaFuncSetAttribute(ntt_dif_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(ntt_dif_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
         attr_set = true;
     }
     uint32_t threads = (uint32_t)(M >> 4);

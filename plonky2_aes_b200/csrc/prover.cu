@@ -339,7 +339,13 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = ctx_alloc(ctx, &d_qv, (size_t)nch * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_qa, (size_t)nch * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_qc, (size_t)nch * N))) return rc;
-    P2G_COUNT_LAUNCH(1); quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
+    {
+        bool has_pos = false;
+        for (const auto& g : C->gates) has_pos |= g.kind == P2G_GATE_POSEIDON;
+        P2G_COUNT_LAUNCH(1);
+        if (has_pos) quotient_kernel<true><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
+        else quotient_kernel<false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
+    }
     CU(cudaGetLastError());
     {
         const NttPlan* inv;

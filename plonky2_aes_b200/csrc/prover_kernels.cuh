@@ -348,6 +348,7 @@ lut_eval_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const uint16_
     if (threadIdx.x == 0) out[ch * 8 + lut] = sm[0];
 }
 
+template <bool HAS_POSEIDON>
 __global__ void __launch_bounds__(128)
 quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ lut_evals, const p2g_gate* __restrict__ gates,
                 const gl_t* __restrict__ cs, const gl_t* __restrict__ wl, const gl_t* __restrict__ zl,
@@ -491,7 +492,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             if (k < 4 && f_pi) v = gl_add(v, gl_mul(f_pi, gl_sub(wl[(size_t)k * N + j], pc->pi_hash[k])));
             return v;
         };
-        if (has_poseidon) {
+        if (HAS_POSEIDON && has_poseidon) {
             gl_t a0 = acc[0], a1 = acc[1];
             const int tbase = t;
             poseidon_gate_constraints(wl, N, j, [&](int k, gl_t cval) {
