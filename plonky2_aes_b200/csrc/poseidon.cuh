@@ -82,46 +82,61 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 // which IMAD.WIDE does not (profiles/r1_int_pipes_microbench.jsonl: dfma+iadd3 2.08 cyc/pair,
 // imad.wide+iadd3 5.3).  Accumulators start at 2^52 + round constant, so the integer result can
 // be read straight out of the mantissa with no conversion instruction.
-__device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
+// SBOX_ALL: apply the S-box to every word right before it enters the accumulation (full rounds),
+// so the IMAD/IADD3 work of word i+1 overlaps the DFMAs of word i inside one warp.
+// Otherwise (partial rounds) only word 0 goes through the S-box and it is accumulated LAST, so
+// the 264 DFMAs of the other words hide the latency of that dependent multiply chain.
+template <bool SBOX_ALL>
+__device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
-    const double MAGIC = 4503599627370496.0;   // 2^52
-    // u32 -> f64 with I2F (conversion pipe) rather than the magic-number DADD: measured +4.5 %
-#define POS_CVT(u) ((double)(u))
-    (void)MAGIC;
-    uint32_t al0[12], al1[12];
-    {
-        double acc[12];
+    double al[12], ah[12];
 #pragma unroll
-        for (int r = 0; r < 12; r++) acc[r] = POSEIDON_RCD_LO[12 * next_row + r];
+    for (int r = 0; r < 12; r++) { al[r] = POSEIDON_RCD_LO[12 * next_row + r]; ah[r] = POSEIDON_RCD_HI[12 * next_row + r]; }
 #pragma unroll
-        for (int i = 0; i < 12; i++) {
-            const double x = POS_CVT((uint32_t)s[i]);
-#pragma unroll
-            for (int r = 0; r < 12; r++) acc[r] = __fma_rn(x, C[(i - r + 12) % 12], acc[r]);
-            if (i == 0) acc[0] = __fma_rn(x, 8., acc[0]);
-        }
-#pragma unroll
-        for (int r = 0; r < 12; r++) { al0[r] = (uint32_t)__double2loint(acc[r]); al1[r] = (uint32_t)__double2hiint(acc[r]) & 0xFFFFFu; }
-    }
-    {
-        double acc[12];
-#pragma unroll
-        for (int r = 0; r < 12; r++) acc[r] = POSEIDON_RCD_HI[12 * next_row + r];
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            const double x = POS_CVT((uint32_t)(s[i] >> 32));
-#pragma unroll
-            for (int r = 0; r < 12; r++) acc[r] = __fma_rn(x, C[(i - r + 12) % 12], acc[r]);
-            if (i == 0) acc[0] = __fma_rn(x, 8., acc[0]);
-        }
+    for (int ii = 0; ii < 12; ii++) {
+        const int i = SBOX_ALL ? ii : (ii + 1) % 12;            // 1, 2, ..., 11, 0
+        const gl_t v = (SBOX_ALL || i == 0) ? poseidon_sbox(s[i]) : s[i];
+        const double xl = (double)(uint32_t)v, xh = (double)(uint32_t)(v >> 32);   // I2F: conversion pipe
 #pragma unroll
         for (int r = 0; r < 12; r++) {
-            // value = al + ah * 2^32 with al, ah < 2^43
-            const uint32_t ah0 = (uint32_t)__double2loint(acc[r]), ah1 = (uint32_t)__double2hiint(acc[r]) & 0xFFFFFu;
-            uint32_t m, t;
-            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1[r]), "r"(ah0), "r"(ah1));
-            s[r] = gl_fold3(al0[r], m, t);
+            al[r] = __fma_rn(xl, C[(i - r + 12) % 12], al[r]);
+            ah[r] = __fma_rn(xh, C[(i - r + 12) % 12], ah[r]);
         }
+        if (i == 0) { al[0] = __fma_rn(xl, 8., al[0]); ah[0] = __fma_rn(xh, 8., ah[0]); }
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        // accumulators are 2^52 + integer (< 2^43): the integer sits in the low mantissa bits
+        const uint32_t al0 = (uint32_t)__double2loint(al[r]), al1 = (uint32_t)__double2hiint(al[r]) & 0xFFFFFu;
+        const uint32_t ah0 = (uint32_t)__double2loint(ah[r]), ah1 = (uint32_t)__double2hiint(ah[r]) & 0xFFFFFu;
+        uint32_t m, t;
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
+        s[r] = gl_fold3(al0, m, t);
+    }
+}
+// MDS only (used by the PoseidonGate constraint evaluator, where the S-box inputs are wires)
+__device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    double al[12], ah[12];
+#pragma unroll
+    for (int r = 0; r < 12; r++) { al[r] = POSEIDON_RCD_LO[12 * next_row + r]; ah[r] = POSEIDON_RCD_HI[12 * next_row + r]; }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const double xl = (double)(uint32_t)s[i], xh = (double)(uint32_t)(s[i] >> 32);
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            al[r] = __fma_rn(xl, C[(i - r + 12) % 12], al[r]);
+            ah[r] = __fma_rn(xh, C[(i - r + 12) % 12], ah[r]);
+        }
+        if (i == 0) { al[0] = __fma_rn(xl, 8., al[0]); ah[0] = __fma_rn(xh, 8., ah[0]); }
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        const uint32_t al0 = (uint32_t)__double2loint(al[r]), al1 = (uint32_t)__double2hiint(al[r]) & 0xFFFFFu;
+        const uint32_t ah0 = (uint32_t)__double2loint(ah[r]), ah1 = (uint32_t)__double2hiint(ah[r]) & 0xFFFFFu;
+        uint32_t m, t;
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
+        s[r] = gl_fold3(al0, m, t);
     }
 }
 __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonical
@@ -139,15 +154,12 @@ __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
     for (int phase = 0; phase < 2; phase++) {
 #pragma unroll 1
         for (int r = 0; r < 4; r++, k++) {
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(s[i]);
-            poseidon_mds_rc(s, k + 1);
+            poseidon_round<true>(s, k + 1);
         }
         if (phase == 0) {
 #pragma unroll 1
             for (int r = 0; r < 22; r++, k++) {
-                s[0] = poseidon_sbox(s[0]);
-                poseidon_mds_rc(s, k + 1);
+                poseidon_round<false>(s, k + 1);
             }
         }
     }
