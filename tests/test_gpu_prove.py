@@ -124,3 +124,25 @@ def test_stage_helpers(gpu_ctx, oracle):
     nv = np.stack([oracle.coset_fft(folded[:, 0], nshift), oracle.coset_fft(folded[:, 1], nshift)], axis=1)
     rev2 = np.array([int(format(i, f"0{log_len - ab}b")[::-1], 2) for i in range(ln >> ab)])
     assert np.array_equal(out, nv[rev2])
+
+
+def test_error_behaviour(gpu_ctx, oracle):
+    """argument errors come back as codes (no crash, no fallback): the C ABI's contract."""
+    lib = gpu_ctx.lib
+    h = C.c_void_p()
+    cols = np.zeros((1, 8), dtype=np.uint64)
+    assert lib.p2g_commit_from_values(gpu_ctx.handle, cols.ctypes.data, 0, 3, 3, 4, C.byref(h), None) == -2   # no columns
+    assert lib.p2g_commit_from_values(gpu_ctx.handle, cols.ctypes.data, 1, 3, 3, 9, C.byref(h), None) == -2   # cap above the tree
+    assert lib.p2g_commit_from_values(gpu_ctx.handle, None, 1, 3, 3, 4, C.byref(h), None) == -2
+    data, wires = circuits.tiny_arith()
+    data.load(gpu_ctx)
+    # a configuration the prover does not implement is refused at load time
+    desc = data.descriptor()
+    desc.rate_bits = 2
+    assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(desc), C.byref(h), None) == -2
+    # proof buffer too small
+    out = np.zeros(16, dtype=np.uint64)
+    got = C.c_size_t()
+    assert lib.p2g_prove(gpu_ctx.handle, data._gpu_circuit, wires.ctypes.data, None, out.ctypes.data, out.size, C.byref(got)) == -2
+    # the context is still usable afterwards
+    assert oracle_lib.OracleCircuit(oracle, data).verify(data.prove_wires(wires)) == 0
