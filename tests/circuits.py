@@ -70,10 +70,18 @@ def aes_gcm(L=16, tag=True):
 def gcm_inputs(tg, seed, count):
     """`count` random (key, nonce, pt) with their ct/tag as witness input rows"""
     rows = []
+    try:                                   # same ct || tag as gadgets/native.py (tested), much faster
+        from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+    except ImportError:
+        AESGCM = None
     for i in range(count):
         raw = np.random.default_rng(seed + i).bytes(28 + tg.L)
         key, nonce, pt = raw[:16], raw[16:28], raw[28:]
-        ct, tagv = native.gcm_encrypt(key, nonce, pt)
+        if AESGCM is not None and tg.nk == 4:
+            out = AESGCM(key).encrypt(nonce, pt, None)
+            ct, tagv = out[:-16], out[-16:]
+        else:
+            ct, tagv = native.gcm_encrypt(key, nonce, pt)
         rows.append(tg.input_values(key, nonce, pt, ct, tagv))
     return np.array(rows, dtype=np.uint64)
 

@@ -78,6 +78,22 @@ def test_aes_gcm_256_tag_c2(gpu_ctx, oracle):
     _check(gpu_ctx, oracle, data, wires).free()
 
 
+def test_aes256_gcm_and_no_tag_variants(gpu_ctx, oracle):
+    """AES-256 key schedule (NK=8, NR=14) and the TAG=false alias (`AesGcm128Target`, lib.rs:19)."""
+    from plonky2_aes_b200.host.circuit_builder import CircuitBuilder, PartialWitness
+    from plonky2_aes_b200.host.gadgets import native
+    from plonky2_aes_b200.host.gadgets.gcm import AesGcmTarget
+    for nk, nr, L, tag in ((8, 14, 17, True), (4, 10, 42, False)):
+        b = CircuitBuilder()
+        tg = AesGcmTarget(b, nk, nr, L, tag)
+        data = b.build()
+        key, nonce, pt = bytes(range(4 * nk)), bytes([111] * 12), bytes([231] * L)
+        ct, tagv = native.gcm_encrypt(key, nonce, pt, nk=nk, nr=nr)
+        pw = PartialWitness()
+        tg.set_targets(pw, key, nonce, pt, ct, tagv)
+        _check(gpu_ctx, oracle, data, data.generate_witness(pw)).free()
+
+
 def test_feistel_poseidon_gate(gpu_ctx, oracle):
     """config 3 (Feistel half): PoseidonGate constraints in the quotient kernel, two selector groups."""
     data, wires, _ = circuits.feistel_poseidon()
