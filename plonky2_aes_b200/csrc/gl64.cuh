@@ -70,9 +70,10 @@ __device__ __forceinline__ gl_t gl_mulw(uint32_t a, uint32_t b) { gl_t r; asm("m
 __device__ __forceinline__ void gl_fold3w(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t& w0, uint32_t& w1) {
     gl_t v;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(v) : "r"(h0), "r"(GL_EPS_DEV), "l"(gl_pack(l0, l1)));
-    uint32_t v0, v1; gl_unpack(v, v0, v1);
-    uint32_t c = v1 < l1 ? 0xffffffffu : 0u;
-    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(w0), "=&r"(w1) : "r"(v0), "r"(c), "r"(v1));
+    gl_unpack(v, w0, w1);
+    // wrapped past 2^64  <=>  high word went down: add EPS with a predicated carry pair (no SEL)
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.cc.u32 %0, %0, 0xffffffff;\n\t@p addc.u32 %1, %1, 0;\n\t}"
+        : "+r"(w0), "+r"(w1) : "r"(l1));
 }
 __device__ __forceinline__ gl_t gl_fold3(uint32_t l0, uint32_t l1, uint32_t h0) {
     uint32_t w0, w1; gl_fold3w(l0, l1, h0, w0, w1);

@@ -86,6 +86,9 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 // so the IMAD/IADD3 work of word i+1 overlaps the DFMAs of word i inside one warp.
 // Otherwise (partial rounds) only word 0 goes through the S-box and it is accumulated LAST, so
 // the 264 DFMAs of the other words hide the latency of that dependent multiply chain.
+// accumulators start at 2^52 + constant: the integer sits in the low mantissa bits (an F2I readout
+// from plain-constant accumulators was measured slower: 0.96 vs 0.99 G perm/s)
+#define POS_READ(d, w0, w1) do { w0 = (uint32_t)__double2loint(d); w1 = (uint32_t)__double2hiint(d) & 0xFFFFFu; } while (0)
 template <bool SBOX_ALL>
 __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
@@ -107,8 +110,8 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
 #pragma unroll
     for (int r = 0; r < 12; r++) {
         // accumulators are 2^52 + integer (< 2^43): the integer sits in the low mantissa bits
-        const uint32_t al0 = (uint32_t)__double2loint(al[r]), al1 = (uint32_t)__double2hiint(al[r]) & 0xFFFFFu;
-        const uint32_t ah0 = (uint32_t)__double2loint(ah[r]), ah1 = (uint32_t)__double2hiint(ah[r]) & 0xFFFFFu;
+        uint32_t al0, al1, ah0, ah1;
+        POS_READ(al[r], al0, al1); POS_READ(ah[r], ah0, ah1);
         uint32_t m, t;
         asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
         s[r] = gl_fold3(al0, m, t);
@@ -132,8 +135,8 @@ __device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        const uint32_t al0 = (uint32_t)__double2loint(al[r]), al1 = (uint32_t)__double2hiint(al[r]) & 0xFFFFFu;
-        const uint32_t ah0 = (uint32_t)__double2loint(ah[r]), ah1 = (uint32_t)__double2hiint(ah[r]) & 0xFFFFFu;
+        uint32_t al0, al1, ah0, ah1;
+        POS_READ(al[r], al0, al1); POS_READ(ah[r], ah0, ah1);
         uint32_t m, t;
         asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
         s[r] = gl_fold3(al0, m, t);
