@@ -78,12 +78,32 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
         for (uint32_t i = tid; i < total; i += nth) tws[i] = __ldg(tw + i);
     }
 
-    // load + fold: y[t] = sum_k x[t + kM] * T[k][t]
-    for (uint32_t t = tid; t < M; t += nth) {
-        gl_t acc = gl_mul(__ldg(x + t), __ldg(Tq + t));
-        for (uint32_t k = 1; k < R; k++)
-            acc = gl_add(acc, gl_mul(__ldg(x + t + ((size_t)k << log_m)), __ldg(Tq + ((size_t)k << log_m) + t)));
-        sm[smpad(t)] = acc;
+    // load + fold: y[t] = sum_k x[t + kM] * T[k][t].  All loads of a batch of 8 points are issued
+    // before any arithmetic so that one block per SM still keeps ~32 loads per thread in flight
+    // (the kernel was stalled on these loads: long_scoreboard 3.0 per issue).
+    if (R <= 2 && (M % (8 * nth)) == 0) {
+        for (uint32_t t0 = tid; t0 < M; t0 += 8 * nth) {
+            gl_t xv[8][2], tv[8][2];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t t = t0 + u * nth;
+                xv[u][0] = __ldg(x + t); tv[u][0] = __ldg(Tq + t);
+                if (R == 2) { xv[u][1] = __ldg(x + t + M); tv[u][1] = __ldg(Tq + M + t); }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                gl_t acc = gl_mul(xv[u][0], tv[u][0]);
+                if (R == 2) acc = gl_add(acc, gl_mul(xv[u][1], tv[u][1]));
+                sm[smpad(t0 + u * nth)] = acc;
+            }
+        }
+    } else {
+        for (uint32_t t = tid; t < M; t += nth) {
+            gl_t acc = gl_mul(__ldg(x + t), __ldg(Tq + t));
+            for (uint32_t k = 1; k < R; k++)
+                acc = gl_add(acc, gl_mul(__ldg(x + t + ((size_t)k << log_m)), __ldg(Tq + ((size_t)k << log_m) + t)));
+            sm[smpad(t)] = acc;
+        }
     }
     __syncthreads();
 
