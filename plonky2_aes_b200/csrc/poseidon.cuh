@@ -210,23 +210,65 @@ __device__ __forceinline__ gl_t poseidon_coop(gl_t x, uint32_t l, uint32_t group
 // ------------------------------------------------------------------------------------------
 // host implementation (transcript only: a few hundred permutations per proof)
 // ------------------------------------------------------------------------------------------
+// Host permutation (Fiat-Shamir transcript: ~170 permutations per proof, on the critical path
+// between kernels).  Branch-free reductions, MDS on 32-bit halves, sparse partial rounds.
+namespace p2g_host {
+#define PFAST_QUAL static const
+#include "poseidon_fast.inc"
+#undef PFAST_QUAL
+inline gl_t red128(unsigned __int128 x) {
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    uint64_t hh = hi >> 32, hl = hi & GL_EPS;
+    uint64_t t0 = lo - hh; t0 -= GL_EPS & (0 - (uint64_t)(lo < hh));
+    uint64_t t1 = hl * GL_EPS, t2 = t0 + t1;
+    t2 += GL_EPS & (0 - (uint64_t)(t2 < t1));
+    t2 -= GL_P & (0 - (uint64_t)(t2 >= GL_P));
+    return t2;
+}
+inline gl_t mul(gl_t a, gl_t b) { return red128((unsigned __int128)a * b); }
+inline gl_t add(gl_t a, gl_t b) { uint64_t s = a + b; return s - (GL_P & (0 - ((uint64_t)(s < a) | (uint64_t)(s >= GL_P)))); }
+inline gl_t sbox(gl_t x) { gl_t x2 = mul(x, x), x4 = mul(x2, x2), x3 = mul(x, x2); return mul(x3, x4); }
+inline void mds(gl_t s[12]) {
+    static const uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t lo[24], hi[24];
+    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = (uint32_t)s[i]; hi[i] = hi[i + 12] = (uint32_t)(s[i] >> 32); }
+    uint64_t al[12] = {0}, ah[12] = {0};
+    for (int i = 0; i < 12; i++)
+        for (int r = 0; r < 12; r++) { al[r] += (uint64_t)lo[i + r] * C[i]; ah[r] += (uint64_t)hi[i + r] * C[i]; }
+    al[0] += (uint64_t)lo[0] * 8; ah[0] += (uint64_t)hi[0] * 8;
+    for (int r = 0; r < 12; r++) s[r] = red128((unsigned __int128)al[r] + ((unsigned __int128)ah[r] << 32));
+}
+inline gl_t dot11(const gl_t* a, const gl_t* b, unsigned __int128 init) {
+    unsigned __int128 accl = init, acch = 0;
+    for (int j = 0; j < 11; j++) {
+        accl += (unsigned __int128)a[j] * (uint32_t)b[j];
+        acch += (unsigned __int128)a[j] * (uint32_t)(b[j] >> 32);
+    }
+    return add(red128(accl), mul(red128(acch), (gl_t)1 << 32));
+}
+}  // namespace p2g_host
 inline void poseidon_permute(gl_t s[12]) {
-    static const uint64_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    for (int r = 0; r < 30; r++) {
-        const bool full = r < 4 || r >= 26;
-        for (int i = 0; i < 12; i++) s[i] = gl_add(gl_canon(s[i]), POSEIDON_RC_HOST[12 * r + i]);
-        for (int i = 0; i < (full ? 12 : 1); i++) {
-            gl_t x = s[i], x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x, x2);
-            s[i] = gl_mul(x3, x4);
-        }
-        gl_t o[12];
-        for (int q = 0; q < 12; q++) {
-            unsigned __int128 acc = 0;
-            for (int i = 0; i < 12; i++) acc += (unsigned __int128)s[(i + q) % 12] * C[i];
-            if (q == 0) acc += (unsigned __int128)s[0] * 8;
-            o[q] = gl_canon(gl_reduce128_lazy((gl_t)acc, (gl_t)(acc >> 64)));
-        }
-        for (int i = 0; i < 12; i++) s[i] = o[i];
+    using namespace p2g_host;
+    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox(add(s[i], POSEIDON_RC_HOST[12 * r + i]));
+        mds(s);
+    }
+    for (int i = 0; i < 12; i++) s[i] = add(s[i], PFAST_FIRST_C[i]);
+    {
+        gl_t t[11];
+        for (int r = 0; r < 11; r++) t[r] = dot11(PFAST_INIT + r * 11, s + 1, 0);
+        for (int r = 0; r < 11; r++) s[r + 1] = t[r];
+    }
+    for (int r = 0; r < 22; r++) {
+        gl_t t = add(sbox(s[0]), PFAST_K[r]);
+        gl_t s0 = dot11(PFAST_VROW + r * 11, s + 1, (unsigned __int128)t * 25);
+        for (int j = 0; j < 11; j++) s[j + 1] = add(s[j + 1], mul(PFAST_WCOL[r * 11 + j], t));
+        s[0] = s0;
+    }
+    for (int r = 26; r < 30; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox(add(s[i], POSEIDON_RC_HOST[12 * r + i]));
+        mds(s);
     }
 }
 inline void poseidon_permute_lazy(gl_t s[12]) { poseidon_permute(s); }
