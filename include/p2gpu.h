@@ -56,6 +56,13 @@ int32_t p2g_commit_from_values_dev(p2g_ctx* ctx, const uint64_t* cols_dev, uint3
                                    uint32_t rate_bits, uint32_t cap_height, p2g_batch** out, uint64_t* cap_out);
 int32_t p2g_commit_from_coeffs_dev(p2g_ctx* ctx, const uint64_t* cols_dev, uint32_t ncols, uint32_t log_n,
                                    uint32_t rate_bits, uint32_t cap_height, p2g_batch** out, uint64_t* cap_out);
+/* Multi-GPU split of ONE commitment (coset sharding): this rank extends and hashes only the leaf blocks
+ * [blk_first, blk_first + blk_count) of the 2^rate_bits cosets (block b = coset bitrev(b), a contiguous run of n
+ * Merkle leaves).  cap_part_out receives this shard's 2^cap_height * blk_count / 2^rate_bits cap entries; the
+ * ranks all-gather them (NCCL) in block order to obtain MerkleTree::new(...).cap.  blk_count: power of two. */
+int32_t p2g_commit_blocks_from_values_dev(p2g_ctx* ctx, const uint64_t* cols_dev, uint32_t ncols, uint32_t log_n,
+                                          uint32_t rate_bits, uint32_t cap_height, uint32_t blk_first, uint32_t blk_count,
+                                          p2g_batch** out, uint64_t* cap_part_out);
 int32_t p2g_batch_free(p2g_ctx* ctx, p2g_batch* b);
 /* read-back (parity tests, query phase). */
 int32_t p2g_batch_get_coeffs(p2g_ctx* ctx, const p2g_batch* b, uint64_t* out /*[ncols][n]*/);

@@ -66,10 +66,14 @@ int ctx_alloc(p2g_ctx* ctx, gl_t** p, size_t words) {
 void ctx_free(p2g_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->st); }
 
 int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
-               uint32_t cap_height, bool from_values, p2g_batch** out, bool sync_cap) {
-    if (!ncols || log_n > 22 || log_n + rate_bits > 26 || cap_height > log_n + rate_bits) return P2G_E_BADARG;
+               uint32_t cap_height, bool from_values, p2g_batch** out, bool sync_cap, uint32_t blk_first, uint32_t blk_count) {
+    if (blk_count == 0) { blk_first = 0; blk_count = 1u << rate_bits; }
+    uint32_t blk_log = 0; while ((1u << blk_log) < blk_count) blk_log++;
+    if ((1u << blk_log) != blk_count || blk_first % blk_count || blk_first + blk_count > (1u << rate_bits)) return P2G_E_BADARG;
+    if (!ncols || log_n > 22 || log_n + rate_bits > 26 || cap_height > log_n + blk_log) return P2G_E_BADARG;
     p2g_batch* b = new p2g_batch();
     b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->blk_first = blk_first; b->blk_log = blk_log;
     b->coeffs = b->lde = b->digests = b->cap = nullptr;
     const size_t n = b->n(), N = b->N();
     int rc;
@@ -89,7 +93,7 @@ int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_
     }
     if (tim) cudaEventRecord(ev[1], ctx->st);
     if ((rc = ctx_get_plan(ctx, NTT_KIND_LDE, log_n, rate_bits, &lde))) return rc;
-    if (ntt_launch(lde, b->coeffs, n, b->lde, N, ncols, 0, ctx->st)) { ctx->err = "lde launch"; return P2G_E_CUDA; }
+    if (ntt_launch(lde, b->coeffs, n, b->lde, N, ncols, 0, ctx->st, blk_first, blk_count)) { ctx->err = "lde launch"; return P2G_E_CUDA; }
     if (tim) cudaEventRecord(ev[2], ctx->st);
     if (merkle_build(b->lde, 1, N, ncols, b->log_N(), cap_height, b->digests, b->cap, ctx->st)) { ctx->err = "merkle launch"; return P2G_E_CUDA; }
     if (tim) {
@@ -141,6 +145,18 @@ extern "C" int32_t p2g_commit_from_values_dev(p2g_ctx* ctx, const uint64_t* c, u
 extern "C" int32_t p2g_commit_from_coeffs_dev(p2g_ctx* ctx, const uint64_t* c, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
                                               uint32_t cap_height, p2g_batch** out, uint64_t* cap_out) {
     return commit_any(ctx, c, false, false, ncols, log_n, rate_bits, cap_height, out, cap_out);
+}
+extern "C" int32_t p2g_commit_blocks_from_values_dev(p2g_ctx* ctx, const uint64_t* cols_dev, uint32_t ncols, uint32_t log_n,
+                                                     uint32_t rate_bits, uint32_t cap_height, uint32_t blk_first, uint32_t blk_count,
+                                                     p2g_batch** out, uint64_t* cap_part_out) {
+    if (!ctx || !cols_dev || !out || blk_count == 0) return P2G_E_BADARG;
+    uint32_t blk_log = 0; while ((1u << blk_log) < blk_count) blk_log++;
+    if (cap_height + blk_log < rate_bits) return P2G_E_BADARG;      // a shard must own whole cap entries
+    CU(cudaSetDevice(ctx->device));
+    int rc = commit_dev(ctx, cols_dev, ncols, log_n, rate_bits, cap_height + blk_log - rate_bits, true, out, true, blk_first, blk_count);
+    if (rc) return rc;
+    if (cap_part_out) memcpy(cap_part_out, (*out)->cap_host.data(), (*out)->cap_host.size() * sizeof(gl_t));
+    return P2G_OK;
 }
 extern "C" int32_t p2g_last_commit_timings(p2g_ctx* ctx, float out[3]) {
     if (!ctx || !out) return P2G_E_BADARG;

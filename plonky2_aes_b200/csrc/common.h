@@ -29,8 +29,10 @@ void ntt_plan_free(NttPlan* plan);
 // out_mode 0: block (variant,q) writes M contiguous words at out[col*out_stride + bitrev(variant)*n + q*M]
 //             (bit-reversed order: the layout MerkleTree leaves and the quotient kernel use)
 // out_mode 1: natural order, out[col*out_stride + f] (variants must be 1)
+// blk_first / blk_count: only the output blocks (cosets in leaf order) [blk_first, blk_first + blk_count) are
+// produced, into out[col*out_stride + (b - blk_first)*n ...]; blk_count = 0 means all
 int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out, size_t out_stride,
-               int ncols, int out_mode, cudaStream_t st);
+               int ncols, int out_mode, cudaStream_t st, uint32_t blk_first = 0, uint32_t blk_count = 0);
 
 // ---- Merkle (merkle.cu) -------------------------------------------------------------------
 // Leaves are read either column-major (element c of leaf j at data[c*col_stride + j]) or

@@ -9,14 +9,15 @@
 
 struct p2g_batch {
     uint32_t ncols, log_n, rate_bits, cap_height;
+    uint32_t blk_first, blk_log;   // leaf blocks held: [blk_first, blk_first + 2^blk_log) of the 2^rate_bits cosets
     gl_t* coeffs;    // [ncols][n]  natural coefficient order
     gl_t* lde;       // [ncols][N]  column-major, bit-reversed point order (== Merkle leaf order)
     gl_t* digests;   // tree levels 0..L-1
     gl_t* cap;       // [2^cap_height][4] device
     std::vector<gl_t> cap_host;
     size_t n() const { return (size_t)1 << log_n; }
-    size_t N() const { return (size_t)1 << (log_n + rate_bits); }
-    uint32_t log_N() const { return log_n + rate_bits; }
+    size_t N() const { return (size_t)1 << (log_n + blk_log); }          // leaves held by this batch
+    uint32_t log_N() const { return log_n + blk_log; }
     uint32_t path_len() const { return log_N() - cap_height; }
 };
 
@@ -45,5 +46,8 @@ int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan
 int ctx_alloc(p2g_ctx* ctx, gl_t** p, size_t words);
 void ctx_free(p2g_ctx* ctx, void* p);
 // builds coefficients (optional inverse NTT), LDE and Merkle tree for device-resident columns
+// blk_count = 0: the whole LDE domain.  Otherwise only leaf blocks [blk_first, blk_first + blk_count) are
+// extended and hashed; cap_height then counts the levels below this shard's subtree roots.
 int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
-               uint32_t cap_height, bool from_values, p2g_batch** out, bool sync_cap);
+               uint32_t cap_height, bool from_values, p2g_batch** out, bool sync_cap,
+               uint32_t blk_first = 0, uint32_t blk_count = 0);

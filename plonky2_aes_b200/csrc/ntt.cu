@@ -58,11 +58,14 @@ __device__ __forceinline__ void dif_pass(gl_t* sm, int log_m, int log_b, const g
 __global__ void __launch_bounds__(512, 1)
 ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__ out, size_t out_stride,
                const gl_t* __restrict__ T, const gl_t* __restrict__ tw,
-               int log_n, int log_m, int log_variants, int out_mode) {
+               int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first) {
     extern __shared__ gl_t sm[];
     const int log_r = log_n - log_m;
     const uint32_t M = 1u << log_m, R = 1u << log_r;
-    const uint32_t variant = blockIdx.x >> log_r, q = blockIdx.x & (R - 1);
+    // output block b (a contiguous run of n leaves) holds coset variant bitrev(b); a launch may cover
+    // only blocks [blk_first, blk_first + gridDim.x / R) (multi-GPU coset sharding)
+    const uint32_t blk_local = blockIdx.x >> log_r, q = blockIdx.x & (R - 1);
+    const uint32_t variant = out_mode == 0 ? gl_bitrev(blk_first + blk_local, log_variants) : blk_local;
     const uint32_t col = blockIdx.y;
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     const gl_t* x = in + (size_t)col * in_stride;
@@ -125,7 +128,7 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
 
     gl_t* o = out + (size_t)col * out_stride;
     if (out_mode == 0) {
-        size_t base = ((size_t)gl_bitrev(variant, log_variants) << log_n) + ((size_t)q << log_m);
+        size_t base = ((size_t)blk_local << log_n) + ((size_t)q << log_m);
         for (uint32_t m = tid; m < M; m += nth) o[base + m] = sm[smpad(m)];
     } else {
         uint32_t qr = gl_bitrev(q, log_r);
@@ -181,7 +184,7 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
 void ntt_plan_free(NttPlan* plan) { cudaFree(plan->T); cudaFree(plan->tw); plan->T = plan->tw = nullptr; }
 
 int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out, size_t out_stride,
-               int ncols, int out_mode, cudaStream_t st) {
+               int ncols, int out_mode, cudaStream_t st, uint32_t blk_first, uint32_t blk_count) {
     static bool attr_set = false;
     const size_t M = (size_t)1 << plan->log_m;
     size_t smem = (M + (M >> 4) + 1 + (size_t)plan->tw_words) * sizeof(gl_t);
@@ -194,10 +197,11 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
     if (threads > 512) threads = 512;
     for (int c0 = 0; c0 < ncols; c0 += 65535) {
         int nc = ncols - c0 < 65535 ? ncols - c0 : 65535;
-        dim3 grid((1u << plan->log_variants) << plan->log_r, nc);
+        if (blk_count == 0) blk_count = 1u << plan->log_variants;
+        dim3 grid(blk_count << plan->log_r, nc);
         ntt_dif_kernel<<<grid, threads, smem, st>>>(in + (size_t)c0 * in_stride, in_stride, out + (size_t)c0 * out_stride,
                                                     out_stride, plan->T, plan->tw, plan->log_n, plan->log_m,
-                                                    plan->log_variants, out_mode);
+                                                    plan->log_variants, out_mode, blk_first);
         P2G_COUNT_LAUNCH(1);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

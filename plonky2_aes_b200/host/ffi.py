@@ -72,6 +72,7 @@ SIGNATURES = {
     "p2g_commit_from_coeffs": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp), _vp]),
     "p2g_commit_from_values_dev": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp), _vp]),
     "p2g_commit_from_coeffs_dev": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp), _vp]),
+    "p2g_commit_blocks_from_values_dev": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp), _vp]),
     "p2g_batch_free": (C.c_int32, [_vp, _vp]),
     "p2g_batch_get_coeffs": (C.c_int32, [_vp, _vp, _vp]),
     "p2g_batch_get_lde": (C.c_int32, [_vp, _vp, _vp]),

@@ -86,3 +86,31 @@ class BatchProver:
         if errors:
             raise errors[0]
         return out
+
+
+def sharded_commit(ctx, dev_cols, ncols, log_n, rank, world, dist=None, rate_bits=3, cap_height=4):
+    """One PolynomialBatch commitment split over `world` GPUs by coset.
+
+    Every rank holds the column values (they are inputs of the proof on every rank), runs the
+    cheap inverse NTT redundantly, then extends and Merkle-hashes only its 2^rate_bits / world
+    leaf blocks.  The only exchange is the all-gather of each rank's cap entries (64 B .. 512 B),
+    after which every rank knows MerkleTree::new(...).cap.  Returns (cap, handle)."""
+    import ctypes as C
+    import numpy as np
+    nblk = 1 << rate_bits
+    assert nblk % world == 0, "world size must divide the number of cosets"
+    per = nblk // world
+    h = C.c_void_p()
+    part = np.empty(((1 << cap_height) * per // nblk, 4), dtype=np.uint64)
+    ptr = dev_cols.data_ptr() if hasattr(dev_cols, "data_ptr") else int(dev_cols)
+    ctx.check(ctx.lib.p2g_commit_blocks_from_values_dev(ctx.handle, ptr, ncols, log_n, rate_bits, cap_height,
+                                                        rank * per, per, C.byref(h), part.ctypes.data))
+    if world == 1 or dist is None:
+        return part, h
+    import torch
+    dev = torch.device("cuda", ctx.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.from_numpy(part.view(np.int64)).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    cap = torch.cat(parts).cpu().numpy().view(np.uint64)
+    return cap, h

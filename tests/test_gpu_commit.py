@@ -99,3 +99,27 @@ def test_hash_and_merkle_helpers(gpu_ctx, oracle):
     # poseidon KAT through the device: hash of 8 zeros = permutation(0)[0..4]
     z = gpu_ctx.hash_no_pad_many(np.zeros((1, 8), dtype=np.uint64))
     assert [hex(int(v)) for v in z[0]] == ['0x3c18a9786cb0b359', '0xc4055e3364a246c3', '0x7953db0ab48808f4', '0xc71603f33a1144ca']
+
+
+def test_coset_sharded_commit_matches_full(gpu_ctx, oracle):
+    """multi-GPU coset split of one commitment, emulated on one GPU: every shard's LDE block and cap
+    entries equal the corresponding slice of the full commitment (and of the oracle's)."""
+    import ctypes as C
+    import torch
+    from plonky2_aes_b200.host.sharding import sharded_commit
+    cols = _cols(77, 20, 10)
+    ob = oracle.batch(cols, True)
+    dev = torch.from_numpy(cols.view(np.int64)).cuda()
+    N = 8 << 10
+    for world in (1, 2, 4, 8):
+        caps = []
+        for rank in range(world):
+            part, h = sharded_commit(gpu_ctx, dev, 20, 10, rank, world)
+            caps.append(part)
+            per = 8 // world
+            lde = np.empty((20, per << 10), dtype=np.uint64)
+            gpu_ctx.check(gpu_ctx.lib.p2g_batch_get_lde(gpu_ctx.handle, h, lde.ctypes.data))
+            assert np.array_equal(lde.T, ob.leaves()[rank * (N // world):(rank + 1) * (N // world)])
+            gpu_ctx.check(gpu_ctx.lib.p2g_batch_free(gpu_ctx.handle, h))
+        assert np.array_equal(np.concatenate(caps), ob.tree.cap), world
+    ob.free()
