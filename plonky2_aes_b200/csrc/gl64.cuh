@@ -127,11 +127,17 @@ GL_HD gl_t gl_inv(gl_t a) {
     gl_t t = a;                       // a^(2^1-1)
     gl_t x = a;
     // e31 = a^(2^31-1)
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int i = 1; i < 31; i++) { x = gl_sqr(x); x = gl_mul(x, a); }
     gl_t e31 = x;
     // a^(2^32-2) = e31^2 ; a^(2^32 - 1) not needed.  exponent p-2 = (2^31-1)*2^33 + (2^32-1)
     // = e31 << 33 | (2^32 - 1):  p-2 = 0xFFFFFFFE_FFFFFFFF = (2^31-1)<<33 + 2^32-1
     gl_t y = e31;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int i = 0; i < 33; i++) y = gl_sqr(y);
     gl_t e32 = gl_mul(gl_sqr(e31), a);  // a^(2^32-1)
     (void)t;

@@ -517,7 +517,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         for (int i = 0; i < pos; i++) ps.s[i] = ch.in_buf[i];
         unsigned long long* d_best;
         CU(cudaMallocFromPoolAsync((void**)&d_best, 8, ctx->pool, st));
-        const unsigned long long WIN = 1ull << 17;   // expected hit within 2^16 candidates; P(miss per window) = e^-2
+        const unsigned long long WIN = 1ull << 18;   // expected hit within 2^16 candidates; P(miss per window) = e^-4
         bool found = false;
         for (unsigned long long base = 0; !found && base < (1ull << 30); base += WIN) {
             CU(cudaMemsetAsync(d_best, 0xFF, 8, st));

@@ -11,6 +11,7 @@
 #define MAX_CH 2
 #define MAX_ROUTED 80
 
+
 // ---------------------------------------------------------------------------------------------
 // affine maps x -> a*x + b and their block-wide exclusive scan (prefix products, running sums,
 // the RE recurrence of the lookup argument are all instances)
@@ -95,6 +96,7 @@ zs_chunk_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
     for (int ck = 0; ck < nchunks; ck++) {
         gl_t np = 1, dp = 1;
         int lo = ck * cd.qdf, hi = min(lo + cd.qdf, cd.R);
+#pragma unroll 1
         for (int j = lo; j < hi; j++) {
             gl_t w = wires[(size_t)j * n + r];
             gl_t num = gl_add(gl_add(w, gl_mul(pc->beta_kis[ch][j], x)), gamma);
@@ -378,11 +380,13 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
     {
         gl_t prev[MAX_CH];
         for (int c = 0; c < nch; c++) prev[c] = zl[(size_t)c * N + j];
+#pragma unroll 1
         for (int ck = 0; ck <= cd.num_prods; ck++) {
             gl_t np[MAX_CH], dp[MAX_CH];
 #pragma unroll
             for (int c = 0; c < MAX_CH; c++) { np[c] = 1; dp[c] = 1; }
             int lo = ck * cd.qdf, hi = min(lo + cd.qdf, R);
+#pragma unroll 1
             for (int w = lo; w < hi; w++) {
                 gl_t wv = wl[(size_t)w * N + j], sv = cs[(size_t)(cd.NC + w) * N + j];
 #pragma unroll
@@ -408,6 +412,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
         const gl_t* lsel = cs + (size_t)cd.num_sel * N;       // lookup selector columns
         const gl_t s_trans_sre = lsel[0 * N + j], s_trans_ldc = lsel[1 * N + j], s_init = lsel[2 * N + j], s_last = lsel[3 * N + j];
         const int n_lookup_terms = 4 + cd.num_luts + 2 * cd.num_sldc;
+#pragma unroll 1
         for (int c = 0; c < nch; c++) {
             const gl_t da = pc->deltas[c][0], db = pc->deltas[c][1], dalpha = pc->deltas[c][2], ddelta = pc->deltas[c][3];
             const gl_t* lz = zl + (size_t)(zpp + c * cd.nlp) * N;
@@ -420,6 +425,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
                 ADD_TERM(tb + 3 + r, gl_mul(lsel[(size_t)(4 + r) * N + j], gl_sub(z_re, lut_evals[c * 8 + r])));
             gl_t re_cur = next_z_re;
             const int tt = tb + 4 + cd.num_luts;   // index of the first per-poly term (after RE transition at tt-1)
+#pragma unroll 1
             for (int poly = 0; poly < cd.num_sldc; poly++) {
                 gl_t fl[8], fu[8];
                 int a0 = poly * cd.lut_degree, a1 = min(a0 + cd.lut_degree, cd.lut_slots);
@@ -502,6 +508,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             });
             acc[0] = a0; acc[1] = a1;
         } else {
+#pragma unroll 1
             for (int k = 0; k < cd.num_gate_constraints; k++) ADD_TERM(t + k, small_gates(k));
         }
     }
