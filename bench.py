@@ -248,7 +248,10 @@ def main():
         poseidon_peak = ctx.poseidon_peak(32)
         roof = {"bound": "hbm", "kernel": "merkle_leaves_kernel (Poseidon leaf sponge + in-block tree levels)",
                 "achieved": merkle_bytes / merkle_ms / 1e6, "peak": peak, "unit": "GB/s",
-                "frac": merkle_bytes / merkle_ms / 1e6 / peak, "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
+                "frac": merkle_bytes / merkle_ms / 1e6 / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
+                # profiles/r1_kernels_final_ncu_summary.txt (284.5 MB + 12.9 MB; algorithmic 308 MB)
+                "traffic": 297.5e6, "algorithmic_bytes": merkle_bytes, "peak_kind": peak_kind + " copy bandwidth",
                 "int_pipe": {"perms_per_s": perms / merkle_ms * 1e3, "peak_perms_per_s": poseidon_peak,
                              "frac": perms / merkle_ms * 1e3 / poseidon_peak,
                              "note": "Poseidon is INT-pipe bound (63 B of input per permutation); peak = chained "
