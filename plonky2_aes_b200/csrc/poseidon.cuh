@@ -89,6 +89,63 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 // accumulators start at 2^52 + constant: the integer sits in the low mantissa bits (an F2I readout
 // from plain-constant accumulators was measured slower: 0.96 vs 0.99 G perm/s)
 #define POS_READ(d, w0, w1) do { w0 = (uint32_t)__double2loint(d); w1 = (uint32_t)__double2hiint(d) & 0xFFFFFu; } while (0)
+#ifndef P2G_MDS_SPLIT
+#define P2G_MDS_SPLIT 1
+#endif
+#if P2G_MDS_SPLIT
+// Split-circulant form of the same layer.  The MDS matrix is circ(C) (+ 8 on entry [0][0]), i.e.
+// [[A, B], [B, A]] in 6x6 blocks, so with X+ = x_lo + x_hi and X- = x_lo - x_hi (word halves j, j+6)
+//     y_lo = ((A+B)/2) X+  +  ((A-B)/2) X-,      y_hi = ((A+B)/2) X+  -  ((A-B)/2) X-
+// which is 72 products per 32-bit half instead of 144 (204 FP64-pipe instructions per round
+// instead of 290).  (A+-B)/2 are multiples of 1/2, so the two accumulators are biased by 2^51
+// (ulp 1/2, POSEIDON_RCS_*): every partial sum stays exact, acc+ + acc- lands in [2^52, 2^53)
+// as 2^52 + integer, and acc+ - acc- is a plain non-negative integer that gets its 2^52 added.
+template <bool SBOX_ALL>
+__device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    double apl[6], aml[6], aph[6], amh[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        apl[r] = POSEIDON_RCS_LO[12 * next_row + r]; aml[r] = POSEIDON_RCS_LO[12 * next_row + 6 + r];
+        aph[r] = POSEIDON_RCS_HI[12 * next_row + r]; amh[r] = POSEIDON_RCS_HI[12 * next_row + 6 + r];
+    }
+#pragma unroll
+    for (int jj = 0; jj < 6; jj++) {
+        const int j = SBOX_ALL ? jj : (jj + 1) % 6;             // pair (0, 6) last in partial rounds
+        const gl_t v0 = (SBOX_ALL || j == 0) ? poseidon_sbox(s[j]) : s[j];
+        const gl_t v1 = SBOX_ALL ? poseidon_sbox(s[j + 6]) : s[j + 6];
+        const double x0l = (double)(uint32_t)v0, x0h = (double)(uint32_t)(v0 >> 32);
+        const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
+        const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
+        const double ph = __dadd_rn(x0h, x1h), mh = __dsub_rn(x0h, x1h);
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const double a = C[(j - r + 12) % 12], b = C[(j + 6 - r + 12) % 12];
+            const double P = 0.5 * (a + b), N = 0.5 * (a - b);
+            apl[r] = __fma_rn(pl, P, apl[r]); aml[r] = __fma_rn(ml, N, aml[r]);
+            aph[r] = __fma_rn(ph, P, aph[r]); amh[r] = __fma_rn(mh, N, amh[r]);
+        }
+        if (j == 0) {                                            // + 8 x_0 on row 0 only
+            apl[0] = __fma_rn(x0l, 4., apl[0]); aml[0] = __fma_rn(x0l, 4., aml[0]);
+            aph[0] = __fma_rn(x0h, 4., aph[0]); amh[0] = __fma_rn(x0h, 4., amh[0]);
+        }
+    }
+    const double BIAS = 4503599627370496.0;                      // 2^52
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        const double yl[2] = {__dadd_rn(apl[r], aml[r]), __dadd_rn(__dsub_rn(apl[r], aml[r]), BIAS)};
+        const double yh[2] = {__dadd_rn(aph[r], amh[r]), __dadd_rn(__dsub_rn(aph[r], amh[r]), BIAS)};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t al0, al1, ah0, ah1;
+            POS_READ(yl[h], al0, al1); POS_READ(yh[h], ah0, ah1);
+            uint32_t m, t;
+            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
+            s[r + 6 * h] = gl_fold3(al0, m, t);
+        }
+    }
+}
+#else
 template <bool SBOX_ALL>
 __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
@@ -117,6 +174,7 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
         s[r] = gl_fold3(al0, m, t);
     }
 }
+#endif
 // MDS only (used by the PoseidonGate constraint evaluator, where the S-box inputs are wires)
 __device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
