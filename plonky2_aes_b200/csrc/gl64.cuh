@@ -116,6 +116,24 @@ GL_HD gl_t gl_mul_lazy(gl_t a, gl_t b) {
 GL_HD gl_t gl_mul(gl_t a, gl_t b) { return gl_canon(gl_mul_lazy(a, b)); }
 GL_HD gl_t gl_sqr(gl_t a) { return gl_mul(a, a); }
 
+// canonical x -> canonical x * 2^K, 0 < K < 96, by shifts and the 2^64 = 2^32 - 1, 2^96 = -1 folds.
+// In Goldilocks 2 has order 192 and plonky2's roots of unity of order <= 64 are powers of two
+// (w_64 = 2^39, w_16 = 2^156 = -2^60, w_4 = 2^48), so the twiddles of the last NTT stages need no
+// general multiplication.
+template <int K>
+GL_HD gl_t gl_mul_pow2(gl_t x) {
+    static_assert(K > 0 && K < 96, "shift out of range");
+    if (K < 64) {
+        const int k = K < 64 ? K : 1;
+        return gl_canon(gl_reduce128_lazy(x << k, x >> (64 - k)));
+    } else {
+        // x 2^K = (A + B 2^64) 2^64 with A = low 64 bits of x << (K-64), B the bits above:
+        // A 2^64 folds as usual and B 2^128 = -B 2^32
+        const int j = K >= 64 ? K - 64 : 0;
+        const gl_t A = x << j, B = j ? x >> ((64 - j) & 63) : 0;
+        return gl_sub(gl_canon(gl_reduce128_lazy(0, A)), B << 32);
+    }
+}
 GL_HD gl_t gl_pow(gl_t b, uint64_t e) {
     gl_t r = 1;
     while (e) { if (e & 1) r = gl_mul(r, b); b = gl_sqr(b); e >>= 1; }

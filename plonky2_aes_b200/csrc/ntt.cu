@@ -55,10 +55,49 @@ __device__ __forceinline__ void dif_pass(gl_t* sm, int log_m, int log_b, const g
     }
 }
 
+// DIF butterfly with the twiddle w_16^(+-E0) = 2^(156 E mod 192) as a compile-time shift; shifts of
+// 96 and more are -2^(s-96), absorbed by swapping the operands of the subtraction.
+template <int E0, bool INV>
+__device__ __forceinline__ void bfly16(gl_t& x, gl_t& y) {
+    const gl_t a = x, b = y;
+    x = gl_add(a, b);
+    constexpr int E = INV ? (16 - E0) % 16 : E0;     // inverse transform: w_16^-E
+    constexpr int SH = (156 * E) % 192;
+    if (SH == 0) y = gl_sub(a, b);
+    else if (SH < 96) y = gl_mul_pow2<(SH > 0 && SH < 96) ? SH : 1>(gl_sub(a, b));
+    else y = gl_mul_pow2<(SH >= 97) ? SH - 96 : 1>(gl_sub(b, a));
+}
+// The last pass (block size 16, points contiguous): every twiddle is one of w_16^0..7, fixed by the
+// register index, so the 32 general multiplications and 32 twiddle loads of dif_pass<4> become
+// 15 plain butterflies and 17 shift-multiplies.
+template <bool INV>
+__device__ __forceinline__ void dif_pass_last16(gl_t* sm, int log_m, uint32_t tid, uint32_t nthreads) {
+    const uint32_t M = 1u << log_m;
+    for (uint32_t g = tid; g < (M >> 4); g += nthreads) {
+        const uint32_t base = g << 4;
+        gl_t a[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = sm[smpad(base + i)];
+        bfly16<0, INV>(a[0], a[8]);  bfly16<1, INV>(a[1], a[9]);  bfly16<2, INV>(a[2], a[10]); bfly16<3, INV>(a[3], a[11]);
+        bfly16<4, INV>(a[4], a[12]); bfly16<5, INV>(a[5], a[13]); bfly16<6, INV>(a[6], a[14]); bfly16<7, INV>(a[7], a[15]);
+#pragma unroll
+        for (int h = 0; h < 16; h += 8) {
+            bfly16<0, INV>(a[h + 0], a[h + 4]); bfly16<2, INV>(a[h + 1], a[h + 5]);
+            bfly16<4, INV>(a[h + 2], a[h + 6]); bfly16<6, INV>(a[h + 3], a[h + 7]);
+        }
+#pragma unroll
+        for (int h = 0; h < 16; h += 4) { bfly16<0, INV>(a[h], a[h + 2]); bfly16<4, INV>(a[h + 1], a[h + 3]); }
+#pragma unroll
+        for (int h = 0; h < 16; h += 2) bfly16<0, INV>(a[h], a[h + 1]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) sm[smpad(base + i)] = a[i];
+    }
+}
+
 __global__ void __launch_bounds__(512, 1)
 ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__ out, size_t out_stride,
                const gl_t* __restrict__ T, const gl_t* __restrict__ tw,
-               int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first) {
+               int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first, int inverse) {
     extern __shared__ gl_t sm[];
     const int log_r = log_n - log_m;
     const uint32_t M = 1u << log_m, R = 1u << log_r;
@@ -120,7 +159,8 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
         twp += 1u << (log_b - 1); log_b -= rem; __syncthreads();
     }
     while (log_b > 0) {
-        dif_pass<4>(sm, log_m, log_b, twp, tid, nth);
+        if (log_b == 4) { if (inverse) dif_pass_last16<true>(sm, log_m, tid, nth); else dif_pass_last16<false>(sm, log_m, tid, nth); }
+        else dif_pass<4>(sm, log_m, log_b, twp, tid, nth);
         twp += 1u << (log_b - 1);
         log_b -= 4;
         __syncthreads();
@@ -201,7 +241,7 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
         dim3 grid(blk_count << plan->log_r, nc);
         ntt_dif_kernel<<<grid, threads, smem, st>>>(in + (size_t)c0 * in_stride, in_stride, out + (size_t)c0 * out_stride,
                                                     out_stride, plan->T, plan->tw, plan->log_n, plan->log_m,
-                                                    plan->log_variants, out_mode, blk_first);
+                                                    plan->log_variants, out_mode, blk_first, plan->kind == NTT_KIND_INV ? 1 : 0);
         P2G_COUNT_LAUNCH(1);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
