@@ -18,16 +18,58 @@
 
 typedef uint64_t gl_t;
 
-GL_HD gl_t gl_canon(gl_t a) { return a >= GL_P ? a - GL_P : a; }
-
-// canonical + canonical -> canonical
-GL_HD gl_t gl_add(gl_t a, gl_t b) {
-    gl_t s = a + b;
-    return (s < a || s >= GL_P) ? s - GL_P : s;
+// Device forms are carry-chain PTX: the compiler's compare-and-select versions cost 8-11 SASS
+// instructions, most of them on the 16-lane ALU pipe, which is the pipe the NTT saturates
+// (profiles/r1_kernels_final_ncu_summary.txt: alu 71 %).
+GL_HD gl_t gl_canon(gl_t a) {
+#if defined(__CUDA_ARCH__)
+    // a >= p  <=>  a + (2^32 - 1) carries out of 64 bits (c = 1); then a - p = (low - 1, 0), and
+    // the high word is all ones, so both words are fixed by one independent add of -+c each
+    gl_t r;
+    asm("{\n\t.reg .u32 a0, a1, t, c;\n\t"
+        "mov.b64 {a0,a1}, %1;\n\t"
+        "add.cc.u32 t, a0, 0xffffffff;\n\taddc.cc.u32 t, a1, 0;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.u32 a0, a0, c;\n\tadd.u32 a1, a1, c;\n\t"
+        "mov.b64 %0, {a0,a1};\n\t}" : "=l"(r) : "l"(a));
+    return r;
+#else
+    return a >= GL_P ? a - GL_P : a;
+#endif
 }
+
+// canonical - canonical -> canonical  (device: also  any u64 - canonical -> same residue, any u64)
 GL_HD gl_t gl_sub(gl_t a, gl_t b) {
+#if defined(__CUDA_ARCH__)
+    // d = a - b; on borrow add p = 2^64 - 2^32 + 1, i.e. subtract the all-ones borrow mask from the
+    // low word and propagate: 5 carry-chain instructions, no compare, no select
+    gl_t d;
+    asm("{\n\t.reg .u32 a0, a1, b0, b1, m;\n\t"
+        "mov.b64 {a0,a1}, %1;\n\tmov.b64 {b0,b1}, %2;\n\t"
+        "sub.cc.u32 a0, a0, b0;\n\tsubc.cc.u32 a1, a1, b1;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 a0, a0, m;\n\tsubc.u32 a1, a1, 0;\n\t"
+        "mov.b64 %0, {a0,a1};\n\t}" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+#else
     gl_t d = a - b;
     return (a < b) ? d + GL_P : d;
+#endif
+}
+// canonical + canonical -> canonical
+GL_HD gl_t gl_add(gl_t a, gl_t b) {
+#if defined(__CUDA_ARCH__)
+    // a + b = a - (p - b): two more carry-chain instructions in front of gl_sub (p - 0 = p is fine)
+    gl_t d;
+    asm("{\n\t.reg .u32 a0, a1, b0, b1, m;\n\t"
+        "mov.b64 {a0,a1}, %1;\n\tmov.b64 {b0,b1}, %2;\n\t"
+        "sub.cc.u32 b0, 1, b0;\n\tsubc.u32 b1, 0xffffffff, b1;\n\t"
+        "sub.cc.u32 a0, a0, b0;\n\tsubc.cc.u32 a1, a1, b1;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 a0, a0, m;\n\tsubc.u32 a1, a1, 0;\n\t"
+        "mov.b64 %0, {a0,a1};\n\t}" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+#else
+    gl_t s = a + b;
+    return (s < a || s >= GL_P) ? s - GL_P : s;
+#endif
 }
 GL_HD gl_t gl_neg(gl_t a) { return a ? GL_P - a : 0; }
 
