@@ -256,11 +256,11 @@ def main():
                              "frac": perms / merkle_ms * 1e3 / poseidon_peak,
                              "note": "Poseidon is INT-pipe bound (63 B of input per permutation); peak = chained "
                                      "permutations without memory traffic (p2g_poseidon_peak)",
-                             # hardware-derived ceiling: the 30 x 288 exact multiply-adds of the MDS layers issue on
-                             # the FP64 pipe at one warp-instruction per 2.07 cycles per SM sub-partition
+                             # hardware-derived ceiling: the 30 x 204 FP64 instructions of the split-circulant MDS
+                             # layers issue at one warp-instruction per 2.07 cycles per SM sub-partition
                              # (profiles/r1_int_pipes_microbench.jsonl), the S-box multiplies overlap on the IMAD pipe
-                             "pipe_roofline_perms_per_s": 148 * 4 * 1.965e9 / 2.07 * 32 / 8640,
-                             "pipe_roofline_frac": perms / merkle_ms * 1e3 / (148 * 4 * 1.965e9 / 2.07 * 32 / 8640)},
+                             "pipe_roofline_perms_per_s": 148 * 4 * 1.965e9 / 2.07 * 32 / 6120,
+                             "pipe_roofline_frac": perms / merkle_ms * 1e3 / (148 * 4 * 1.965e9 / 2.07 * 32 / 6120)},
                 "lde": {"ms": lde_ms, "achieved": lde_bytes / lde_ms / 1e6, "frac": lde_bytes / lde_ms / 1e6 / peak},
                 "intt_ms": intt_ms, "merkle_ms": merkle_ms,
                 "lde_merkle_gbs": (136 * W + 768) * n / (intt_ms + lde_ms + merkle_ms) / 1e6}
