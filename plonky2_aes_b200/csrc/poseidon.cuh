@@ -200,6 +200,57 @@ __device__ __forceinline__ void poseidon_mds_rc(gl_t s[12], int next_row) {
         s[r] = gl_fold3(al0, m, t);
     }
 }
+// 2^52-biased (low, high) accumulator pair -> lazy residue
+__device__ __forceinline__ gl_t pos_readout(double l, double h) {
+    uint32_t al0, al1, ah0, ah1;
+    POS_READ(l, al0, al1); POS_READ(h, ah0, ah1);
+    uint32_t m, t;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
+    return gl_fold3(al0, m, t);
+}
+#ifndef P2G_PARTIAL_PAIRS
+#define P2G_PARTIAL_PAIRS 1
+#endif
+// Two consecutive partial rounds in one pass over the state.  With s' = (sbox(s0), s1..s11),
+//     t = M s' + cA,   u = M (sbox(t0), t1..t11) + cB
+// collapses to   u = A s' + col0(M) sbox(t0) + K,   t0 = row0(M) s' + cA_0,
+// A = M~ M (M~: M with column 0 zeroed) and K = M~ cA + cB precomputed (tools/gen_poseidon_f64.py,
+// which also checks the identity against the plain rounds).  The entries of A stay below 2^15, so
+// the products with 32-bit halves are still exact on the FP64 pipe (row sums < 2^49), and the 11
+// words that skip the S-box are read out of the accumulators and converted back once per TWO rounds:
+// 336 FP64 instructions and 13 readouts per pair instead of 408 and 24.
+__device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair) {
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    const double A[144] = POSEIDON_PAIR_A_INIT;
+    double al[12], ah[12];
+#pragma unroll
+    for (int r = 0; r < 12; r++) { al[r] = POSEIDON_PAIRK_LO[12 * pair + r]; ah[r] = POSEIDON_PAIRK_HI[12 * pair + r]; }
+    const int row_a = 5 + 2 * pair;                       // constants between the two rounds
+    double tl = POSEIDON_RCD_LO[12 * row_a], th = POSEIDON_RCD_HI[12 * row_a];
+    const gl_t y0 = poseidon_sbox(s[0]);
+#pragma unroll
+    for (int jj = 0; jj < 12; jj++) {
+        const int j = (jj + 1) % 12;                      // word 0 last: its S-box chain hides behind the others
+        const gl_t v = j == 0 ? y0 : s[j];
+        const double xl = (double)(uint32_t)v, xh = (double)(uint32_t)(v >> 32);
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            al[r] = __fma_rn(xl, A[12 * r + j], al[r]);
+            ah[r] = __fma_rn(xh, A[12 * r + j], ah[r]);
+        }
+        const double m0j = C[j] + (j == 0 ? 8. : 0.);
+        tl = __fma_rn(xl, m0j, tl); th = __fma_rn(xh, m0j, th);
+    }
+    const gl_t z0 = poseidon_sbox(pos_readout(tl, th));
+    const double zl = (double)(uint32_t)z0, zh = (double)(uint32_t)(z0 >> 32);
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        const double mr0 = C[(12 - r) % 12] + (r == 0 ? 8. : 0.);
+        al[r] = __fma_rn(zl, mr0, al[r]); ah[r] = __fma_rn(zh, mr0, ah[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = pos_readout(al[r], ah[r]);
+}
 __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonical
     gl_t s = a + c;
     return s < a ? s + GL_EPS : s;
@@ -218,10 +269,15 @@ __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
             poseidon_round<true>(s, k + 1);
         }
         if (phase == 0) {
+#if P2G_PARTIAL_PAIRS
+#pragma unroll 1
+            for (int p = 0; p < 11; p++, k += 2) poseidon_partial_pair(s, p);
+#else
 #pragma unroll 1
             for (int r = 0; r < 22; r++, k++) {
                 poseidon_round<false>(s, k + 1);
             }
+#endif
         }
     }
 }
