@@ -107,15 +107,17 @@ __device__ __forceinline__ void gl_unpack(gl_t x, uint32_t& lo, uint32_t& hi) { 
 __device__ __forceinline__ gl_t gl_pack(uint32_t lo, uint32_t hi) { gl_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 __device__ __forceinline__ gl_t gl_mulw(uint32_t a, uint32_t b) { gl_t r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
 
-// (l1:l0) + h0*2^64 -> lazy residue:  one IMAD.WIDE, then +EPS if the 64-bit sum wrapped
-// (h0*EPS <= 2^64 - 2^33 + 1, so a wrap always lowers the high word: one 32-bit compare)
+// (l1:l0) + h0*2^64 -> lazy residue.  h0*2^64 = h0*2^32 - h0: subtract h0 from the low word and add
+// it (minus the borrow) to the high word -- two carry-chain instructions instead of an IMAD.WIDE
+// whose 64-bit addend is never register-pair aligned here (ptxas split it into IMAD.WIDE + IADD3 +
+// IMAD.X).  The 64-bit sum wrapped  <=>  the high word went down: then add 2^64 = EPS once more
+// (the sum is below 2^64 + 2^64 - 2^33, so this cannot wrap again).
 __device__ __forceinline__ void gl_fold3w(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t& w0, uint32_t& w1) {
-    gl_t v;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(v) : "r"(h0), "r"(GL_EPS_DEV), "l"(gl_pack(l0, l1)));
-    gl_unpack(v, w0, w1);
-    // wrapped past 2^64  <=>  high word went down: add EPS with a predicated carry pair (no SEL)
-    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.cc.u32 %0, %0, 0xffffffff;\n\t@p addc.u32 %1, %1, 0;\n\t}"
-        : "+r"(w0), "+r"(w1) : "r"(l1));
+    asm("{\n\t.reg .u32 nh;\n\t.reg .pred p;\n\t"
+        "neg.s32 nh, %4;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, nh;\n\t"
+        "setp.lt.u32 p, %1, %3;\n\t@p add.cc.u32 %0, %0, 0xffffffff;\n\t@p addc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(w0), "=&r"(w1) : "r"(l0), "r"(l1), "r"(h0));
 }
 __device__ __forceinline__ gl_t gl_fold3(uint32_t l0, uint32_t l1, uint32_t h0) {
     uint32_t w0, w1; gl_fold3w(l0, l1, h0, w0, w1);

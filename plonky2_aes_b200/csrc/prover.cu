@@ -48,6 +48,7 @@ struct p2g_circuit {
     gl_t* d_sigmas;           // [R][n] values on H
     gl_t* d_subgroup;         // g^i
     gl_t* d_domain;           // x_j = 7 w_N^bitrev(j)
+    gl_t* d_l0inv;            // 1 / (n (x_j - 1))
     gl_t* d_qtable;           // [8][n]: h_s^(-j)/8
     gl_t* d_small;            // w8inv_pows[8], shift_n_inv_pows[8]
     p2g_gate* d_gates;
@@ -138,6 +139,8 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
     if ((rc = ctx_alloc(ctx, &C->d_domain, N))) return rc;
     P2G_COUNT_LAUNCH(1); domain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(cd.logn, gl_root_of_unity(cd.logn), 1, C->d_subgroup, 0);
     P2G_COUNT_LAUNCH(1); domain_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->st>>>(logN, gl_root_of_unity(logN), 7, C->d_domain, 1);
+    if ((rc = ctx_alloc(ctx, &C->d_l0inv, N))) return rc;
+    P2G_COUNT_LAUNCH(1); l0inv_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->st>>>(N, (gl_t)n, C->d_domain, C->d_l0inv);
     CU(cudaGetLastError());
     // quotient coefficient recovery tables
     {
@@ -188,7 +191,7 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
 extern "C" int32_t p2g_circuit_free(p2g_ctx* ctx, p2g_circuit* C) {
     if (!ctx || !C) return P2G_E_BADARG;
     p2g_batch_free(ctx, C->cs);
-    ctx_free(ctx, C->d_sigmas); ctx_free(ctx, C->d_subgroup); ctx_free(ctx, C->d_domain); ctx_free(ctx, C->d_qtable);
+    ctx_free(ctx, C->d_sigmas); ctx_free(ctx, C->d_subgroup); ctx_free(ctx, C->d_domain); ctx_free(ctx, C->d_l0inv); ctx_free(ctx, C->d_qtable);
     ctx_free(ctx, C->d_small); ctx_free(ctx, C->d_row_kind); ctx_free(ctx, C->d_gates);
     ctx_free(ctx, C->d_lut_data); ctx_free(ctx, C->d_lut_off); ctx_free(ctx, C->d_lut_len);
     delete C;
@@ -343,8 +346,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         bool has_pos = false;
         for (const auto& g : C->gates) has_pos |= g.kind == P2G_GATE_POSEIDON;
         P2G_COUNT_LAUNCH(1);
-        if (has_pos) quotient_kernel<true><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
-        else quotient_kernel<false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, d_qv);
+        if (has_pos) quotient_kernel<true><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
+        else quotient_kernel<false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
     }
     CU(cudaGetLastError());
     {

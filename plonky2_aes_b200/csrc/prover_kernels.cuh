@@ -316,6 +316,39 @@ __device__ __noinline__ void poseidon_gate_constraints(const gl_t* __restrict__ 
 #endif
 }
 
+// lazy helpers of the quotient kernel (device only): results are any-u64 residues that only feed
+// further multiplications or a final gl_canon
+#if defined(__CUDA_ARCH__)
+// a (any) + b (canonical) -> any u64, same residue: on carry add 2^64 = EPS, as the all-ones mask
+// -carry on the low word.  (The carry is materialised with addc: an add chain must not be continued
+// with subc -- ptxas keeps the hardware flag, where borrow = !carry.)
+__device__ __forceinline__ gl_t qadd_lazy(gl_t a, gl_t b) {
+    gl_t d;
+    asm("{\n\t.reg .u32 a0, a1, b0, b1, m;\n\t"
+        "mov.b64 {a0,a1}, %1;\n\tmov.b64 {b0,b1}, %2;\n\t"
+        "add.cc.u32 a0, a0, b0;\n\taddc.cc.u32 a1, a1, b1;\n\taddc.u32 m, 0, 0;\n\tneg.s32 m, m;\n\t"
+        "add.cc.u32 a0, a0, m;\n\taddc.u32 a1, a1, 0;\n\t"
+        "mov.b64 %0, {a0,a1};\n\t}" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// a*b + c*d (all any u64) -> lazy residue with a single fold
+__device__ __forceinline__ gl_t pmul2(gl_t a, gl_t b, gl_t c, gl_t d) {
+    uint32_t l0, l1, h0, h1, m0, m1, n0, n1, h2;
+    pmul128(a, b, l0, l1, h0, h1); pmul128(c, d, m0, m1, n0, n1);
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, 0, 0;"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "=r"(h2) : "r"(m0), "r"(m1), "r"(n0), "r"(n1));
+    return gl_fold5(l0, l1, h0, h1, h2);
+}
+#else
+__device__ __forceinline__ gl_t qadd_lazy(gl_t a, gl_t b) { return gl_add_lazy(a, b); }
+__device__ __forceinline__ gl_t pmul2(gl_t a, gl_t b, gl_t c, gl_t d) { return gl_add(gl_mul(a, b), gl_mul(c, d)); }
+__device__ __forceinline__ gl_t pmul(gl_t a, gl_t b) { return gl_mul(a, b); }
+__device__ __forceinline__ gl_t pmul_add(gl_t a, gl_t b, gl_t c) { return gl_add(gl_mul(a, b), gl_canon(c)); }
+struct Acc160 { gl_t v; };
+__device__ __forceinline__ void acc_mul(Acc160& A, gl_t a, gl_t b) { A.v = gl_add(A.v, gl_mul(a, b)); }
+__device__ __forceinline__ gl_t acc_fold(const Acc160& A) { return A.v; }
+#endif
+
 __device__ __forceinline__ gl_t gate_filter(int row, int gs, int ge, gl_t s, bool many) {
     gl_t f = 1;
     for (int i = gs; i < ge; i++) if (i != row) f = gl_mul(f, gl_sub((gl_t)i, s));
@@ -354,7 +387,7 @@ template <bool HAS_POSEIDON>
 __global__ void __launch_bounds__(128)
 quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ lut_evals, const p2g_gate* __restrict__ gates,
                 const gl_t* __restrict__ cs, const gl_t* __restrict__ wl, const gl_t* __restrict__ zl,
-                const gl_t* __restrict__ domain, gl_t* __restrict__ out) {
+                const gl_t* __restrict__ domain, const gl_t* __restrict__ l0inv, gl_t* __restrict__ out) {
     const int logn = cd.logn, logN = logn + cd.rate_bits;
     const size_t n = (size_t)1 << logn, N = (size_t)1 << logN;
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,14 +398,15 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
     const uint32_t coset = gl_bitrev(blk, cd.rate_bits);
     const gl_t x = domain[j];
     const gl_t zh = pc->zh[coset];
-    const gl_t l0 = gl_mul(zh, gl_inv(gl_mul((gl_t)n, gl_sub(x, 1))));
+    const gl_t l0 = gl_mul(zh, l0inv[j]);       // L_0(x) = Z_H(x) / (n (x - 1)), inverse tabulated at circuit load
     const int nch = cd.nch, R = cd.R;
-    gl_t acc[MAX_CH];
+    // sum_k alpha^k term_k per challenge: 128-bit products accumulated in 160 bits, one fold at the end
+    Acc160 acc[MAX_CH];
 #pragma unroll
-    for (int c = 0; c < MAX_CH; c++) acc[c] = 0;
+    for (int c = 0; c < MAX_CH; c++) acc[c] = Acc160{};
     int t = 0;   // running term index
 #define ADD_TERM(idx, val) do { gl_t v_ = (val); _Pragma("unroll") for (int c_ = 0; c_ < MAX_CH; c_++) if (c_ < nch) \
-        acc[c_] = gl_add(acc[c_], gl_mul(v_, pc->alpha_pows[c_][(idx)])); } while (0)
+        acc_mul(acc[c_], v_, pc->alpha_pows[c_][(idx)]); } while (0)
     // Z(x) - 1 terms
     for (int c = 0; c < nch; c++) ADD_TERM(t + c, gl_mul(l0, gl_sub(zl[(size_t)c * N + j], 1)));
     t += nch;
@@ -391,9 +425,10 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
                 gl_t wv = wl[(size_t)w * N + j], sv = cs[(size_t)(cd.NC + w) * N + j];
 #pragma unroll
                 for (int c = 0; c < MAX_CH; c++) if (c < nch) {
-                    gl_t num = gl_add(gl_add(wv, gl_mul(pc->beta_kis[c][w], x)), pc->gammas[c]);
-                    gl_t den = gl_add(gl_add(wv, gl_mul(pc->betas[c], sv)), pc->gammas[c]);
-                    np[c] = gl_mul(np[c], num); dp[c] = gl_mul(dp[c], den);
+                    // lazy residues: they only feed the running products
+                    gl_t num = qadd_lazy(pmul_add(pc->beta_kis[c][w], x, wv), pc->gammas[c]);
+                    gl_t den = qadd_lazy(pmul_add(pc->betas[c], sv, wv), pc->gammas[c]);
+                    np[c] = pmul(np[c], num); dp[c] = pmul(dp[c], den);
                 }
             }
 #pragma unroll
@@ -427,44 +462,32 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             const int tt = tb + 4 + cd.num_luts;   // index of the first per-poly term (after RE transition at tt-1)
 #pragma unroll 1
             for (int poly = 0; poly < cd.num_sldc; poly++) {
-                gl_t fl[8], fu[8];
                 int a0 = poly * cd.lut_degree, a1 = min(a0 + cd.lut_degree, cd.lut_slots);
                 int b0 = poly * cd.lu_degree, b1 = min(b0 + cd.lu_degree, cd.lu_slots);
-                gl_t mults[8];
+                // prod_i f_i and sum_i m_i prod_{j != i} f_j by the running pair (S, P) <- (S f + m P, P f)
+                gl_t lut_prod = 1, lut_sum = 0, lu_prod = 1, lu_sum = 0;
                 for (int s = a0; s < a1; s++) {
                     gl_t in = wl[(size_t)(3 * s) * N + j], o = wl[(size_t)(3 * s + 1) * N + j];
-                    mults[s - a0] = wl[(size_t)(3 * s + 2) * N + j];
-                    fl[s - a0] = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
-                    re_cur = gl_add(gl_mul(re_cur, ddelta), gl_add(in, gl_mul(db, o)));
+                    gl_t mult = wl[(size_t)(3 * s + 2) * N + j];
+                    gl_t f = gl_sub(dalpha, gl_canon(pmul_add(da, o, in)));
+                    re_cur = pmul_add(re_cur, ddelta, pmul_add(db, o, in));
+                    lut_sum = pmul2(lut_sum, f, mult, lut_prod);
+                    lut_prod = pmul(lut_prod, f);
                 }
                 for (int s = b0; s < b1; s++) {
                     gl_t in = wl[(size_t)(2 * s) * N + j], o = wl[(size_t)(2 * s + 1) * N + j];
-                    fu[s - b0] = gl_sub(dalpha, gl_add(in, gl_mul(da, o)));
+                    gl_t f = gl_sub(dalpha, gl_canon(pmul_add(da, o, in)));
+                    lu_sum = pmul_add(lu_sum, f, lu_prod);
+                    lu_prod = pmul(lu_prod, f);
                 }
-                // prod and sum_i prod_{j != i} via prefix/suffix products
-                const int na = a1 - a0, nb = b1 - b0;
-                gl_t lut_prod = 1, lut_sum = 0, lu_prod = 1, lu_sum = 0;
-                {
-                    gl_t suf[9]; suf[na] = 1;
-                    for (int i = na - 1; i >= 0; i--) suf[i] = gl_mul(suf[i + 1], fl[i]);
-                    gl_t pre = 1;
-                    for (int i = 0; i < na; i++) { lut_sum = gl_add(lut_sum, gl_mul(mults[i], gl_mul(pre, suf[i + 1]))); pre = gl_mul(pre, fl[i]); }
-                    lut_prod = pre;
-                }
-                {
-                    gl_t suf[9]; suf[nb] = 1;
-                    for (int i = nb - 1; i >= 0; i--) suf[i] = gl_mul(suf[i + 1], fu[i]);
-                    gl_t pre = 1;
-                    for (int i = 0; i < nb; i++) { lu_sum = gl_add(lu_sum, gl_mul(pre, suf[i + 1])); pre = gl_mul(pre, fu[i]); }
-                    lu_prod = pre;
-                }
+                lut_sum = gl_canon(lut_sum); lu_sum = gl_canon(lu_sum);
                 gl_t cur = lz[(size_t)(poly + 1) * N + j];
                 gl_t prev = poly == 0 ? lz[(size_t)cd.num_sldc * N + jn] : lz[(size_t)poly * N + j];
                 gl_t diff = gl_sub(cur, prev);
                 ADD_TERM(tt + 2 * poly, gl_mul(s_trans_sre, gl_sub(gl_mul(lut_prod, diff), lut_sum)));
                 ADD_TERM(tt + 2 * poly + 1, gl_mul(s_trans_ldc, gl_add(gl_mul(lu_prod, diff), lu_sum)));
             }
-            ADD_TERM(tt - 1, gl_mul(s_trans_sre, gl_sub(z_re, re_cur)));
+            ADD_TERM(tt - 1, gl_mul(s_trans_sre, gl_sub(z_re, gl_canon(re_cur))));
         }
         t += nch * n_lookup_terms;
     }
@@ -499,12 +522,12 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             return v;
         };
         if (HAS_POSEIDON && has_poseidon) {
-            gl_t a0 = acc[0], a1 = acc[1];
+            Acc160 a0 = acc[0], a1 = acc[1];
             const int tbase = t;
             poseidon_gate_constraints(wl, N, j, [&](int k, gl_t cval) {
                 gl_t v = gl_add(gl_mul(f_pos, cval), small_gates(k));
-                a0 = gl_add(a0, gl_mul(v, pc->alpha_pows[0][tbase + k]));
-                if (nch > 1) a1 = gl_add(a1, gl_mul(v, pc->alpha_pows[1][tbase + k]));
+                acc_mul(a0, v, pc->alpha_pows[0][tbase + k]);
+                if (nch > 1) acc_mul(a1, v, pc->alpha_pows[1][tbase + k]);
             });
             acc[0] = a0; acc[1] = a1;
         } else {
@@ -515,7 +538,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
 #undef ADD_TERM
     const gl_t zi = pc->zh_inv[coset];
     for (int c = 0; c < nch; c++)
-        out[(size_t)c * N + ((size_t)blk << logn) + k] = gl_mul(acc[c], zi);
+        out[(size_t)c * N + ((size_t)blk << logn) + k] = gl_mul(acc_fold(acc[c]), zi);
 }
 
 // Recover the quotient chunk coefficients from the 8 per-coset inverse NTTs:
@@ -690,6 +713,12 @@ query_gather_kernel(const GatherTree* __restrict__ trees, int ntrees, const unsi
     }
 }
 
+// 1 / (n (x_j - 1)) on the LDE domain: the point-dependent factor of L_0(x) = Z_H(x) / (n (x - 1))
+__global__ void l0inv_kernel(size_t N, gl_t n, const gl_t* __restrict__ domain, gl_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    out[j] = gl_inv(gl_mul(n, gl_sub(domain[j], 1)));
+}
 // domain points in leaf order: x_j = 7 * w_N^bitrev(j);  subgroup g^i
 __global__ void domain_kernel(int logN, gl_t wN, gl_t shift, gl_t* __restrict__ out, int bitrev_order) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
