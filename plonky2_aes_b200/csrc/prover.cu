@@ -300,7 +300,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     gl_t* d_lut_evals;
     if ((rc = ctx_alloc(ctx, &d_lut_evals, MAX_CH * 8))) return rc;
     if (has_lookup) {
-        P2G_COUNT_LAUNCH(1); lut_eval_kernel<<<dim3(cd.num_luts, nch), 256, 0, st>>>(cd, d_pc, C->d_lut_data, C->d_lut_off, C->d_lut_len, d_lut_evals);
+        P2G_COUNT_LAUNCH(1); lut_eval_kernel<<<dim3(cd.num_luts, nch), 1024, 0, st>>>(cd, d_pc, C->d_lut_data, C->d_lut_off, C->d_lut_len, d_lut_evals);
     }
 
     // ---- Z, partial products, lookup polys ----
@@ -436,8 +436,19 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = ctx_alloc(ctx, &d_comp, 4 * n))) return rc;
     if ((rc = ctx_alloc(ctx, &d_comp_lde, 4 * N))) return rc;
     if ((rc = ctx_alloc(ctx, &d_vals, 2 * N))) return rc;
-    P2G_COUNT_LAUNCH(1); fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist, tot0, fri_alpha, n, d_comp, d_comp + n);
-    P2G_COUNT_LAUNCH(1); fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist + tot0, tot1, fri_alpha, n, d_comp + 2 * n, d_comp + 3 * n);
+    gl_t* d_apow;
+    {
+        // alpha^j for j < max(|batch 0|, |batch 1|)
+        const size_t na_ = (size_t)(tot0 > tot1 ? tot0 : tot1);
+        if ((rc = ctx_alloc(ctx, &d_apow, 2 * na_))) return rc;
+        Pow2Table ta;
+        ta.p[0] = fri_alpha;
+        for (int b = 1; b < 32; b++) ta.p[b] = ext_mul(ta.p[b - 1], ta.p[b - 1]);
+        const size_t na = (size_t)(tot0 > tot1 ? tot0 : tot1);
+        P2G_COUNT_LAUNCH(1); ext_powers_kernel2<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(ta, na, d_apow);
+    }
+    P2G_COUNT_LAUNCH(1); fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist, tot0, d_apow, n, d_comp, d_comp + n);
+    P2G_COUNT_LAUNCH(1); fri_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_plist + tot0, tot1, d_apow, n, d_comp + 2 * n, d_comp + 3 * n);
     CU(cudaGetLastError());
     {
         const NttPlan* lde;
@@ -594,7 +605,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     // release
     for (int l = 0; l < nl; l++) { ctx_free(ctx, layers[l].digests); ctx_free(ctx, layers[l].cap); if (l > 0) ctx_free(ctx, layers[l].vals); }
     if (nl > 0) ctx_free(ctx, cur_vals);
-    ctx_free(ctx, d_vals); ctx_free(ctx, d_comp); ctx_free(ctx, d_comp_lde); ctx_free(ctx, d_zp); ctx_free(ctx, d_open);
+    ctx_free(ctx, d_vals); ctx_free(ctx, d_comp); ctx_free(ctx, d_comp_lde); ctx_free(ctx, d_zp); ctx_free(ctx, d_apow); ctx_free(ctx, d_open);
     ctx_free(ctx, d_lut_evals);
     cudaFreeAsync((void*)d_plist, st); cudaFreeAsync(d_gt, st); cudaFreeAsync(d_qidx, st); ctx_free(ctx, d_q); cudaFreeAsync(d_pc, st);
     p2g_batch_free(ctx, wb); p2g_batch_free(ctx, zb); p2g_batch_free(ctx, qb);

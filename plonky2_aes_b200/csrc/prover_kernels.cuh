@@ -358,10 +358,10 @@ __device__ __forceinline__ gl_t gate_filter(int row, int gs, int ge, gl_t s, boo
 
 // get_lut_poly(lut, deltas).eval(delta) (plonk/vanishing_poly.rs): sum_e (in_e + b*out_e) * delta^(degree-1-e)
 // with the table zero-padded to `degree` = rows * slots entries.  One block per (lut, challenge).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 lut_eval_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const uint16_t* __restrict__ lut_data,
                 const int* __restrict__ lut_off, const int* __restrict__ lut_len, gl_t* __restrict__ out /*[nch][8]*/) {
-    __shared__ gl_t sm[256];
+    __shared__ gl_t sm[1024];
     const int lut = blockIdx.x, ch = blockIdx.y;
     const int len = lut_len[lut];
     const int degree = ((len + cd.lut_slots - 1) / cd.lut_slots) * cd.lut_slots;
@@ -376,7 +376,7 @@ lut_eval_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const uint16_
     }
     sm[threadIdx.x] = gl_mul(acc, gl_pow(delta, (uint64_t)(degree - e1)));
     __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
+    for (int d = blockDim.x / 2; d > 0; d >>= 1) {
         if ((int)threadIdx.x < d) sm[threadIdx.x] = gl_add(sm[threadIdx.x], sm[threadIdx.x + d]);
         __syncthreads();
     }
@@ -585,11 +585,14 @@ __global__ void __launch_bounds__(256)
 eval_polys_kernel(const gl_t* const* __restrict__ polys, const gl_t* __restrict__ zp, size_t n, gl_t* __restrict__ out) {
     __shared__ gl_t s0[256], s1[256];
     const gl_t* c = polys[blockIdx.x];
-    gl_t a0 = 0, a1 = 0;
+    // 160-bit lazy sums; four coefficients per trip keep 12 loads in flight per thread
+    Acc160 A0 = Acc160{}, A1 = Acc160{};
+#pragma unroll 4
     for (size_t j = threadIdx.x; j < n; j += blockDim.x) {
         gl_t cv = c[j];
-        a0 = gl_add(a0, gl_mul(cv, zp[2 * j])); a1 = gl_add(a1, gl_mul(cv, zp[2 * j + 1]));
+        acc_mul(A0, cv, zp[2 * j]); acc_mul(A1, cv, zp[2 * j + 1]);
     }
+    gl_t a0 = gl_canon(acc_fold(A0)), a1 = gl_canon(acc_fold(A1));
     s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
     __syncthreads();
     for (int d = 128; d > 0; d >>= 1) {
@@ -601,16 +604,22 @@ eval_polys_kernel(const gl_t* const* __restrict__ polys, const gl_t* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 // PolynomialBatch::prove_openings (fri/oracle.rs): composition polynomial of one batch,
-// comp[k] = sum_j alpha^j f_j[k] (Horner from the last polynomial), output as two base columns.
+// comp[k] = sum_j alpha^j f_j[k], output as two base columns.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-fri_compose_kernel(const gl_t* const* __restrict__ polys, int npolys, ext_t alpha, size_t n,
+fri_compose_kernel(const gl_t* const* __restrict__ polys, int npolys, const gl_t* __restrict__ apow /*[npolys][2]*/, size_t n,
                    gl_t* __restrict__ out_c0, gl_t* __restrict__ out_c1) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    ext_t acc = ext_make(0, 0);
-    for (int j = npolys - 1; j >= 0; j--) acc = ext_add_base(ext_mul(acc, alpha), polys[j][k]);
-    out_c0[k] = acc.c0; out_c1[k] = acc.c1;
+    // sum_j alpha^j f_j[k] with tabulated powers: two base multiplications per polynomial,
+    // accumulated lazily in 160 bits (the Horner form costs a full extension multiply each)
+    Acc160 A0 = Acc160{}, A1 = Acc160{};
+#pragma unroll 4
+    for (int j = 0; j < npolys; j++) {
+        const gl_t v = polys[j][k];
+        acc_mul(A0, v, apow[2 * j]); acc_mul(A1, v, apow[2 * j + 1]);
+    }
+    out_c0[k] = gl_canon(acc_fold(A0)); out_c1[k] = gl_canon(acc_fold(A1));
 }
 // final(x) = alpha^{|b1|} (comp0(x) - comp0(zeta)) / (x - zeta) + (comp1(x) - comp1(g zeta)) / (x - g zeta)
 // lde: [4][N] = comp0.c0, comp0.c1, comp1.c0, comp1.c1 on the LDE domain (bit-reversed); out [N][2]
