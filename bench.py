@@ -49,7 +49,11 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_begin = index, [], None, 0.0
+
+    def mark_begin(self):
+        """samples received before this point (start-up, warm-up) are dropped"""
+        self.t_begin = time.monotonic()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -63,11 +67,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        self.rows = [r for t, r in self.rows if t >= self.t_begin]
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -115,7 +120,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -198,18 +203,22 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(args.warmup):
-        step_device()
-    launches0 = lib.p2g_launch_count()
+    # nvidia-smi needs a few hundred ms to produce its first line: start it before the warm-up and keep
+    # the samples that arrive between the start of the device-timed leg and the end of the end-to-end
+    # leg (both legs and the warm-up between them run the same proofs back to back)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = lib.p2g_launch_count()
+    sampler.mark_begin()
     ms_dev = timed(step_device, args.steps)
     launches = lib.p2g_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     for _ in range(args.warmup):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
     total_proofs = B * args.steps * world
     value = total_proofs / (ms_dev * 1e-3)
     e2e = total_proofs / (ms_e2e * 1e-3)
@@ -250,8 +259,8 @@ def main():
                 "achieved": merkle_bytes / merkle_ms / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": merkle_bytes / merkle_ms / 1e6 / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
-                # profiles/r1_kernels_final_ncu_summary.txt (284.5 MB + 12.9 MB; algorithmic 308 MB)
-                "traffic": 297.5e6, "algorithmic_bytes": merkle_bytes, "peak_kind": peak_kind + " copy bandwidth",
+                # profiles/r1_kernels_final_ncu_summary.txt (283.3 MB + 12.2 MB; algorithmic 308 MB)
+                "traffic": 295.5e6, "algorithmic_bytes": merkle_bytes, "peak_kind": peak_kind + " copy bandwidth",
                 "int_pipe": {"perms_per_s": perms / merkle_ms * 1e3, "peak_perms_per_s": poseidon_peak,
                              "frac": perms / merkle_ms * 1e3 / poseidon_peak,
                              "note": "Poseidon is INT-pipe bound (63 B of input per permutation); peak = chained "
