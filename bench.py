@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 L_BYTES = 256
-PROOFS_PER_STEP = 4
+PROOFS_PER_STEP = int(os.environ.get('P2G_BENCH_PROOFS_PER_STEP', '8'))
 METRIC = "AES-128 block proofs/sec at 1/2/4/8 B200; LDE+Merkle GB/s vs HBM peak"
 UNIT = "proofs/s"
 WORKLOAD = ("AES-GCM-128 16-block (256 B) plaintext with GHASH tag, standard_recursion_config, "
@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="proofs in flight per GPU (one p2g context + host thread each)")
+    ap.add_argument("--streams", type=int, default=8, help="proofs in flight per GPU (one p2g context + host thread each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,9 +140,14 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    T = max(1, args.streams)
+    # host threads waiting for their proof's stream spin by default; if this node has fewer cores than
+    # ranks x proofs in flight they sleep on a blocking-sync event instead (csrc/ctx.h, ctx_wait)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ.setdefault("P2G_SYNC", "spin" if T * local_world <= cores else "block")
     ctx = Context(local_rank)
     lib = ctx.lib
-    T = max(1, args.streams)
     ctxs = [ctx] + [Context(local_rank) for _ in range(T - 1)]
     streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local_rank)) for c in ctxs]
 
@@ -294,7 +299,7 @@ def main():
                "dtype": "u64 (Goldilocks p=2^64-2^32+1, exact)", "data": "synthetic",
                "config": {"workload": WORKLOAD, "proofs_per_step_per_gpu": B, "aes_blocks_per_proof": L_BYTES // 16,
                           "aes_block_proofs_per_s": value * (L_BYTES // 16), "l2": "per-proof working set 1.0 GB > 126 MB L2",
-                          "proofs_in_flight_per_gpu": T,
+                          "proofs_in_flight_per_gpu": T, "host_wait": os.environ["P2G_SYNC"], "host_cores": cores,
                           "parallelism": f"independent proofs sharded over {world} GPU(s)"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * W * n * 8, "d2h_bytes_per_step": B * words * 8,
                        "ms_per_step": ms_e2e / args.steps},

@@ -20,6 +20,13 @@ extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
     memset(&ctx->transcript, 0, sizeof(ctx->transcript));
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
     {
+        const char* mode = getenv("P2G_SYNC");
+        ctx->blocking_wait = mode && strcmp(mode, "block") == 0;
+        if (cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(ctx->st); delete ctx; return P2G_E_CUDA;
+        }
+    }
+    {
         cudaMemPoolProps props; memset(&props, 0, sizeof(props));
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
@@ -40,12 +47,13 @@ extern "C" void p2g_ctx_destroy(p2g_ctx* ctx) {
     cudaStreamSynchronize(ctx->st);
     for (auto& kv : ctx->plans) ntt_plan_free(&kv.second);
     cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->wait_ev);
     cudaMemPoolDestroy(ctx->pool);
     cudaStreamDestroy(ctx->st);
     delete ctx;
 }
 extern "C" const char* p2g_last_error(p2g_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
-extern "C" int32_t p2g_ctx_sync(p2g_ctx* ctx) { CU(cudaStreamSynchronize(ctx->st)); return P2G_OK; }
+extern "C" int32_t p2g_ctx_sync(p2g_ctx* ctx) { CU(ctx_wait(ctx)); return P2G_OK; }
 extern "C" void* p2g_ctx_stream(p2g_ctx* ctx) { return (void*)ctx->st; }
 
 int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan** out) {
@@ -104,7 +112,7 @@ int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_
     b->cap_host.resize((size_t)4 << cap_height);
     if (sync_cap) {
         CU(cudaMemcpyAsync(ctx->pinned, b->cap, b->cap_host.size() * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
+        CU(ctx_wait(ctx));
         memcpy(b->cap_host.data(), ctx->pinned, b->cap_host.size() * sizeof(gl_t));
     }
     *out = b;
@@ -171,12 +179,12 @@ extern "C" int32_t p2g_batch_free(p2g_ctx* ctx, p2g_batch* b) {
 }
 extern "C" int32_t p2g_batch_get_coeffs(p2g_ctx* ctx, const p2g_batch* b, uint64_t* out) {
     CU(cudaMemcpyAsync(out, b->coeffs, (size_t)b->ncols * b->n() * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     return P2G_OK;
 }
 extern "C" int32_t p2g_batch_get_lde(p2g_ctx* ctx, const p2g_batch* b, uint64_t* out) {
     CU(cudaMemcpyAsync(out, b->lde, (size_t)b->ncols * b->N() * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     return P2G_OK;
 }
 extern "C" int32_t p2g_batch_get_level(p2g_ctx* ctx, const p2g_batch* b, uint32_t level, uint64_t* out) {
@@ -185,7 +193,7 @@ extern "C" int32_t p2g_batch_get_level(p2g_ctx* ctx, const p2g_batch* b, uint32_
     const gl_t* src = level == L ? b->cap : b->digests + merkle_level_offset(b->log_N(), level);
     size_t words = (size_t)4 << (b->log_N() - level);
     CU(cudaMemcpyAsync(out, src, words * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     return P2G_OK;
 }
 extern "C" int32_t p2g_batch_open_leaf(p2g_ctx* ctx, const p2g_batch* b, uint64_t leaf, uint64_t* row_out, uint64_t* sib_out) {
@@ -198,7 +206,7 @@ extern "C" int32_t p2g_batch_open_leaf(p2g_ctx* ctx, const p2g_batch* b, uint64_
         CU(cudaMemcpyAsync(sib_out + 4 * k, lvl + 4 * (idx ^ 1), 4 * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
         idx >>= 1;
     }
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     return P2G_OK;
 }
 
@@ -218,7 +226,7 @@ extern "C" int32_t p2g_merkle_cap(p2g_ctx* ctx, const uint64_t* leaves_host, uin
         const gl_t* src = log_leaves == cap_height ? d_cap : d_dig;
         CU(cudaMemcpyAsync(leaf_digests_out, src, ((size_t)4 << log_leaves) * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
     }
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     ctx_free(ctx, d_leaves); ctx_free(ctx, d_dig); ctx_free(ctx, d_cap);
     return P2G_OK;
 }
@@ -247,7 +255,7 @@ extern "C" int32_t p2g_hash_no_pad_many(p2g_ctx* ctx, const uint64_t* in_host, u
     hash_no_pad_many_kernel<<<(count + 127) / 128, 128, 0, ctx->st>>>(d_in, count, len, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_host, d_out, (size_t)count * 4 * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     ctx_free(ctx, d_in); ctx_free(ctx, d_out);
     return P2G_OK;
 }
@@ -264,7 +272,7 @@ extern "C" int32_t p2g_poseidon_peak(p2g_ctx* ctx, uint32_t iters, double* perms
     CU(cudaEventRecord(e0, ctx->st));
     if (poseidon_bench_launch(d_out, nthreads, iters, ctx->st)) { ctx->err = "poseidon bench launch"; return P2G_E_CUDA; }
     CU(cudaEventRecord(e1, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
     *perms_per_sec = (double)nthreads * iters / (ms * 1e-3);
     cudaEventDestroy(e0); cudaEventDestroy(e1);

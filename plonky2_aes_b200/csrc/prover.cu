@@ -158,7 +158,7 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
         if ((rc = ctx_alloc(ctx, &C->d_small, 16))) return rc;
         CU(cudaMemcpyAsync(C->d_qtable, tab.data(), tab.size() * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
         CU(cudaMemcpyAsync(C->d_small, small.data(), small.size() * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
+        CU(ctx_wait(ctx));
     }
     // gates and row kinds
     {
@@ -181,7 +181,7 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
         CU(cudaMemcpyAsync(C->d_lut_data, C->lut_data.data(), 4 * lut_total, cudaMemcpyHostToDevice, ctx->st));
         CU(cudaMemcpyAsync(C->d_lut_off, off.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
         CU(cudaMemcpyAsync(C->d_lut_len, len.data(), 8 * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
+        CU(ctx_wait(ctx));
     }
     size_t fin = n; for (int l = 0; l < d.num_reduction_arity_bits; l++) fin >>= d.reduction_arity_bits[l];
     C->final_len = (int)fin;
@@ -404,7 +404,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     std::vector<ext_t> open((size_t)tot0 + tot1);
     CU(cudaMemcpyAsync(ctx->pinned, d_open, open.size() * sizeof(ext_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(ctx_wait(ctx));
     memcpy(open.data(), ctx->pinned, open.size() * sizeof(ext_t));
     tm.mark();
     ch.observe_many((const gl_t*)open.data(), 2 * open.size());
@@ -480,7 +480,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         if ((rc = ctx_alloc(ctx, &L.cap, capw))) return rc;
         if (merkle_build(cur_vals, 0, 0, 2u << ab, log_leaves, d.cap_height, L.digests, L.cap, st)) { ctx->err = "fri merkle"; return P2G_E_CUDA; }
         CU(cudaMemcpyAsync(ctx->pinned, L.cap, capw * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(ctx_wait(ctx));
         memcpy(w, ctx->pinned, capw * sizeof(gl_t));
         ch.observe_many(w, capw);
         w += capw;
@@ -499,7 +499,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     const size_t fl = (size_t)1 << cur_log;
     std::vector<ext_t> fvals(fl), fcoef(fl);
     CU(cudaMemcpyAsync(ctx->pinned, cur_vals, fl * sizeof(ext_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(ctx_wait(ctx));
     memcpy(fvals.data(), ctx->pinned, fl * sizeof(ext_t));
     {
         // natural-order values, then coset_ifft(shift): c_i = shift^-i / len * sum_m v[m] w^-(i m)
@@ -538,7 +538,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
             P2G_COUNT_LAUNCH(1); pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, st>>>(ps, pos, d.pow_bits, base, d_best);
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            CU(ctx_wait(ctx));
             unsigned long long best = *(unsigned long long*)ctx->pinned;
             if (best != ~0ull) { pow_witness = best; found = true; }
         }
@@ -584,7 +584,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     P2G_COUNT_LAUNCH(1); query_gather_kernel<<<dim3(nq, (unsigned)gt.size()), 128, 0, st>>>(d_gt, (int)gt.size(), d_qidx, rec, d_q);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(w, d_q, rec * nq * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(ctx_wait(ctx));
     w += rec * nq;
     memcpy(w, fcoef.data(), final_len * sizeof(ext_t)); w += 2 * final_len;
     *w++ = pow_witness;
@@ -656,7 +656,7 @@ extern "C" int32_t p2g_pow_grind(p2g_ctx* ctx, const uint64_t state[12], uint32_
         CU(cudaMemsetAsync(d_best, 0xFF, 8, ctx->st));
         P2G_COUNT_LAUNCH(1); pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, ctx->st>>>(ps, (int)pos, (int)pow_bits, base, d_best);
         CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
+        CU(ctx_wait(ctx));
         unsigned long long best = *(unsigned long long*)ctx->pinned;
         if (best != ~0ull) { *nonce_out = best; cudaFreeAsync(d_best, ctx->st); return P2G_OK; }
     }
@@ -679,7 +679,7 @@ extern "C" int32_t p2g_fri_fold(p2g_ctx* ctx, const uint64_t* values_host, uint3
                                                                          gl_inv((gl_t)1 << arity_bits), b, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_host, d_out, 2 * chunks * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(ctx_wait(ctx));
     ctx_free(ctx, d_in); ctx_free(ctx, d_out);
     return P2G_OK;
 }
