@@ -161,6 +161,14 @@ int32_t p2g_fri_fold(p2g_ctx* ctx, const uint64_t* values_host /*[N][2]*/, uint3
 /* chained Poseidon permutations without memory traffic: the INT-pipe peak used as roofline
  * denominator for the Merkle kernels.  Returns permutations per second. */
 int32_t p2g_poseidon_peak(p2g_ctx* ctx, uint32_t iters, double* perms_per_sec);
+/* Device field arithmetic exposed for parity tests (plonky2 field/src/goldilocks_field.rs Add / Sub /
+ * Mul and to_canonical_u64): for i < n,
+ *   out[0][i] = a+b, out[1][i] = a-b, out[2][i] = a*b   (a, b canonical),
+ *   out[3][i] = canonical form of the arbitrary u64 la[i],
+ *   out[4][i] = canonical form of la[i]*lb[i]            (la, lb arbitrary u64 residues),
+ *   out[5][i] = canonical form of a * 2^(i mod 96)       (the shift-multiply of the last NTT pass). */
+int32_t p2g_field_ops(p2g_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* la, const uint64_t* lb,
+                      size_t n, uint64_t* out /*[6][n]*/);
 
 #ifdef __cplusplus
 }

@@ -279,3 +279,39 @@ extern "C" int32_t p2g_poseidon_peak(p2g_ctx* ctx, uint32_t iters, double* perms
     ctx_free(ctx, d_out);
     return P2G_OK;
 }
+
+// ---- device field arithmetic behind a test entry point ---------------------------------------
+template <int K> struct Pow2Dispatch {
+    static __device__ __forceinline__ gl_t run(gl_t x, int k) { return k == K ? gl_mul_pow2<K>(x) : Pow2Dispatch<K - 1>::run(x, k); }
+};
+template <> struct Pow2Dispatch<0> { static __device__ __forceinline__ gl_t run(gl_t x, int) { return x; } };
+
+__global__ void field_ops_kernel(const gl_t* __restrict__ a, const gl_t* __restrict__ b, const gl_t* __restrict__ la,
+                                 const gl_t* __restrict__ lb, size_t n, gl_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = gl_add(a[i], b[i]);
+    out[n + i] = gl_sub(a[i], b[i]);
+    out[2 * n + i] = gl_mul(a[i], b[i]);
+    out[3 * n + i] = gl_canon(la[i]);
+    out[4 * n + i] = gl_canon(gl_mul_lazy(la[i], lb[i]));
+    out[5 * n + i] = Pow2Dispatch<95>::run(a[i], (int)(i % 96));
+}
+
+extern "C" int32_t p2g_field_ops(p2g_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* la, const uint64_t* lb,
+                                 size_t n, uint64_t* out) {
+    if (!ctx || !a || !b || !la || !lb || !out || !n) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    gl_t *d_in, *d_out; int rc;
+    if ((rc = ctx_alloc(ctx, &d_in, 4 * n))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_out, 6 * n))) return rc;
+    const uint64_t* src[4] = {a, b, la, lb};
+    for (int k = 0; k < 4; k++) CU(cudaMemcpyAsync(d_in + k * n, src[k], n * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+    field_ops_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(d_in, d_in + n, d_in + 2 * n, d_in + 3 * n, n, d_out);
+    P2G_COUNT_LAUNCH(1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, 6 * n * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(ctx_wait(ctx));
+    ctx_free(ctx, d_in); ctx_free(ctx, d_out);
+    return P2G_OK;
+}
