@@ -148,12 +148,23 @@ __device__ __forceinline__ gl_t gl_mul_lazy(gl_t a, gl_t b) {
     uint32_t l0, l1, h0, h1; pmul128(a, b, l0, l1, h0, h1);
     return gl_fold4(l0, l1, h0, h1);
 }
+// a*b + c*d (all any u64) -> lazy residue: the two 128-bit products are added before the single fold
+__device__ __forceinline__ gl_t gl_mul2_lazy(gl_t a, gl_t b, gl_t c, gl_t d) {
+    uint32_t l0, l1, h0, h1, m0, m1, n0, n1, h2;
+    pmul128(a, b, l0, l1, h0, h1); pmul128(c, d, m0, m1, n0, n1);
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, 0, 0;"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "=r"(h2) : "r"(m0), "r"(m1), "r"(n0), "r"(n1));
+    return gl_fold5(l0, l1, h0, h1, h2);
+}
 #else
 // any u64 * any u64 -> lazy residue
 GL_HD gl_t gl_mul_lazy(gl_t a, gl_t b) {
     gl_t lo, hi;
     gl_mul_wide(a, b, lo, hi);
     return gl_reduce128_lazy(lo, hi);
+}
+GL_HD gl_t gl_mul2_lazy(gl_t a, gl_t b, gl_t c, gl_t d) {
+    return gl_add_lazy(gl_mul_lazy(a, b), gl_canon(gl_mul_lazy(c, d)));
 }
 #endif
 // any * any -> canonical

@@ -16,6 +16,7 @@
 #include "common.h"
 #include <vector>
 #include <stdio.h>
+#include <stdlib.h>
 
 __device__ __forceinline__ uint32_t smpad(uint32_t i) { return i + (i >> 4); }
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ void dif_pass_last16(gl_t* sm, int log_m, uint32_t ti
 __global__ void __launch_bounds__(512, 1)
 ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__ out, size_t out_stride,
                const gl_t* __restrict__ T, const gl_t* __restrict__ tw,
-               int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first, int inverse) {
+               int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first, int inverse, uint32_t tw_skip) {
     extern __shared__ gl_t sm[];
     const int log_r = log_n - log_m;
     const uint32_t M = 1u << log_m, R = 1u << log_r;
@@ -111,13 +112,15 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
     const gl_t* Tq = T + ((size_t)(variant * R + q) << log_n);   // [k][t]
     // per-pass twiddle tables live behind the data in shared memory (global/L2 twiddle loads were
     // the dominant stall of this kernel: long_scoreboard 3.0 per issue, profiles/)
+    // tw_skip: leading table words left in global memory (the block-size-2^13 table of the two-blocks-
+    // per-SM configuration, which would not fit twice)
     gl_t* tws = sm + M + (M >> 4) + 1;
     {
         uint32_t total = 0;
         int lb = log_m, rem0 = log_m & 3;
         if (rem0) { total += 1u << (lb - 1); lb -= rem0; }
         while (lb > 0) { total += 1u << (lb - 1); lb -= 4; }
-        for (uint32_t i = tid; i < total; i += nth) tws[i] = __ldg(tw + i);
+        for (uint32_t i = tw_skip + tid; i < total; i += nth) tws[i - tw_skip] = __ldg(tw + i);
     }
 
     // load + fold: y[t] = sum_k x[t + kM] * T[k][t].  All loads of a batch of 8 points are issued
@@ -139,6 +142,20 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
                 sm[smpad(t0 + u * nth)] = acc;
             }
         }
+    } else if (R == 4 && (M % (4 * nth)) == 0) {
+        for (uint32_t t0 = tid; t0 < M; t0 += 4 * nth) {
+            gl_t xv[4][4], tv[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t t = t0 + u * nth;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { xv[u][k] = __ldg(x + t + k * M); tv[u][k] = __ldg(Tq + (size_t)k * M + t); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                sm[smpad(t0 + u * nth)] = gl_add(gl_canon(gl_mul2_lazy(xv[u][0], tv[u][0], xv[u][1], tv[u][1])),
+                                                 gl_canon(gl_mul2_lazy(xv[u][2], tv[u][2], xv[u][3], tv[u][3])));
+        }
     } else {
         for (uint32_t t = tid; t < M; t += nth) {
             gl_t acc = gl_mul(__ldg(x + t), __ldg(Tq + t));
@@ -151,12 +168,18 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
 
     int log_b = log_m;
     int rem = log_m & 3;
-    const gl_t* twp = tws;
+    const gl_t* twp = tws;      // always a shared-memory pointer, so the passes below compile to LDS
     if (rem) {
-        if (rem == 1) dif_pass<1>(sm, log_m, log_b, twp, tid, nth);
-        else if (rem == 2) dif_pass<2>(sm, log_m, log_b, twp, tid, nth);
-        else dif_pass<3>(sm, log_m, log_b, twp, tid, nth);
-        twp += 1u << (log_b - 1); log_b -= rem; __syncthreads();
+        if (tw_skip) {
+            // two-blocks-per-SM configuration: the first (radix-2) pass reads its table from global memory
+            dif_pass<1>(sm, log_m, log_b, tw, tid, nth);
+        } else {
+            if (rem == 1) dif_pass<1>(sm, log_m, log_b, twp, tid, nth);
+            else if (rem == 2) dif_pass<2>(sm, log_m, log_b, twp, tid, nth);
+            else dif_pass<3>(sm, log_m, log_b, twp, tid, nth);
+            twp += 1u << (log_b - 1);
+        }
+        log_b -= rem; __syncthreads();
     }
     while (log_b > 0) {
         if (log_b == 4) { if (inverse) dif_pass_last16<true>(sm, log_m, tid, nth); else dif_pass_last16<false>(sm, log_m, tid, nth); }
@@ -180,6 +203,14 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
     plan->kind = kind; plan->log_n = log_n;
     plan->log_m = log_n < P2G_MAX_LOG_M ? log_n : P2G_MAX_LOG_M;
     if (log_n == 13) plan->log_m = 13;
+    // n = 2^14, 2^15: 2^13-point chunks, two 256-thread blocks per SM, so one block's load / store phases
+    // overlap the other's butterflies (LDE of the 135 x 2^15 wires 0.68 -> 0.65 ms); larger n keep
+    // 2^14-point chunks.  P2G_NTT_LOG_M overrides (A/B knob).
+    if (log_n == 14 || log_n == 15) plan->log_m = 13;
+    {
+        const char* e = getenv("P2G_NTT_LOG_M");
+        if (e && atoi(e) >= 10 && atoi(e) <= P2G_MAX_LOG_M && log_n > atoi(e) && log_n - atoi(e) <= 2) plan->log_m = atoi(e);
+    }
     plan->log_r = log_n - plan->log_m;
     plan->log_variants = kind == NTT_KIND_LDE ? rate_bits : 0;
     const size_t n = (size_t)1 << log_n, M = (size_t)1 << plan->log_m, R = (size_t)1 << plan->log_r;
@@ -227,7 +258,11 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
                int ncols, int out_mode, cudaStream_t st, uint32_t blk_first, uint32_t blk_count) {
     static bool attr_set = false;
     const size_t M = (size_t)1 << plan->log_m;
-    size_t smem = (M + (M >> 4) + 1 + (size_t)plan->tw_words) * sizeof(gl_t);
+    // a 2^13-point chunk with a non-trivial fold (n > 2^13) runs two blocks per SM: 256 threads each and
+    // the first pass's table (4096 words) stays in global memory
+    const bool two_per_sm = plan->log_m == 13 && plan->log_r > 0;
+    const uint32_t tw_skip = two_per_sm ? 4096u : 0u;
+    size_t smem = (M + (M >> 4) + 1 + (size_t)plan->tw_words - tw_skip) * sizeof(gl_t);
     if (!attr_set) {
         if (cudaFuncSetAttribute(ntt_dif_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
         attr_set = true;
@@ -235,13 +270,14 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
     uint32_t threads = (uint32_t)(M >> 4);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
+    if (two_per_sm) threads = 256;
     for (int c0 = 0; c0 < ncols; c0 += 65535) {
         int nc = ncols - c0 < 65535 ? ncols - c0 : 65535;
         if (blk_count == 0) blk_count = 1u << plan->log_variants;
         dim3 grid(blk_count << plan->log_r, nc);
         ntt_dif_kernel<<<grid, threads, smem, st>>>(in + (size_t)c0 * in_stride, in_stride, out + (size_t)c0 * out_stride,
                                                     out_stride, plan->T, plan->tw, plan->log_n, plan->log_m,
-                                                    plan->log_variants, out_mode, blk_first, plan->kind == NTT_KIND_INV ? 1 : 0);
+                                                    plan->log_variants, out_mode, blk_first, plan->kind == NTT_KIND_INV ? 1 : 0, tw_skip);
         P2G_COUNT_LAUNCH(1);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

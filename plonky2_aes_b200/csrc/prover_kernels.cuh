@@ -331,14 +331,7 @@ __device__ __forceinline__ gl_t qadd_lazy(gl_t a, gl_t b) {
         "mov.b64 %0, {a0,a1};\n\t}" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-// a*b + c*d (all any u64) -> lazy residue with a single fold
-__device__ __forceinline__ gl_t pmul2(gl_t a, gl_t b, gl_t c, gl_t d) {
-    uint32_t l0, l1, h0, h1, m0, m1, n0, n1, h2;
-    pmul128(a, b, l0, l1, h0, h1); pmul128(c, d, m0, m1, n0, n1);
-    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, 0, 0;"
-        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "=r"(h2) : "r"(m0), "r"(m1), "r"(n0), "r"(n1));
-    return gl_fold5(l0, l1, h0, h1, h2);
-}
+__device__ __forceinline__ gl_t pmul2(gl_t a, gl_t b, gl_t c, gl_t d) { return gl_mul2_lazy(a, b, c, d); }
 #else
 __device__ __forceinline__ gl_t qadd_lazy(gl_t a, gl_t b) { return gl_add_lazy(a, b); }
 __device__ __forceinline__ gl_t pmul2(gl_t a, gl_t b, gl_t c, gl_t d) { return gl_add(gl_mul(a, b), gl_mul(c, d)); }
