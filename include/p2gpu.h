@@ -133,6 +133,20 @@ typedef struct {
     uint64_t pow_witness;
     uint64_t query_indices[64];
 } p2g_transcript;
+/* Device-side PartitionWitness::full_witness (plonky2 iop/witness.rs) in front of the prover.
+ * The host keeps one value per copy-constraint partition ("slot"); `wire_map[col*n + row]` is the slot
+ * of that wire cell (or -1 for an empty cell) and (fixed_pos, fixed_val) are the constant cells.
+ * p2g_prove_slots uploads the slot values (a few MB instead of the num_wires * n matrix), gathers the
+ * wire matrix on the device and runs the same prover as p2g_prove_dev; the proof is identical to
+ * p2g_prove on the host-filled matrix. */
+typedef struct p2g_wmap p2g_wmap;
+int32_t p2g_wmap_load(p2g_ctx* ctx, const p2g_circuit* c, const int32_t* wire_map /*[num_wires][n]*/, uint32_t num_slots,
+                      const int64_t* fixed_pos, const uint64_t* fixed_val, uint32_t num_fixed, p2g_wmap** out);
+int32_t p2g_wmap_free(p2g_ctx* ctx, p2g_wmap* m);
+int32_t p2g_prove_slots(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_host /*[num_slots]*/,
+                        const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
+/* the gathered wire matrix of the last p2g_prove_slots call is not kept; this fills one for tests */
+int32_t p2g_wmap_fill(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_host, uint64_t* wires_out_host);
 int32_t p2g_last_transcript(p2g_ctx* ctx, p2g_transcript* out);
 int32_t p2g_last_zs_values(p2g_ctx* ctx, uint64_t* out /*[num_zs_cols][n]*/);
 int32_t p2g_last_quotient_chunks(p2g_ctx* ctx, uint64_t* out /*[num_challenges*qdf][n]*/);

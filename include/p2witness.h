@@ -58,7 +58,20 @@ void p2w_program_destroy(p2w_program* p);
  * wires_out: [num_wires][n] column-major, fully overwritten. */
 int32_t p2w_generate(const p2w_program* p, const int32_t* input_slots, const uint64_t* input_vals,
                      uint32_t num_inputs, uint64_t* wires_out);
-/* same for `count` independent witnesses laid out back to back (OpenMP over witnesses) */
+/* Two-step form for the device-side wire fill (p2g_prove_slots, include/p2gpu.h).  The generators and
+ * set_lookup_wires fill an "extended slot vector" -- the analogue of PartitionWitness::values
+ * (iop/witness.rs): program slots, then the multiplicity of every LUT entry, then the 111 internal
+ * wires of every PoseidonGate row -- and `wire_map` ([num_wires][n], index into that vector or -1)
+ * plus the list of constant cells say where each value goes, which is what
+ * PartitionWitness::full_witness does with representative_map. */
+uint32_t p2w_ext_slots(const p2w_program* p);
+int32_t p2w_wire_map(const p2w_program* p, int32_t* map_out /*[num_wires][n]*/);
+int32_t p2w_fixed_cells(const p2w_program* p, uint32_t* count, const int64_t** pos, const uint64_t** val);
+int32_t p2w_generate_slots(const p2w_program* p, const int32_t* input_slots, const uint64_t* input_vals,
+                           uint32_t num_inputs, uint64_t* ext_out /*[p2w_ext_slots]*/);
+int32_t p2w_generate_slots_many(const p2w_program* p, const int32_t* input_slots, const uint64_t* input_vals,
+                                uint32_t num_inputs, uint32_t count, uint64_t* ext_out);
+/* p2w_generate for `count` independent witnesses laid out back to back (OpenMP over witnesses) */
 int32_t p2w_generate_many(const p2w_program* p, const int32_t* input_slots, const uint64_t* input_vals,
                           uint32_t num_inputs, uint32_t count, uint64_t* wires_out);
 #ifdef __cplusplus

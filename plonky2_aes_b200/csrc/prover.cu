@@ -623,6 +623,87 @@ extern "C" int32_t p2g_prove_dev(p2g_ctx* ctx, const p2g_circuit* c, const uint6
                                  uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {
     return prove_impl(ctx, c, wires_dev, false, public_inputs, proof_out, proof_cap_words, proof_words_out);
 }
+// ---- device-side PartitionWitness::full_witness (iop/witness.rs) --------------------------------
+struct p2g_wmap {
+    int32_t* d_map;      // [W][n] slot index or -1
+    int64_t* d_fixed_pos; gl_t* d_fixed_val;
+    uint32_t num_slots, num_fixed;
+    size_t cells;
+};
+__global__ void __launch_bounds__(256)
+wire_gather_kernel(const int32_t* __restrict__ map, const gl_t* __restrict__ slots, size_t cells, gl_t* __restrict__ wires) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    const int32_t m = __ldg(map + i);
+    wires[i] = m >= 0 ? __ldg(slots + m) : 0;
+}
+__global__ void __launch_bounds__(256)
+wire_fixed_kernel(const int64_t* __restrict__ pos, const gl_t* __restrict__ val, uint32_t count, gl_t* __restrict__ wires) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) wires[pos[i]] = val[i];
+}
+extern "C" int32_t p2g_wmap_load(p2g_ctx* ctx, const p2g_circuit* c, const int32_t* wire_map, uint32_t num_slots,
+                                 const int64_t* fixed_pos, const uint64_t* fixed_val, uint32_t num_fixed, p2g_wmap** out) {
+    if (!ctx || !c || !wire_map || !out || !num_slots || (num_fixed && (!fixed_pos || !fixed_val))) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    const size_t cells = (size_t)c->cd.W << c->cd.logn;
+    for (size_t i = 0; i < cells; i++) if (wire_map[i] >= (int32_t)num_slots || wire_map[i] < -1) { ctx->err = "wire map entry out of range"; return P2G_E_BADARG; }
+    for (uint32_t i = 0; i < num_fixed; i++) if (fixed_pos[i] < 0 || (size_t)fixed_pos[i] >= cells || fixed_val[i] >= GL_P) { ctx->err = "fixed cell out of range"; return P2G_E_BADARG; }
+    p2g_wmap* m = new p2g_wmap();
+    m->num_slots = num_slots; m->num_fixed = num_fixed; m->cells = cells;
+    m->d_map = nullptr; m->d_fixed_pos = nullptr; m->d_fixed_val = nullptr;
+    bool ok = cudaMalloc(&m->d_map, cells * sizeof(int32_t)) == cudaSuccess;
+    if (ok && num_fixed) ok = cudaMalloc(&m->d_fixed_pos, num_fixed * sizeof(int64_t)) == cudaSuccess && cudaMalloc(&m->d_fixed_val, num_fixed * sizeof(gl_t)) == cudaSuccess;
+    if (ok) ok = cudaMemcpyAsync(m->d_map, wire_map, cells * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->st) == cudaSuccess;
+    if (ok && num_fixed) ok = cudaMemcpyAsync(m->d_fixed_pos, fixed_pos, num_fixed * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st) == cudaSuccess &&
+                              cudaMemcpyAsync(m->d_fixed_val, fixed_val, num_fixed * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st) == cudaSuccess;
+    if (ok) ok = ctx_wait(ctx) == cudaSuccess;
+    if (!ok) { cudaFree(m->d_map); cudaFree(m->d_fixed_pos); cudaFree(m->d_fixed_val); delete m; ctx->err = "wmap upload"; return P2G_E_CUDA; }
+    *out = m;
+    return P2G_OK;
+}
+extern "C" int32_t p2g_wmap_free(p2g_ctx* ctx, p2g_wmap* m) {
+    if (!ctx || !m) return P2G_E_BADARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    cudaFree(m->d_map); cudaFree(m->d_fixed_pos); cudaFree(m->d_fixed_val);
+    delete m;
+    return P2G_OK;
+}
+// slots (host) -> wire matrix (device, from the context's pool)
+static int wmap_gather(p2g_ctx* ctx, const p2g_wmap* m, const uint64_t* slots_host, gl_t** d_wires_out) {
+    int rc; gl_t *d_slots, *d_wires;
+    if ((rc = ctx_alloc(ctx, &d_slots, m->num_slots))) return rc;
+    if ((rc = ctx_alloc(ctx, &d_wires, m->cells))) return rc;
+    CU(cudaMemcpyAsync(d_slots, slots_host, (size_t)m->num_slots * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+    P2G_COUNT_LAUNCH(1); wire_gather_kernel<<<(unsigned)((m->cells + 255) / 256), 256, 0, ctx->st>>>(m->d_map, d_slots, m->cells, d_wires);
+    if (m->num_fixed) { P2G_COUNT_LAUNCH(1); wire_fixed_kernel<<<(m->num_fixed + 255) / 256, 256, 0, ctx->st>>>(m->d_fixed_pos, m->d_fixed_val, m->num_fixed, d_wires); }
+    CU(cudaGetLastError());
+    ctx_free(ctx, d_slots);                 // stream-ordered: released after the gather
+    *d_wires_out = d_wires;
+    return P2G_OK;
+}
+extern "C" int32_t p2g_prove_slots(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_host,
+                                   const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {
+    if (!ctx || !c || !m || !slots_host) return P2G_E_BADARG;
+    if (m->cells != ((size_t)c->cd.W << c->cd.logn)) { ctx->err = "wire map belongs to another circuit"; return P2G_E_BADARG; }
+    CU(cudaSetDevice(ctx->device));
+    gl_t* d_wires; int rc;
+    if ((rc = wmap_gather(ctx, m, slots_host, &d_wires))) return rc;
+    rc = prove_impl(ctx, c, d_wires, false, public_inputs, proof_out, proof_cap_words, proof_words_out);
+    ctx_free(ctx, d_wires);
+    return rc;
+}
+extern "C" int32_t p2g_wmap_fill(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_host, uint64_t* wires_out_host) {
+    if (!ctx || !c || !m || !slots_host || !wires_out_host) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    gl_t* d_wires; int rc;
+    if ((rc = wmap_gather(ctx, m, slots_host, &d_wires))) return rc;
+    CU(cudaMemcpyAsync(wires_out_host, d_wires, m->cells * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(ctx_wait(ctx));
+    ctx_free(ctx, d_wires);
+    return P2G_OK;
+}
 extern "C" int32_t p2g_last_transcript(p2g_ctx* ctx, p2g_transcript* out) {
     if (!ctx || !out) return P2G_E_BADARG;
     *out = ctx->transcript; return P2G_OK;

@@ -62,6 +62,11 @@ struct p2w_program {
     std::vector<int32_t> lookup_counts, lookup_slots, lookup_padding, lookup_off;
     std::vector<int64_t> mult_pos;
     std::vector<int32_t> poseidon_rows;
+    // extended slot vector ("partition values"): [program slots | multiplicities of every LUT entry |
+    // 111 internal wires per PoseidonGate row]; wire_map indexes it (-1 = empty cell)
+    uint32_t ext_mult, ext_pos, ext_total;
+    std::vector<int32_t> wire_map;
+    std::vector<int64_t> fixed_pos_eff; std::vector<uint64_t> fixed_val_eff;   // fixed cells not overridden by the map
 };
 
 extern "C" int32_t p2w_program_create(const p2w_program_desc* d, p2w_program** out) {
@@ -90,6 +95,23 @@ extern "C" int32_t p2w_program_create(const p2w_program_desc* d, p2w_program** o
     p->lookup_slots.assign(d->lookup_slots, d->lookup_slots + totl);
     p->mult_pos.assign(d->mult_pos, d->mult_pos + tot);
     if (d->num_poseidon) p->poseidon_rows.assign(d->poseidon_rows, d->poseidon_rows + (size_t)25 * d->num_poseidon);
+    // wire map over the extended slot vector
+    const size_t n = (size_t)1 << d->log_n;
+    p->ext_mult = d->num_slots;
+    p->ext_pos = p->ext_mult + (uint32_t)tot;
+    p->ext_total = p->ext_pos + 111u * d->num_poseidon;
+    p->wire_map = p->wire_slot;
+    for (uint32_t k = 0; k < d->num_poseidon; k++) {
+        const size_t row = (size_t)p->poseidon_rows[(size_t)25 * k];
+        for (int c = 24; c < 135; c++) p->wire_map[(size_t)c * n + row] = (int32_t)(p->ext_pos + 111u * k + (uint32_t)(c - 24));
+    }
+    for (size_t e = 0; e < tot; e++) p->wire_map[p->mult_pos[e]] = (int32_t)(p->ext_mult + e);
+    for (uint32_t i = 0; i < d->num_fixed; i++) {
+        const int32_t m = p->wire_map[p->fixed_pos[i]];
+        if (m >= (int32_t)p->ext_mult) continue;            // a multiplicity / Poseidon cell wins, as in the fill order
+        p->wire_map[p->fixed_pos[i]] = -1;
+        p->fixed_pos_eff.push_back(p->fixed_pos[i]); p->fixed_val_eff.push_back(p->fixed_val[i]);
+    }
     *out = p;
     return 0;
 }
@@ -101,8 +123,10 @@ static inline int set_slot(std::vector<uint64_t>& val, std::vector<uint8_t>& has
     return 0;
 }
 
-extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, const uint64_t* in_vals, uint32_t num_inputs,
-                                uint64_t* wires) {
+// Runs the generators and set_lookup_wires: fills the extended slot vector (p->ext_total words).
+extern "C" int32_t p2w_generate_slots(const p2w_program* p, const int32_t* in_slots, const uint64_t* in_vals, uint32_t num_inputs,
+                                      uint64_t* ext) {
+    if (!p || !ext || (num_inputs && (!in_slots || !in_vals))) return P2W_E_BADARG;
     const p2w_program_desc& d = p->d;
     std::vector<uint64_t> val(d.num_slots, 0);
     std::vector<uint8_t> has(d.num_slots, 0);
@@ -151,17 +175,13 @@ extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, c
         default: return P2W_E_BADARG;
         }
     }
-    const size_t n = (size_t)1 << d.log_n, cells = (size_t)d.num_wires * n;
-    const int32_t* ws = p->wire_slot.data();
-    for (size_t i = 0; i < cells; i++) wires[i] = ws[i] >= 0 ? val[ws[i]] : 0;
-    for (uint32_t i = 0; i < d.num_fixed; i++) wires[p->fixed_pos[i]] = p->fixed_val[i];
-    for (uint32_t k = 0; k < d.num_poseidon; k++) {       // internal wires of every PoseidonGate row
-        const size_t row = (size_t)p->poseidon_rows[(size_t)25 * k];
-        for (int c = 24; c < 135; c++) wires[(size_t)c * n + row] = ptrace[(size_t)123 * k + c - 12];
-    }
+    memcpy(ext, val.data(), (size_t)d.num_slots * sizeof(uint64_t));
+    for (uint32_t k = 0; k < d.num_poseidon; k++)           // internal wires 24..134 of every PoseidonGate row
+        memcpy(ext + p->ext_pos + (size_t)111 * k, ptrace.data() + (size_t)123 * k + 12, 111 * sizeof(uint64_t));
     // set_lookup_wires: multiplicities
     for (uint32_t l = 0; l < d.num_luts; l++) {
-        std::vector<uint64_t> mult(p->lut_lens[l], 0);
+        uint64_t* mult = ext + p->ext_mult + p->lut_off[l];
+        memset(mult, 0, (size_t)p->lut_lens[l] * sizeof(uint64_t));
         const int32_t* ls = p->lookup_slots.data() + p->lookup_off[l];
         for (int32_t i = 0; i < p->lookup_counts[l]; i++) {
             if (!has[ls[i]]) return P2W_E_UNSET;
@@ -170,10 +190,48 @@ extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, c
             mult[p->key_to_entry[l][x]]++;
         }
         if (p->lut_lens[l]) mult[0] += p->lookup_padding[l];
-        const int64_t* mp = p->mult_pos.data() + p->lut_off[l];
-        for (int32_t e = 0; e < p->lut_lens[l]; e++) wires[mp[e]] = mult[e];
     }
     return 0;
+}
+extern "C" uint32_t p2w_ext_slots(const p2w_program* p) { return p ? p->ext_total : 0; }
+extern "C" int32_t p2w_wire_map(const p2w_program* p, int32_t* map_out) {
+    if (!p || !map_out) return P2W_E_BADARG;
+    memcpy(map_out, p->wire_map.data(), p->wire_map.size() * sizeof(int32_t));
+    return 0;
+}
+extern "C" int32_t p2w_fixed_cells(const p2w_program* p, uint32_t* count, const int64_t** pos, const uint64_t** val) {
+    if (!p || !count || !pos || !val) return P2W_E_BADARG;
+    *count = (uint32_t)p->fixed_pos_eff.size(); *pos = p->fixed_pos_eff.data(); *val = p->fixed_val_eff.data();
+    return 0;
+}
+// PartitionWitness::full_witness on the host: wires[cell] = ext[wire_map[cell]], then the fixed cells.
+// (p2g_prove_slots does the same gather on the device.)
+extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, const uint64_t* in_vals, uint32_t num_inputs,
+                                uint64_t* wires) {
+    if (!p || !wires) return P2W_E_BADARG;
+    std::vector<uint64_t> ext(p->ext_total);
+    int32_t rc = p2w_generate_slots(p, in_slots, in_vals, num_inputs, ext.data());
+    if (rc) return rc;
+    const size_t cells = (size_t)p->d.num_wires << p->d.log_n;
+    const int32_t* wm = p->wire_map.data();
+    for (size_t i = 0; i < cells; i++) wires[i] = wm[i] >= 0 ? ext[wm[i]] : 0;
+    for (size_t i = 0; i < p->fixed_pos_eff.size(); i++) wires[p->fixed_pos_eff[i]] = p->fixed_val_eff[i];
+    return 0;
+}
+
+extern "C" int32_t p2w_generate_slots_many(const p2w_program* p, const int32_t* in_slots, const uint64_t* in_vals, uint32_t num_inputs,
+                                           uint32_t count, uint64_t* ext_out) {
+    if (!p || !ext_out) return P2W_E_BADARG;
+    int32_t rc_all = 0;
+#pragma omp parallel for schedule(dynamic)
+    for (int64_t w = 0; w < (int64_t)count; w++) {
+        int32_t rc = p2w_generate_slots(p, in_slots, in_vals + (size_t)w * num_inputs, num_inputs, ext_out + (size_t)w * p->ext_total);
+        if (rc) {
+#pragma omp critical
+            rc_all = rc;
+        }
+    }
+    return rc_all;
 }
 
 extern "C" int32_t p2w_generate_many(const p2w_program* p, const int32_t* in_slots, const uint64_t* in_vals, uint32_t num_inputs,

@@ -498,6 +498,7 @@ class CircuitData:
         """Upload the preprocessed data: commits (constants, sigmas) on the GPU and derives the
         circuit digest = hash_no_pad(cap || hash_pad([]) || degree_bits) on the device."""
         self.ctx = ctx
+        self._wmap = None
         lib = ctx.lib
         f = self.config.fri_config
         from .polynomial_batch import PolynomialBatch
@@ -589,6 +590,12 @@ class CircuitData:
         lib.p2w_program_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.p2w_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.p2w_generate_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.p2w_ext_slots.argtypes = [C.c_void_p]
+        lib.p2w_ext_slots.restype = C.c_uint32
+        lib.p2w_wire_map.argtypes = [C.c_void_p, C.c_void_p]
+        lib.p2w_fixed_cells.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        lib.p2w_generate_slots.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.p2w_generate_slots_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         return lib
 
     def _program(self):
@@ -628,6 +635,75 @@ class CircuitData:
                               -12: "generator input unset"}.get(rc, f"witness error {rc}"))
         return out
 
+    # ---- slot form: the device fills the wire matrix (p2g_prove_slots) ---------------------------
+    _WERR = {-10: "partition set twice with different values", -11: "lookup input not in table", -12: "generator input unset"}
+
+    @property
+    def ext_slots(self):
+        """length of the extended slot vector (PartitionWitness::values analogue, include/p2witness.h)"""
+        prog = self._program()
+        return int(self._wlib.p2w_ext_slots(prog))
+
+    def generate_slots(self, pw, out=None):
+        """generate_partial_witness + set_lookup_wires, WITHOUT full_witness(): one value per partition."""
+        prog = self._program()
+        slots = np.array([self._slot(t) for t in pw.values], dtype=np.int32)
+        vals = np.array(list(pw.values.values()), dtype=np.uint64)
+        if out is None:
+            out = np.empty(self.ext_slots, dtype=np.uint64)
+        rc = self._wlib.p2w_generate_slots(prog, slots.ctypes.data, vals.ctypes.data, len(slots), out.ctypes.data)
+        if rc != 0:
+            raise ValueError(self._WERR.get(rc, f"witness error {rc}"))
+        return out
+
+    def generate_slots_many(self, targets, values, out=None):
+        """Batch form of generate_slots: [count][ext_slots]."""
+        prog = self._program()
+        slots = np.array([self._slot(t) for t in targets], dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        count = values.shape[0]
+        if out is None:
+            out = np.empty((count, self.ext_slots), dtype=np.uint64)
+        rc = self._wlib.p2w_generate_slots_many(prog, slots.ctypes.data, values.ctypes.data, len(slots), count, out.ctypes.data)
+        if rc != 0:
+            raise ValueError(self._WERR.get(rc, f"witness error {rc}"))
+        return out
+
+    def load_wire_map(self, ctx=None, circuit=None):
+        """Uploads the wire map (representative_map analogue) next to a loaded circuit; returns the handle."""
+        ctx = ctx or self.ctx
+        circuit = circuit or self._gpu_circuit
+        if ctx is None or circuit is None:
+            raise ffi.P2GError(-1, "circuit not loaded on a GPU context (no CPU fallback)")
+        prog = self._program()
+        wm = np.empty((NUM_WIRES, self.n), dtype=np.int32)
+        assert self._wlib.p2w_wire_map(prog, wm.ctypes.data) == 0
+        cnt, pos, val = C.c_uint32(), C.c_void_p(), C.c_void_p()
+        assert self._wlib.p2w_fixed_cells(prog, C.byref(cnt), C.byref(pos), C.byref(val)) == 0
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2g_wmap_load(ctx.handle, circuit, wm.ctypes.data, self.ext_slots, pos, val, cnt.value, C.byref(h)))
+        return h
+
+    def prove_slots(self, slots, ctx=None, circuit=None, wmap=None):
+        """Slot vector -> proof; the wire matrix is gathered on the device (PartitionWitness::full_witness)."""
+        ctx = ctx or self.ctx
+        circuit = circuit or self._gpu_circuit
+        if ctx is None or circuit is None:
+            raise ffi.P2GError(-1, "circuit not loaded on a GPU context (no CPU fallback)")
+        if wmap is None:
+            if getattr(self, "_wmap", None) is None:
+                self._wmap = self.load_wire_map(ctx, circuit)
+            wmap = self._wmap
+        words = self.proof_words
+        out = np.empty(words, dtype=np.uint64)
+        got = C.c_size_t()
+        slots = np.ascontiguousarray(slots, dtype=np.uint64)
+        rc = ctx.lib.p2g_prove_slots(ctx.handle, circuit, wmap, slots.ctypes.data, None, out.ctypes.data, words, C.byref(got))
+        if rc == -3:
+            raise ValueError("witness does not satisfy the circuit (P2G_E_UNSAT)")
+        ctx.check(rc)
+        return out[:got.value]
+
     def generate_witnesses(self, targets, values, out=None):
         """Batch form: `targets` (list) and `values` [count][len(targets)] -> [count][135][n]."""
         prog = self._program()
@@ -644,8 +720,7 @@ class CircuitData:
     # ---- prove ------------------------------------------------------------------------------
     def prove(self, pw):
         """CircuitData::prove(pw) -> proof (flat u64 words, layout in DESIGN.md)."""
-        wires = self.generate_witness(pw)
-        return self.prove_wires(wires)
+        return self.prove_slots(self.generate_slots(pw))
 
     def prove_wires(self, wires):
         ctx = self.ctx

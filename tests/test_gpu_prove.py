@@ -162,3 +162,45 @@ def test_error_behaviour(gpu_ctx, oracle):
     assert lib.p2g_prove(gpu_ctx.handle, data._gpu_circuit, wires.ctypes.data, None, out.ctypes.data, out.size, C.byref(got)) == -2
     # the context is still usable afterwards
     assert oracle_lib.OracleCircuit(oracle, data).verify(data.prove_wires(wires)) == 0
+
+
+def test_prove_slots_device_wire_fill(gpu_ctx, oracle):
+    """p2g_prove_slots: the wire matrix gathered on the device from one value per partition
+    (PartitionWitness::full_witness, iop/witness.rs) equals the host fill, and the proof is
+    bit-identical to p2g_prove on the host matrix.  AES-GCM (LUT multiplicities, constant cells)
+    and Feistel (PoseidonGate internal wires)."""
+    lib = gpu_ctx.lib
+    data, wires, tg = circuits.aes_gcm(13, True)
+    data.load(gpu_ctx)
+    vals = circuits.gcm_inputs(tg, 11, 3)
+    host = data.generate_witnesses(tg.input_targets(), vals)
+    slots = data.generate_slots_many(tg.input_targets(), vals)
+    assert slots.shape == (3, data.ext_slots)
+    wmap = data.load_wire_map()
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    for i in range(3):
+        filled = np.empty_like(host[i])
+        gpu_ctx.check(lib.p2g_wmap_fill(gpu_ctx.handle, data._gpu_circuit, wmap, slots[i].ctypes.data, filled.ctypes.data))
+        assert np.array_equal(filled, host[i])
+        p_slots = data.prove_slots(slots[i], wmap=wmap)
+        assert np.array_equal(p_slots, data.prove_wires(host[i]))
+        assert oc.verify(p_slots) == 0
+    oc.free()
+    # bad arguments: a map entry past the slot vector
+    bad = np.full((135, data.n), data.ext_slots, dtype=np.int32)
+    h = C.c_void_p()
+    assert lib.p2g_wmap_load(gpu_ctx.handle, data._gpu_circuit, bad.ctypes.data, data.ext_slots, None, None, 0, C.byref(h)) == -2
+    gpu_ctx.check(lib.p2g_wmap_free(gpu_ctx.handle, wmap))
+
+    fdata, fwires, (st, ks, out, state, keys, exp) = circuits.feistel_poseidon()
+    from plonky2_aes_b200.host.circuit_builder import PartialWitness
+    fdata.load(gpu_ctx)
+    pw = PartialWitness()
+    for t, v in zip(st, state):
+        pw.set_target(t, v)
+    for kt, kv in zip(ks, keys):
+        for t, v in zip(kt, kv):
+            pw.set_target(t, v)
+    for t, v in zip(out, exp):
+        pw.set_target(t, v)
+    assert np.array_equal(fdata.prove(pw), fdata.prove_wires(fwires))      # prove(pw) goes through the slot path
