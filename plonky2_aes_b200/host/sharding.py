@@ -59,12 +59,22 @@ class BatchProver:
         self.data, self.ctxs = data, ctxs
         self.handles = [data._gpu_circuit if c is data.ctx else data.load_handle(c) for c in ctxs]
 
-    def prove_many(self, wires_list, device_resident=False):
+    def prove_many(self, wires_list, device_resident=False, slots=False):
+        """wires_list: wire matrices [135][n] (host, or device with device_resident=True), or -- with
+        slots=True -- slot vectors from CircuitData.generate_slots*, gathered into wires on the GPU."""
         import ctypes as C
         lib = self.ctxs[0].lib
         words = self.data.proof_words
         out = [None] * len(wires_list)
-        fn = lib.p2g_prove_dev if device_resident else lib.p2g_prove
+        if slots:
+            if getattr(self, "wmap", None) is None:      # device-global, shared by all contexts of this GPU
+                self.wmap = self.data.load_wire_map(self.ctxs[0], self.handles[0])
+            wmap = self.wmap
+
+            def fn(ctx_h, circ_h, ptr, pi, buf, cap, got):
+                return lib.p2g_prove_slots(ctx_h, circ_h, wmap, ptr, pi, buf, cap, got)
+        else:
+            fn = lib.p2g_prove_dev if device_resident else lib.p2g_prove
         errors = []
 
         def worker(t):
