@@ -7,6 +7,7 @@ use std::os::raw::{c_char, c_void};
 
 #[repr(C)] pub struct p2g_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct p2g_batch { _p: [u8; 0] }
+#[repr(C)] pub struct p2g_wmap { _p: [u8; 0] }
 #[repr(C)] pub struct p2g_circuit { _p: [u8; 0] }
 
 pub const P2G_OK: i32 = 0;
@@ -72,6 +73,14 @@ extern "C" {
     pub fn p2g_proof_words(c: *const p2g_circuit) -> usize;
     pub fn p2g_prove(ctx: *mut p2g_ctx, c: *const p2g_circuit, wires: *const u64, public_inputs: *const u64,
                      proof_out: *mut u64, cap_words: usize, words_out: *mut usize) -> i32;
+    pub fn p2g_prove_dev(ctx: *mut p2g_ctx, c: *const p2g_circuit, wires_dev: *const u64, public_inputs: *const u64,
+                         proof_out: *mut u64, cap_words: usize, words_out: *mut usize) -> i32;
+    // device-side PartitionWitness::full_witness: wire_map = representative_map flattened to [col*n + row]
+    pub fn p2g_wmap_load(ctx: *mut p2g_ctx, c: *const p2g_circuit, wire_map: *const i32, num_slots: u32,
+                         fixed_pos: *const i64, fixed_val: *const u64, num_fixed: u32, out: *mut *mut p2g_wmap) -> i32;
+    pub fn p2g_wmap_free(ctx: *mut p2g_ctx, m: *mut p2g_wmap) -> i32;
+    pub fn p2g_prove_slots(ctx: *mut p2g_ctx, c: *const p2g_circuit, m: *const p2g_wmap, slots: *const u64,
+                           public_inputs: *const u64, proof_out: *mut u64, cap_words: usize, words_out: *mut usize) -> i32;
     pub fn p2g_set_timing(ctx: *mut p2g_ctx, enabled: i32) -> i32;
     pub fn p2g_last_timings(ctx: *mut p2g_ctx, out: *mut p2g_timings) -> i32;
 }
