@@ -531,11 +531,17 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         for (int i = 0; i < pos; i++) ps.s[i] = ch.in_buf[i];
         unsigned long long* d_best;
         CU(cudaMallocFromPoolAsync((void**)&d_best, 8, ctx->pool, st));
-        const unsigned long long WIN = 1ull << 18;   // expected hit within 2^16 candidates; P(miss per window) = e^-4
+        // Windows of candidates in increasing order keep the "lowest nonce" semantics.  The first window
+        // has 2^pow_bits candidates (a hit with probability 1 - 1/e), then the windows double up to
+        // 2^(pow_bits+2): about 2 x 2^pow_bits permutations on average instead of a fixed 4 x -- with
+        // several proofs in flight the grind is throughput, not latency.
+        unsigned long long win = 1ull << (d.pow_bits < 12 ? 12 : d.pow_bits);
+        const unsigned long long win_max = win << 2;
         bool found = false;
-        for (unsigned long long base = 0; !found && base < (1ull << 30); base += WIN) {
+        int windows = 0;     // bounded: 1024 windows without a hit cannot happen with a working kernel (e^-4000)
+        for (unsigned long long base = 0; !found && windows < 1024; base += win, win = win < win_max ? win * 2 : win, windows++) {
             CU(cudaMemsetAsync(d_best, 0xFF, 8, st));
-            P2G_COUNT_LAUNCH(1); pow_grind_kernel<<<(unsigned)(WIN / 256), 256, 0, st>>>(ps, pos, d.pow_bits, base, d_best);
+            P2G_COUNT_LAUNCH(1); pow_grind_kernel<<<(unsigned)(win / 256), 256, 0, st>>>(ps, pos, d.pow_bits, base, d_best);
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(ctx->pinned, d_best, 8, cudaMemcpyDeviceToHost, st));
             CU(ctx_wait(ctx));
