@@ -204,3 +204,29 @@ def test_prove_slots_device_wire_fill(gpu_ctx, oracle):
     for t, v in zip(out, exp):
         pw.set_target(t, v)
     assert np.array_equal(fdata.prove(pw), fdata.prove_wires(fwires))      # prove(pw) goes through the slot path
+
+
+def test_batch_prover_proofs_in_flight(gpu_ctx, oracle):
+    """Several proofs in flight on one GPU (one context + host thread each, the bench.py / config-5
+    scheme): proofs are identical to the one-at-a-time proofs, for host-filled wires and for the
+    device wire fill, also when the same batch is proved twice (pool reuse)."""
+    from plonky2_aes_b200.host.polynomial_batch import Context
+    from plonky2_aes_b200.host.sharding import BatchProver
+    data, _, tg = circuits.aes_gcm(13, True)
+    data.load(gpu_ctx)
+    vals = circuits.gcm_inputs(tg, 31, 7)
+    host = data.generate_witnesses(tg.input_targets(), vals)
+    slots = data.generate_slots_many(tg.input_targets(), vals)
+    seq = [data.prove_wires(w) for w in host]
+    extra = [Context(0) for _ in range(3)]
+    bp = BatchProver(data, [gpu_ctx] + extra)
+    for _ in range(2):
+        par = bp.prove_many([w for w in host])
+        par_slots = bp.prove_many([s for s in slots], slots=True)
+        for a, b, c in zip(seq, par, par_slots):
+            assert np.array_equal(a, b) and np.array_equal(a, c)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    assert all(oc.verify(p) == 0 for p in par_slots)
+    oc.free()
+    for c in extra:
+        c.close()
