@@ -230,3 +230,11 @@ def test_batch_prover_proofs_in_flight(gpu_ctx, oracle):
     oc.free()
     for c in extra:
         c.close()
+
+
+def test_aes_gcm_1024_bytes_n65536(gpu_ctx, oracle):
+    """A larger instance of the same circuit family: 64 AES blocks, n = 2^16 (LDE domain 2^19, 2^14-point
+    NTT chunks with a 4-way fold, final FRI polynomial of 16 coefficients)."""
+    data, wires, _ = circuits.aes_gcm(1024, True)
+    assert data.n == 1 << 16
+    _check(gpu_ctx, oracle, data, wires).free()
