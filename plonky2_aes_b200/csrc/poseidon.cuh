@@ -92,6 +92,7 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 #ifndef P2G_MDS_SPLIT
 #define P2G_MDS_SPLIT 1
 #endif
+
 #if P2G_MDS_SPLIT
 // Split-circulant form of the same layer.  The MDS matrix is circ(C) (+ 8 on entry [0][0]), i.e.
 // [[A, B], [B, A]] in 6x6 blocks, so with X+ = x_lo + x_hi and X- = x_lo - x_hi (word halves j, j+6)
