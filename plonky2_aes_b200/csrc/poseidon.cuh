@@ -71,9 +71,15 @@ __device__ __forceinline__ void acc_mul(Acc160& A, gl_t a, gl_t b) {
         : "+r"(A.w[0]), "+r"(A.w[1]), "+r"(A.w[2]), "+r"(A.w[3]), "+r"(A.w[4]) : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
 }
 __device__ __forceinline__ gl_t acc_fold(const Acc160& A) { return gl_fold5(A.w[0], A.w[1], A.w[2], A.w[3], A.w[4]); }
+// P2G_DIAG_NO_SBOX / P2G_DIAG_NO_MDS: timing diagnostics only (tools/poseidon_overlap.sh) -- they remove the
+// integer or the FP64 half of every round to measure how much the two halves overlap; results are wrong.
 __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
+#ifdef P2G_DIAG_NO_SBOX
+    return x + 1;
+#else
     gl_t x2 = psqr(x), x4 = psqr(x2), x3 = pmul(x, x2);
     return pmul(x3, x4);
+#endif
 }
 // s <- MDS * s + RC[next_row]   (lazy in, lazy out) on the FP64 pipe.
 // The circulant coefficients are <= 41, so every partial sum of  c_i * (32-bit half)  plus a 32-bit
@@ -119,6 +125,9 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
         const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
         const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
         const double ph = __dadd_rn(x0h, x1h), mh = __dsub_rn(x0h, x1h);
+#ifdef P2G_DIAG_NO_MDS
+        apl[j] = __dadd_rn(apl[j], pl); aph[j] = __dadd_rn(aph[j], ph); aml[j] = __dadd_rn(aml[j], ml); amh[j] = __dadd_rn(amh[j], mh);
+#else
 #pragma unroll
         for (int r = 0; r < 6; r++) {
             const double a = C[(j - r + 12) % 12], b = C[(j + 6 - r + 12) % 12];
@@ -126,6 +135,7 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
             apl[r] = __fma_rn(pl, P, apl[r]); aml[r] = __fma_rn(ml, N, aml[r]);
             aph[r] = __fma_rn(ph, P, aph[r]); amh[r] = __fma_rn(mh, N, amh[r]);
         }
+#endif
         if (j == 0) {                                            // + 8 x_0 on row 0 only
             apl[0] = __fma_rn(x0l, 4., apl[0]); aml[0] = __fma_rn(x0l, 4., aml[0]);
             aph[0] = __fma_rn(x0h, 4., aph[0]); amh[0] = __fma_rn(x0h, 4., amh[0]);
@@ -234,11 +244,15 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair) {
         const int j = (jj + 1) % 12;                      // word 0 last: its S-box chain hides behind the others
         const gl_t v = j == 0 ? y0 : s[j];
         const double xl = (double)(uint32_t)v, xh = (double)(uint32_t)(v >> 32);
+#ifdef P2G_DIAG_NO_MDS
+        al[j] = __dadd_rn(al[j], xl); ah[j] = __dadd_rn(ah[j], xh);
+#else
 #pragma unroll
         for (int r = 0; r < 12; r++) {
             al[r] = __fma_rn(xl, A[12 * r + j], al[r]);
             ah[r] = __fma_rn(xh, A[12 * r + j], ah[r]);
         }
+#endif
         const double m0j = C[j] + (j == 0 ? 8. : 0.);
         tl = __fma_rn(xl, m0j, tl); th = __fma_rn(xh, m0j, th);
     }

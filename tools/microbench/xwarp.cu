@@ -1,7 +1,8 @@
 // Cross-warp pipe sharing on sm_100a: warps of one SM sub-partition run DIFFERENT pure instruction
 // streams (role = warp index mod 2).  If two instruction classes use separate pipes the mixed run
 // takes max(tA, tB); if they share one it takes tA + tB.
-// Classes: 0 = DFMA, 1 = IMAD.WIDE.U32, 2 = carry chain (IADD3 / IADD3.X), 3 = LOP3, 4 = plain IADD3
+// Classes: 0 = DFMA, 1 = IMAD.WIDE.U32, 2 = carry chain (IADD3 / IADD3.X), 3 = LOP3, 4 = plain IADD3,
+// 5 = IMAD (32-bit low), 6 = IMAD.HI, 7 = ISETP + SEL
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdint.h>
@@ -14,6 +15,9 @@ template <int OP> __device__ __forceinline__ void body(uint32_t (&a)[8], uint32_
         if (OP == 2) asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %2;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed));
         if (OP == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
         if (OP == 4) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(seed));
+        if (OP == 5) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+        if (OP == 6) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+        if (OP == 7) asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %1, %2, p; }" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
     }
 }
 template <int OPA, int OPB>
@@ -47,5 +51,8 @@ int main() {
     run<0, 1>("dfma | imad.wide", d, sms); run<0, 2>("dfma | carry2", d, sms); run<0, 3>("dfma | lop3", d, sms);
     run<1, 2>("imad.wide | carry2", d, sms); run<1, 3>("imad.wide | lop3", d, sms); run<1, 4>("imad.wide | iadd3", d, sms);
     run<2, 3>("carry2 | lop3", d, sms); run<0, 4>("dfma | iadd3", d, sms);
+    run<5, 5>("imad.lo | imad.lo", d, sms); run<6, 6>("imad.hi | imad.hi", d, sms); run<7, 7>("isetp+sel | isetp+sel", d, sms);
+    run<5, 3>("imad.lo | lop3", d, sms); run<5, 2>("imad.lo | carry2", d, sms); run<6, 3>("imad.hi | lop3", d, sms);
+    run<5, 1>("imad.lo | imad.wide", d, sms); run<5, 0>("imad.lo | dfma", d, sms); run<6, 0>("imad.hi | dfma", d, sms);
     return cudaDeviceSynchronize() != cudaSuccess;
 }
