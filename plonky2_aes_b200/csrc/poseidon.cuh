@@ -94,7 +94,10 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 // the 264 DFMAs of the other words hide the latency of that dependent multiply chain.
 // accumulators start at 2^52 + constant: the integer sits in the low mantissa bits (an F2I readout
 // from plain-constant accumulators was measured slower: 0.96 vs 0.99 G perm/s)
-#define POS_READ(d, w0, w1) do { w0 = (uint32_t)__double2loint(d); w1 = (uint32_t)__double2hiint(d) & 0xFFFFFu; } while (0)
+// Raw words of the double, exponent bits included: the offset they add to the state word
+// (0x43300000 * 2^32 * (1 + 2^32) once the low and high accumulators are combined) is already
+// subtracted from every bias table (tools/gen_poseidon_f64.py, E_READ), which saves the two masks.
+#define POS_READ(d, w0, w1) do { w0 = (uint32_t)__double2loint(d); w1 = (uint32_t)__double2hiint(d); } while (0)
 #ifndef P2G_MDS_SPLIT
 #define P2G_MDS_SPLIT 1
 #endif
