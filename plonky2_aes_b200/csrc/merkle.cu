@@ -13,8 +13,11 @@
 #ifndef POS_MINB
 #define POS_MINB 3
 #endif
-#define MERKLE_BLOCK 256
-#define MERKLE_BLOCK_LOG 8
+#ifndef POS_BLOCK
+#define POS_BLOCK 256          // threads per block of the thread-per-permutation kernels (power of two)
+#endif
+#define MERKLE_BLOCK POS_BLOCK
+#define MERKLE_BLOCK_LOG (POS_BLOCK == 64 ? 6 : POS_BLOCK == 128 ? 7 : POS_BLOCK == 256 ? 8 : 9)
 
 size_t merkle_level_offset(uint32_t log_leaves, uint32_t level) {
     size_t off = 0;
@@ -130,7 +133,7 @@ merkle_top_kernel(gl_t* digests, gl_t* cap, uint32_t log_leaves, uint32_t L, uin
 }
 
 // one grid-wide level (used when the level is too wide for the single-block finisher)
-__global__ void __launch_bounds__(256, POS_MINB)
+__global__ void __launch_bounds__(POS_BLOCK, POS_MINB)
 merkle_level_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, size_t cnt) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
@@ -216,7 +219,7 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
         const gl_t* src = digests + merkle_level_offset(log_leaves, lv);
         gl_t* dst = (lv + 1 >= L) ? cap : digests + merkle_level_offset(log_leaves, lv + 1);
         if (cnt > COOP_MAX) {
-            merkle_level_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(src, dst, cnt);
+            merkle_level_kernel<<<(uint32_t)((cnt + POS_BLOCK - 1) / POS_BLOCK), POS_BLOCK, 0, st>>>(src, dst, cnt);
         } else {
             uint32_t warps = (uint32_t)((cnt + 1) / 2);
             merkle_level_coop_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(src, dst, (uint32_t)cnt);
@@ -228,7 +231,7 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
 }
 
 // ---- INT-pipe roofline microbenchmark: chained permutations, no memory traffic ------------
-__global__ void __launch_bounds__(256, POS_MINB)
+__global__ void __launch_bounds__(POS_BLOCK, POS_MINB)
 poseidon_bench_kernel(gl_t* out, uint32_t iters) {
     gl_t s[12];
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,7 +244,7 @@ poseidon_bench_kernel(gl_t* out, uint32_t iters) {
     out[g] = acc;
 }
 int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st) {
-    poseidon_bench_kernel<<<nthreads_total / 256, 256, 0, st>>>(out, iters);
+    poseidon_bench_kernel<<<nthreads_total / POS_BLOCK, POS_BLOCK, 0, st>>>(out, iters);
     P2G_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
