@@ -113,10 +113,13 @@ __device__ __forceinline__ gl_t gl_mulw(uint32_t a, uint32_t b) { gl_t r; asm("m
 // IMAD.X).  The 64-bit sum wrapped  <=>  the high word went down: then add 2^64 = EPS once more
 // (the sum is below 2^64 + 2^64 - 2^33, so this cannot wrap again).
 __device__ __forceinline__ void gl_fold3w(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t& w0, uint32_t& w1) {
-    asm("{\n\t.reg .u32 nh;\n\t.reg .pred p;\n\t"
+    // the wrap test "high word went down" is itself a borrow (w1 - l1), turned into the all-ones mask
+    // by subc: carry-chain / IMAD.X instructions instead of ISETP + SEL, which only the ALU pipe runs
+    asm("{\n\t.reg .u32 nh, m, t;\n\t"
         "neg.s32 nh, %4;\n\t"
         "sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, nh;\n\t"
-        "setp.lt.u32 p, %1, %3;\n\t@p add.cc.u32 %0, %0, 0xffffffff;\n\t@p addc.u32 %1, %1, 0;\n\t}"
+        "sub.cc.u32 t, %1, %3;\n\tsubc.u32 m, 0, 0;\n\t"
+        "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
         : "=&r"(w0), "=&r"(w1) : "r"(l0), "r"(l1), "r"(h0));
 }
 __device__ __forceinline__ gl_t gl_fold3(uint32_t l0, uint32_t l1, uint32_t h0) {
