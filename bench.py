@@ -94,6 +94,8 @@ def run_reference(args, rank, world):
         return
     from tests import oracle_lib
     orc = oracle_lib.load()
+    # all the host threads: torchrun exports OMP_NUM_THREADS=1 to its workers
+    orc.lib.orc_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     data, tg, vals = build_workload(2)
     wires = data.generate_witnesses(tg.input_targets(), vals)
     oc = oracle_lib.OracleCircuit(orc, data)

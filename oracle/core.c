@@ -311,6 +311,13 @@ gl_t orc_challenger_get(orc_challenger* c) {
 ext_t orc_challenger_get_ext(orc_challenger* c) {
     ext_t r; r.c0 = orc_challenger_get(c); r.c1 = orc_challenger_get(c); return r;
 }
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

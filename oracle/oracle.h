@@ -134,6 +134,7 @@ long orc_prove_debug(const orc_prover_data* pd, const gl_t* wires, const gl_t* p
                      gl_t* zs_pp_lookup_values /* optional [num_zs_cols][n] */,
                      gl_t* quotient_chunk_coeffs /* optional [nch*qdf][n] */);
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* launchers such as torchrun export OMP_NUM_THREADS=1 */
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,7 @@ class Oracle:
         lib.orc_merkle_verify.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_int, vp, C.c_size_t]
         lib.orc_merkle_verify.restype = C.c_int
         lib.orc_num_threads.restype = C.c_int
+        lib.orc_set_num_threads.argtypes = [C.c_int]
         lib.orc_circuit_load.argtypes = [vp]
         lib.orc_circuit_load.restype = vp
         lib.orc_circuit_free.argtypes = [vp]
