@@ -1,5 +1,6 @@
 // Internal context/batch structures of libp2gpu.so.
 #pragma once
+#include <sched.h>
 #include "common.h"
 #include "../../include/p2gpu.h"
 #include <map>
@@ -38,7 +39,7 @@ struct p2g_ctx {
     bool keep_debug;
     float commit_ms[3];     // last commit: inverse NTT, coset LDE, Merkle (when timing is on)
     cudaEvent_t wait_ev;    // blocking-sync event: host threads sleep while they wait for the stream
-    bool blocking_wait;
+    int wait_mode;          // 0 spin (cudaStreamSynchronize), 1 blocking-sync event, 2 poll + sched_yield
 };
 
 // Host wait for everything queued on the context's stream.  A proof has ~10 such waits (Fiat-Shamir
@@ -47,7 +48,12 @@ struct p2g_ctx {
 // proofs in flight on one B200).  P2G_SYNC=block makes the threads sleep on a blocking-sync event
 // instead, for hosts with fewer cores than ranks x proofs in flight (bench.py picks it that way).
 static inline cudaError_t ctx_wait(p2g_ctx* ctx) {
-    if (!ctx->blocking_wait) return cudaStreamSynchronize(ctx->st);
+    if (ctx->wait_mode == 0) return cudaStreamSynchronize(ctx->st);
+    if (ctx->wait_mode == 2) {          // P2G_SYNC=yield: poll, giving the core away between polls
+        cudaError_t e;
+        while ((e = cudaStreamQuery(ctx->st)) == cudaErrorNotReady) sched_yield();
+        return e;
+    }
     cudaError_t e = cudaEventRecord(ctx->wait_ev, ctx->st);
     return e != cudaSuccess ? e : cudaEventSynchronize(ctx->wait_ev);
 }
