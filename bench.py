@@ -143,11 +143,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     T = max(1, args.streams)
-    # host threads waiting for their proof's stream spin by default; if this node has fewer cores than
-    # ranks x proofs in flight they sleep on a blocking-sync event instead (csrc/ctx.h, ctx_wait)
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    # host threads waiting for their proof's stream poll and yield (csrc/ctx.h, ctx_wait): robust when the
+    # node has fewer cores than ranks x proofs in flight; P2G_SYNC=spin|block selects the other modes
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    os.environ.setdefault("P2G_SYNC", "spin" if T * local_world <= cores else "block")
+    os.environ.setdefault("P2G_SYNC", "yield")
     ctx = Context(local_rank)
     lib = ctx.lib
     ctxs = [ctx] + [Context(local_rank) for _ in range(T - 1)]

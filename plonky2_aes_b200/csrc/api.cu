@@ -21,7 +21,7 @@ extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
     {
         const char* mode = getenv("P2G_SYNC");
-        ctx->wait_mode = !mode ? 0 : strcmp(mode, "block") == 0 ? 1 : strcmp(mode, "yield") == 0 ? 2 : 0;
+        ctx->wait_mode = !mode ? 2 : strcmp(mode, "block") == 0 ? 1 : strcmp(mode, "spin") == 0 ? 0 : 2;
         if (cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
             cudaStreamDestroy(ctx->st); delete ctx; return P2G_E_CUDA;
         }

@@ -44,9 +44,11 @@ struct p2g_ctx {
 
 // Host wait for everything queued on the context's stream.  A proof has ~10 such waits (Fiat-Shamir
 // round trips) and a process keeps several proofs in flight on separate host threads, times one
-// process per GPU.  Default: cudaStreamSynchronize (spins; lowest latency, 124 vs 120 proofs/s with 8
-// proofs in flight on one B200).  P2G_SYNC=block makes the threads sleep on a blocking-sync event
-// instead, for hosts with fewer cores than ranks x proofs in flight (bench.py picks it that way).
+// process per GPU, so the threads can outnumber the cores (8 ranks x 8 threads on a 32-core box).
+// Default (P2G_SYNC unset or "yield"): poll cudaStreamQuery and sched_yield between polls -- as fast
+// as spinning when cores are free (132 proofs/s) and the best mode when they are not (8 threads on
+// 4 cores: 132 vs 127 spinning vs 126 blocking).  P2G_SYNC=spin: cudaStreamSynchronize.
+// P2G_SYNC=block: sleep on a blocking-sync event (no CPU burnt while waiting).
 static inline cudaError_t ctx_wait(p2g_ctx* ctx) {
     if (ctx->wait_mode == 0) return cudaStreamSynchronize(ctx->st);
     if (ctx->wait_mode == 2) {          // P2G_SYNC=yield: poll, giving the core away between polls
