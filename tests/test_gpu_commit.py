@@ -101,23 +101,25 @@ def test_hash_and_merkle_helpers(gpu_ctx, oracle):
     assert [hex(int(v)) for v in z[0]] == ['0x3c18a9786cb0b359', '0xc4055e3364a246c3', '0x7953db0ab48808f4', '0xc71603f33a1144ca']
 
 
-def test_coset_sharded_commit_matches_full(gpu_ctx, oracle):
+@pytest.mark.parametrize("ncols,log_n", [(20, 10), (3, 14)])
+def test_coset_sharded_commit_matches_full(gpu_ctx, oracle, ncols, log_n):
     """multi-GPU coset split of one commitment, emulated on one GPU: every shard's LDE block and cap
-    entries equal the corresponding slice of the full commitment (and of the oracle's)."""
+    entries equal the corresponding slice of the full commitment (and of the oracle's).  log_n = 14
+    takes the 2^13-point / two-blocks-per-SM NTT configuration."""
     import ctypes as C
     import torch
     from plonky2_aes_b200.host.sharding import sharded_commit
-    cols = _cols(77, 20, 10)
+    cols = _cols(77, ncols, log_n)
     ob = oracle.batch(cols, True)
     dev = torch.from_numpy(cols.view(np.int64)).cuda()
-    N = 8 << 10
+    N = 8 << log_n
     for world in (1, 2, 4, 8):
         caps = []
         for rank in range(world):
-            part, h = sharded_commit(gpu_ctx, dev, 20, 10, rank, world)
+            part, h = sharded_commit(gpu_ctx, dev, ncols, log_n, rank, world)
             caps.append(part)
             per = 8 // world
-            lde = np.empty((20, per << 10), dtype=np.uint64)
+            lde = np.empty((ncols, per << log_n), dtype=np.uint64)
             gpu_ctx.check(gpu_ctx.lib.p2g_batch_get_lde(gpu_ctx.handle, h, lde.ctypes.data))
             assert np.array_equal(lde.T, ob.leaves()[rank * (N // world):(rank + 1) * (N // world)])
             gpu_ctx.check(gpu_ctx.lib.p2g_batch_free(gpu_ctx.handle, h))
