@@ -344,6 +344,7 @@ __device__ __forceinline__ gl_t acc_fold(const Acc160& A) { return A.v; }
 
 __device__ __forceinline__ gl_t gate_filter(int row, int gs, int ge, gl_t s, bool many) {
     gl_t f = 1;
+#pragma unroll 1
     for (int i = gs; i < ge; i++) if (i != row) f = gl_mul(f, gl_sub((gl_t)i, s));
     if (many) f = gl_mul(f, gl_sub(0xFFFFFFFFULL, s));
     return f;
@@ -449,6 +450,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             ADD_TERM(tb + 0, gl_mul(s_last, lz[(size_t)cd.num_sldc * N + j]));
             ADD_TERM(tb + 1, gl_mul(s_init, lz[(size_t)1 * N + j]));
             ADD_TERM(tb + 2, gl_mul(s_init, z_re));
+#pragma unroll 1
             for (int r = 0; r < cd.num_luts; r++)
                 ADD_TERM(tb + 3 + r, gl_mul(lsel[(size_t)(4 + r) * N + j], gl_sub(z_re, lut_evals[c * 8 + r])));
             gl_t re_cur = next_z_re;
@@ -459,6 +461,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
                 int b0 = poly * cd.lu_degree, b1 = min(b0 + cd.lu_degree, cd.lu_slots);
                 // prod_i f_i and sum_i m_i prod_{j != i} f_j by the running pair (S, P) <- (S f + m P, P f)
                 gl_t lut_prod = 1, lut_sum = 0, lu_prod = 1, lu_sum = 0;
+#pragma unroll 1
                 for (int s = a0; s < a1; s++) {
                     gl_t in = wl[(size_t)(3 * s) * N + j], o = wl[(size_t)(3 * s + 1) * N + j];
                     gl_t mult = wl[(size_t)(3 * s + 2) * N + j];
@@ -467,6 +470,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
                     lut_sum = pmul2(lut_sum, f, mult, lut_prod);
                     lut_prod = pmul(lut_prod, f);
                 }
+#pragma unroll 1
                 for (int s = b0; s < b1; s++) {
                     gl_t in = wl[(size_t)(2 * s) * N + j], o = wl[(size_t)(2 * s + 1) * N + j];
                     gl_t f = gl_sub(dalpha, gl_canon(pmul_add(da, o, in)));
@@ -491,6 +495,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
         gl_t f_arith = 0, f_const = 0, f_pi = 0, f_pos = 0;
         int arith_ops = 0, nconst = 0;
         bool has_poseidon = false;
+#pragma unroll 1
         for (int g = 0; g < cd.num_gates; g++) {
             const p2g_gate G = gates[g];
             if (G.num_constraints == 0) continue;
