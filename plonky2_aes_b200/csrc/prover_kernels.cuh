@@ -408,6 +408,8 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
     {
         gl_t prev[MAX_CH];
         for (int c = 0; c < nch; c++) prev[c] = zl[(size_t)c * N + j];
+        // the wire / sigma values of routed wire w+1 are loaded while wire w is multiplied in
+        gl_t wv_n = wl[j], sv_n = cs[(size_t)cd.NC * N + j];
 #pragma unroll 1
         for (int ck = 0; ck <= cd.num_prods; ck++) {
             gl_t np[MAX_CH], dp[MAX_CH];
@@ -416,7 +418,8 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             int lo = ck * cd.qdf, hi = min(lo + cd.qdf, R);
 #pragma unroll 1
             for (int w = lo; w < hi; w++) {
-                gl_t wv = wl[(size_t)w * N + j], sv = cs[(size_t)(cd.NC + w) * N + j];
+                const gl_t wv = wv_n, sv = sv_n;
+                if (w + 1 < R) { wv_n = wl[(size_t)(w + 1) * N + j]; sv_n = cs[(size_t)(cd.NC + w + 1) * N + j]; }
 #pragma unroll
                 for (int c = 0; c < MAX_CH; c++) if (c < nch) {
                     // lazy residues: they only feed the running products
@@ -461,18 +464,22 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
                 int b0 = poly * cd.lu_degree, b1 = min(b0 + cd.lu_degree, cd.lu_slots);
                 // prod_i f_i and sum_i m_i prod_{j != i} f_j by the running pair (S, P) <- (S f + m P, P f)
                 gl_t lut_prod = 1, lut_sum = 0, lu_prod = 1, lu_sum = 0;
+                gl_t in_n = 0, o_n = 0, mult_n = 0;
+                if (a0 < a1) { in_n = wl[(size_t)(3 * a0) * N + j]; o_n = wl[(size_t)(3 * a0 + 1) * N + j]; mult_n = wl[(size_t)(3 * a0 + 2) * N + j]; }
 #pragma unroll 1
                 for (int s = a0; s < a1; s++) {
-                    gl_t in = wl[(size_t)(3 * s) * N + j], o = wl[(size_t)(3 * s + 1) * N + j];
-                    gl_t mult = wl[(size_t)(3 * s + 2) * N + j];
+                    const gl_t in = in_n, o = o_n, mult = mult_n;
+                    if (s + 1 < a1) { in_n = wl[(size_t)(3 * s + 3) * N + j]; o_n = wl[(size_t)(3 * s + 4) * N + j]; mult_n = wl[(size_t)(3 * s + 5) * N + j]; }
                     gl_t f = gl_sub(dalpha, gl_canon(pmul_add(da, o, in)));
                     re_cur = pmul_add(re_cur, ddelta, pmul_add(db, o, in));
                     lut_sum = pmul2(lut_sum, f, mult, lut_prod);
                     lut_prod = pmul(lut_prod, f);
                 }
+                if (b0 < b1) { in_n = wl[(size_t)(2 * b0) * N + j]; o_n = wl[(size_t)(2 * b0 + 1) * N + j]; }
 #pragma unroll 1
                 for (int s = b0; s < b1; s++) {
-                    gl_t in = wl[(size_t)(2 * s) * N + j], o = wl[(size_t)(2 * s + 1) * N + j];
+                    const gl_t in = in_n, o = o_n;
+                    if (s + 1 < b1) { in_n = wl[(size_t)(2 * s + 2) * N + j]; o_n = wl[(size_t)(2 * s + 3) * N + j]; }
                     gl_t f = gl_sub(dalpha, gl_canon(pmul_add(da, o, in)));
                     lu_sum = pmul_add(lu_sum, f, lu_prod);
                     lu_prod = pmul(lu_prod, f);
