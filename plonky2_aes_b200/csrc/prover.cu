@@ -231,6 +231,43 @@ static ext_t ext_reduce_with_powers(const ext_t* v, size_t n, ext_t alpha) {
     return acc;
 }
 
+// Owner of the device temporaries of one prove() call.  Buffers are released as soon as the stage that
+// needs them is over (S.free), and the destructor releases the rest, so the early returns of
+// prove_impl (CUDA errors, P2G_E_UNSAT for a witness that does not satisfy the circuit, ...) do not
+// leak pool memory.
+struct Scratch {
+    p2g_ctx* ctx;
+    std::vector<void*> ptrs;
+    std::vector<p2g_batch*> batches;
+    explicit Scratch(p2g_ctx* c) : ctx(c) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    int alloc(gl_t** p, size_t words) {
+        int rc = ctx_alloc(ctx, p, words);
+        if (rc == P2G_OK) ptrs.push_back(*p);
+        return rc;
+    }
+    cudaError_t alloc_bytes(void** p, size_t bytes) {
+        cudaError_t e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, ctx->st);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    void free(const void* p) {
+        if (!p) return;
+        for (size_t i = 0; i < ptrs.size(); i++)
+            if (ptrs[i] == p) { ptrs.erase(ptrs.begin() + (long)i); cudaFreeAsync((void*)p, ctx->st); return; }
+    }
+    void own(p2g_batch* b) { if (b) batches.push_back(b); }
+    void free_batch(p2g_batch* b) {
+        for (size_t i = 0; i < batches.size(); i++)
+            if (batches[i] == b) { batches.erase(batches.begin() + (long)i); p2g_batch_free(ctx, b); return; }
+    }
+    ~Scratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, ctx->st);
+        for (p2g_batch* b : batches) p2g_batch_free(ctx, b);
+    }
+};
+
 static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wires_in, bool wires_on_host,
                           const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap, size_t* proof_words_out) {
     if (!ctx || !C || !d_wires_in || !proof_out) return P2G_E_BADARG;
@@ -246,6 +283,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     const bool has_lookup = cd.num_luts > 0;
     cudaStream_t st = ctx->st;
     int rc;
+    Scratch S(ctx);     // every temporary of this proof; whatever is still held when the function returns
+                        // (an error path, e.g. an unsatisfied witness) is released by its destructor
     StageTimer tm(ctx);
     const bool dbg = getenv("P2G_DEBUG") != nullptr;
 #define DBG(msg) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[p2g] %s (%s)\n", msg, cudaGetErrorString(e_)); } } while (0)
@@ -257,13 +296,14 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     gl_t* d_wires = nullptr;
     const gl_t* wires = d_wires_in;
     if (wires_on_host) {
-        if ((rc = ctx_alloc(ctx, &d_wires, (size_t)W * n))) return rc;
+        if ((rc = S.alloc(&d_wires, (size_t)W * n))) return rc;
         CU(cudaMemcpyAsync(d_wires, d_wires_in, (size_t)W * n * sizeof(gl_t), cudaMemcpyHostToDevice, st));
         wires = d_wires;
     }
     tm.mark();
     p2g_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
     if ((rc = commit_dev(ctx, wires, W, logn, cd.rate_bits, d.cap_height, true, &wb, true))) return rc;
+    S.own(wb);
     tm.mark();
 
     DBG("wires committed");
@@ -295,18 +335,18 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     if (has_lookup) for (int i = 0; i < nch; i++) pc_host->delta_pow_slots[i] = gl_pow(pc_host->deltas[i][3], cd.lut_slots);
     ProofConsts* d_pc;
-    CU(cudaMallocFromPoolAsync((void**)&d_pc, sizeof(ProofConsts), ctx->pool, st));
+    CU(S.alloc_bytes((void**)&d_pc, sizeof(ProofConsts)));
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
     gl_t* d_lut_evals;
-    if ((rc = ctx_alloc(ctx, &d_lut_evals, MAX_CH * 8))) return rc;
+    if ((rc = S.alloc(&d_lut_evals, MAX_CH * 8))) return rc;
     if (has_lookup) {
         P2G_COUNT_LAUNCH(1); lut_eval_kernel<<<dim3(cd.num_luts, nch), 1024, 0, st>>>(cd, d_pc, C->d_lut_data, C->d_lut_off, C->d_lut_len, d_lut_evals);
     }
 
     // ---- Z, partial products, lookup polys ----
     gl_t *d_zs, *d_rowprod;
-    if ((rc = ctx_alloc(ctx, &d_zs, (size_t)zs_cols * n))) return rc;
-    if ((rc = ctx_alloc(ctx, &d_rowprod, (size_t)nch * n))) return rc;
+    if ((rc = S.alloc(&d_zs, (size_t)zs_cols * n))) return rc;
+    if ((rc = S.alloc(&d_rowprod, (size_t)nch * n))) return rc;
     {
         dim3 grid((unsigned)((n + 127) / 128), nch);
         P2G_COUNT_LAUNCH(1); zs_chunk_kernel<<<grid, 128, 0, st>>>(cd, d_pc, wires, C->d_sigmas, C->d_subgroup, d_zs, d_rowprod);
@@ -325,7 +365,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     tm.mark();
     if ((rc = commit_dev(ctx, d_zs, zs_cols, logn, cd.rate_bits, d.cap_height, true, &zb, true))) return rc;
-    ctx_free(ctx, d_zs); ctx_free(ctx, d_rowprod);
+    S.own(zb);
+    S.free(d_zs); S.free(d_rowprod);
     tm.mark();
     ch.observe_many(zb->cap_host.data(), capw);
     // pc_host (pinned) was consumed by the H2D copy above once commit_dev synchronised
@@ -339,9 +380,9 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     DBG("zs committed");
     // ---- quotient ----
     gl_t *d_qv, *d_qa, *d_qc;
-    if ((rc = ctx_alloc(ctx, &d_qv, (size_t)nch * N))) return rc;
-    if ((rc = ctx_alloc(ctx, &d_qa, (size_t)nch * N))) return rc;
-    if ((rc = ctx_alloc(ctx, &d_qc, (size_t)nch * N))) return rc;
+    if ((rc = S.alloc(&d_qv, (size_t)nch * N))) return rc;
+    if ((rc = S.alloc(&d_qa, (size_t)nch * N))) return rc;
+    if ((rc = S.alloc(&d_qc, (size_t)nch * N))) return rc;
     {
         bool has_pos = false;
         for (const auto& g : C->gates) has_pos |= g.kind == P2G_GATE_POSEIDON;
@@ -365,7 +406,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     tm.mark();
     if ((rc = commit_dev(ctx, d_qc, nch * qdf, logn, cd.rate_bits, d.cap_height, false, &qb, true))) return rc;
-    ctx_free(ctx, d_qv); ctx_free(ctx, d_qa); ctx_free(ctx, d_qc);
+    S.own(qb);
+    S.free(d_qv); S.free(d_qa); S.free(d_qc);
     tm.mark();
     ch.observe_many(qb->cap_host.data(), capw);
     const ext_t zeta = ch.get_ext();
@@ -388,10 +430,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         for (int i = zpp; i < zs_cols; i++) plist[k++] = oracles[2]->coeffs + (size_t)i * n;
     }
     const gl_t** d_plist; gl_t *d_zp, *d_open;
-    CU(cudaMallocFromPoolAsync((void**)&d_plist, plist.size() * sizeof(gl_t*), ctx->pool, st));
+    CU(S.alloc_bytes((void**)&d_plist, plist.size() * sizeof(gl_t*)));
     CU(cudaMemcpyAsync(d_plist, plist.data(), plist.size() * sizeof(gl_t*), cudaMemcpyHostToDevice, st));
-    if ((rc = ctx_alloc(ctx, &d_zp, 4 * n))) return rc;
-    if ((rc = ctx_alloc(ctx, &d_open, 2 * (size_t)(tot0 + tot1)))) return rc;
+    if ((rc = S.alloc(&d_zp, 4 * n))) return rc;
+    if ((rc = S.alloc(&d_open, 2 * (size_t)(tot0 + tot1)))) return rc;
     {
         Pow2Table t0, t1;
         t0.p[0] = zeta; t1.p[0] = zeta_next;
@@ -433,14 +475,14 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     // ---- prove_openings: batch combination ----
     const ext_t fri_alpha = ch.get_ext();
     gl_t *d_comp, *d_comp_lde, *d_vals;
-    if ((rc = ctx_alloc(ctx, &d_comp, 4 * n))) return rc;
-    if ((rc = ctx_alloc(ctx, &d_comp_lde, 4 * N))) return rc;
-    if ((rc = ctx_alloc(ctx, &d_vals, 2 * N))) return rc;
+    if ((rc = S.alloc(&d_comp, 4 * n))) return rc;
+    if ((rc = S.alloc(&d_comp_lde, 4 * N))) return rc;
+    if ((rc = S.alloc(&d_vals, 2 * N))) return rc;
     gl_t* d_apow;
     {
         // alpha^j for j < max(|batch 0|, |batch 1|)
         const size_t na_ = (size_t)(tot0 > tot1 ? tot0 : tot1);
-        if ((rc = ctx_alloc(ctx, &d_apow, 2 * na_))) return rc;
+        if ((rc = S.alloc(&d_apow, 2 * na_))) return rc;
         Pow2Table ta;
         ta.p[0] = fri_alpha;
         for (int b = 1; b < 32; b++) ta.p[b] = ext_mul(ta.p[b - 1], ta.p[b - 1]);
@@ -476,8 +518,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         Layer& L = layers[l];
         L.vals = cur_vals; L.log_len = cur_log; L.arity_bits = ab;
         const uint32_t log_leaves = cur_log - ab;
-        if ((rc = ctx_alloc(ctx, &L.digests, merkle_digest_words(log_leaves, d.cap_height)))) return rc;
-        if ((rc = ctx_alloc(ctx, &L.cap, capw))) return rc;
+        if ((rc = S.alloc(&L.digests, merkle_digest_words(log_leaves, d.cap_height)))) return rc;
+        if ((rc = S.alloc(&L.cap, capw))) return rc;
         if (merkle_build(cur_vals, 0, 0, 2u << ab, log_leaves, d.cap_height, L.digests, L.cap, st)) { ctx->err = "fri merkle"; return P2G_E_CUDA; }
         CU(cudaMemcpyAsync(ctx->pinned, L.cap, capw * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
         CU(ctx_wait(ctx));
@@ -487,7 +529,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         const ext_t beta = ch.get_ext();
         fri_betas[l] = beta;
         gl_t* nxt;
-        if ((rc = ctx_alloc(ctx, &nxt, (size_t)2 << log_leaves))) return rc;
+        if ((rc = S.alloc(&nxt, (size_t)2 << log_leaves))) return rc;
         const size_t chunks = (size_t)1 << log_leaves;
         P2G_COUNT_LAUNCH(1); fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, st>>>(cur_vals, cur_log, ab, gl_inv(shift), gl_inv(gl_root_of_unity(cur_log)),
                                                                            gl_inv(gl_root_of_unity(ab)), gl_inv((gl_t)1 << ab), beta, nxt);
@@ -530,7 +572,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         const int pos = ch.in_len;
         for (int i = 0; i < pos; i++) ps.s[i] = ch.in_buf[i];
         unsigned long long* d_best;
-        CU(cudaMallocFromPoolAsync((void**)&d_best, 8, ctx->pool, st));
+        CU(S.alloc_bytes((void**)&d_best, 8));
         // Windows of candidates in increasing order keep the "lowest nonce" semantics.  The first window
         // has 2^pow_bits candidates (a hit with probability 1 - 1/e), then the windows double up to
         // 2^(pow_bits+2): about 2 x 2^pow_bits permutations on average instead of a fixed 4 x -- with
@@ -548,7 +590,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
             unsigned long long best = *(unsigned long long*)ctx->pinned;
             if (best != ~0ull) { pow_witness = best; found = true; }
         }
-        cudaFreeAsync(d_best, st);
+        S.free(d_best);
         if (!found) { ctx->err = "proof of work failed"; return P2G_E_POW; }
         ch.observe(pow_witness);
         gl_t resp = ch.get();
@@ -582,9 +624,9 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         }
     }
     GatherTree* d_gt; unsigned long long* d_qidx; gl_t* d_q;
-    CU(cudaMallocFromPoolAsync((void**)&d_gt, gt.size() * sizeof(GatherTree), ctx->pool, st));
-    CU(cudaMallocFromPoolAsync((void**)&d_qidx, nq * 8, ctx->pool, st));
-    if ((rc = ctx_alloc(ctx, &d_q, rec * nq))) return rc;
+    CU(S.alloc_bytes((void**)&d_gt, gt.size() * sizeof(GatherTree)));
+    CU(S.alloc_bytes((void**)&d_qidx, nq * 8));
+    if ((rc = S.alloc(&d_q, rec * nq))) return rc;
     CU(cudaMemcpyAsync(d_gt, gt.data(), gt.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_qidx, qidx.data(), nq * 8, cudaMemcpyHostToDevice, st));
     P2G_COUNT_LAUNCH(1); query_gather_kernel<<<dim3(nq, (unsigned)gt.size()), 128, 0, st>>>(d_gt, (int)gt.size(), d_qidx, rec, d_q);
@@ -609,13 +651,13 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         for (int q = 0; q < nq && q < 64; q++) tr.query_indices[q] = qidx[q];
     }
     // release
-    for (int l = 0; l < nl; l++) { ctx_free(ctx, layers[l].digests); ctx_free(ctx, layers[l].cap); if (l > 0) ctx_free(ctx, layers[l].vals); }
-    if (nl > 0) ctx_free(ctx, cur_vals);
-    ctx_free(ctx, d_vals); ctx_free(ctx, d_comp); ctx_free(ctx, d_comp_lde); ctx_free(ctx, d_zp); ctx_free(ctx, d_apow); ctx_free(ctx, d_open);
-    ctx_free(ctx, d_lut_evals);
-    cudaFreeAsync((void*)d_plist, st); cudaFreeAsync(d_gt, st); cudaFreeAsync(d_qidx, st); ctx_free(ctx, d_q); cudaFreeAsync(d_pc, st);
-    p2g_batch_free(ctx, wb); p2g_batch_free(ctx, zb); p2g_batch_free(ctx, qb);
-    if (d_wires) ctx_free(ctx, d_wires);
+    for (int l = 0; l < nl; l++) { S.free(layers[l].digests); S.free(layers[l].cap); if (l > 0) S.free(layers[l].vals); }
+    if (nl > 0) S.free(cur_vals);
+    S.free(d_vals); S.free(d_comp); S.free(d_comp_lde); S.free(d_zp); S.free(d_apow); S.free(d_open);
+    S.free(d_lut_evals);
+    S.free(d_plist); S.free(d_gt); S.free(d_qidx); S.free(d_q); S.free(d_pc);
+    S.free_batch(wb); S.free_batch(zb); S.free_batch(qb);
+    if (d_wires) S.free(d_wires);
     if ((size_t)(w - proof_out) != C->proof_words) { ctx->err = "proof length mismatch"; return P2G_E_BADARG; }
     if (proof_words_out) *proof_words_out = (size_t)(w - proof_out);
     return P2G_OK;

@@ -238,3 +238,27 @@ def test_aes_gcm_1024_bytes_n65536(gpu_ctx, oracle):
     data, wires, _ = circuits.aes_gcm(1024, True)
     assert data.n == 1 << 16
     _check(gpu_ctx, oracle, data, wires).free()
+
+
+def test_repeated_proofs_do_not_leak(gpu_ctx, oracle):
+    """Temporaries of a proof are owned by a scope guard (csrc/prover.cu, Scratch) and go back to the
+    context's pool on every return path: device memory outside the pool stays flat over repeated
+    proofs, including proofs of a witness that violates the circuit (the prover still answers, and
+    the restated verifier rejects that proof -- upstream's `data.verify` would too)."""
+    import torch
+    data, wires, _ = circuits.aes_gcm(13, True)
+    data.load(gpu_ctx)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    good = data.prove_wires(wires)
+    bad = wires.copy()
+    bad[0, 5] = (int(bad[0, 5]) + 1) % P
+    free = []
+    for it in range(10):
+        proof = data.prove_wires(bad if it % 2 else wires)
+        assert oc.verify(proof) == (-20 if it % 2 else 0)
+        gpu_ctx.sync()
+        torch.cuda.synchronize()
+        free.append(torch.cuda.mem_get_info()[0])
+    assert free[-1] >= free[2], f"device memory shrinks by {(free[2] - free[-1]) / 7 / 1e6:.1f} MB per proof"
+    assert np.array_equal(data.prove_wires(wires), good)
+    oc.free()
