@@ -166,6 +166,25 @@ class OracleTranscript(C.Structure):
                 ("fri_betas", C.c_uint64 * 32), ("pow_witness", C.c_uint64), ("query_indices", C.c_uint64 * 64)]
 
 
+def set_circuit_digest(orc, data):
+    """circuit_digest = hash_no_pad(constants_sigmas cap || hash_pad([]) || degree_bits) computed with the
+    oracle (CircuitData.load does the same on the device); needed before proving on the CPU only."""
+    oc = OracleCircuit(orc, data)
+    cap = oc.cap.copy()
+    oc.free()
+    lib = orc.lib
+    lib.orc_hash_no_pad.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    pad = np.array([1] + [0] * 10 + [1], dtype=np.uint64)
+    dom = np.zeros(4, dtype=np.uint64)
+    lib.orc_hash_no_pad(pad.ctypes.data, pad.size, dom.ctypes.data)
+    parts = np.concatenate([cap.ravel(), dom, np.array([data.degree_bits], dtype=np.uint64)])
+    dig = np.zeros(4, dtype=np.uint64)
+    lib.orc_hash_no_pad(parts.ctypes.data, parts.size, dig.ctypes.data)
+    data.circuit_digest = dig
+    data.constants_sigmas_cap = cap
+    return dig
+
+
 class OracleCircuit:
     """orc_circuit_load on the descriptor of a host CircuitData (same C layout as p2g_circuit_desc)."""
 

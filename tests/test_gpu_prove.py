@@ -262,3 +262,19 @@ def test_repeated_proofs_do_not_leak(gpu_ctx, oracle):
     assert free[-1] >= free[2], f"device memory shrinks by {(free[2] - free[-1]) / 7 / 1e6:.1f} MB per proof"
     assert np.array_equal(data.prove_wires(wires), good)
     oc.free()
+
+
+def test_golden_proof_digests_gpu(gpu_ctx):
+    """The CUDA path reproduces the committed golden circuit digests and proof hashes
+    (tests/golden/proof_digests.json) without consulting the oracle."""
+    import json
+    import os
+    from tools import gen_golden_proofs as g
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "proof_digests.json")))
+    for name, data, wires in g.cases():
+        ref = gold[name]
+        data.load(gpu_ctx)
+        assert [int(v) for v in data.circuit_digest] == ref["circuit_digest"], name
+        assert g.sha(data.constants_sigmas_cap) == ref["constants_sigmas_cap_sha256"], name
+        proof = data.prove_wires(wires)
+        assert len(proof) == ref["proof_words"] and g.sha(proof) == ref["proof_sha256"], name

@@ -134,3 +134,27 @@ def test_proof_views_and_byte_round_trip(oracle):
     back = Proof.from_bytes(raw, data.descriptor())
     assert np.array_equal(back.words, words) and oc.verify(back.words) == 0
     oc.free()
+
+
+def test_golden_proof_digests(oracle):
+    """Regression anchors (tests/golden/proof_digests.json, written by tools/gen_golden_proofs.py): the
+    oracle reproduces the committed circuit digests and proof hashes bit for bit.  Self-generated, not
+    reference vectors -- they pin today's behaviour of the restated protocol against silent drift."""
+    import hashlib
+    import json
+    import os
+    from tools import gen_golden_proofs as g
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "proof_digests.json")))
+    seen = set()
+    for name, data, wires in g.cases():
+        ref = gold[name]
+        digest = oracle_lib.set_circuit_digest(oracle, data)
+        assert [int(v) for v in digest] == ref["circuit_digest"], name
+        assert g.sha(wires) == ref["wires_sha256"], name
+        oc = oracle_lib.OracleCircuit(oracle, data)
+        assert g.sha(oc.cap) == ref["constants_sigmas_cap_sha256"], name
+        proof = oc.prove(wires)
+        assert len(proof) == ref["proof_words"] and g.sha(proof) == ref["proof_sha256"], name
+        oc.free()
+        seen.add(name)
+    assert seen == set(gold)
