@@ -27,8 +27,15 @@ extern "C" {
 #define P2G_OK 0
 #define P2G_E_CUDA (-1)    /* CUDA runtime error; text via p2g_last_error */
 #define P2G_E_BADARG (-2)
-#define P2G_E_UNSAT (-3)   /* witness does not satisfy the circuit (quotient not a polynomial);
-                              mirrors prove() returning Err, /root/reference/aes-gcm/src/circuit_aes.rs:403-405 */
+#define P2G_E_UNSAT (-3)   /* the FRI final polynomial has non-zero high coefficients (an internal consistency
+                              check).  NOTE: a wire matrix that violates a gate or copy constraint is NOT detected
+                              here: with quotient_degree_factor = 2^rate_bits the quotient is interpolated exactly
+                              on the 8n points, so p2g_prove returns P2G_OK and a proof the verifier rejects --
+                              the behaviour of upstream release builds, where the check is a debug assertion.  The
+                              reference's `prove(..).is_err()` on a bad witness
+                              (/root/reference/aes-gcm/src/circuit_aes.rs:403-405) comes from witness generation
+                              (conflicting partition values), which stays on the host: p2w_generate* returns
+                              P2W_E_CONFLICT (include/p2witness.h). */
 #define P2G_E_POW (-4)
 #define P2G_E_NOMEM (-5)
 

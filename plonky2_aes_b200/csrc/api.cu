@@ -5,39 +5,57 @@
 #include <string.h>
 #include <stdio.h>
 
-unsigned long long g_p2g_launches = 0;
-extern "C" int32_t p2g_version(void) { return 1; }
-extern "C" uint64_t p2g_launch_count(void) { return g_p2g_launches; }
+#include <mutex>
+
+std::atomic<unsigned long long> g_p2g_launches{0};
+extern "C" int32_t p2g_version(void) { return 2; }
+extern "C" uint64_t p2g_launch_count(void) { return g_p2g_launches.load(std::memory_order_relaxed); }
+
+// NTT plans (twiddle / fold tables) are per device, shared by every context of that device: bench.py
+// keeps 8 contexts per GPU and the Rust side one per prover thread.  Freed when the last context
+// of the device goes away.
+static std::mutex g_plan_mu;
+static std::map<std::tuple<int, int, int, int>, NttPlan> g_plans;     // (device, kind, log_n, rate_bits)
+static std::map<int, int> g_ctx_per_device;
 
 extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
     if (!out) return P2G_E_BADARG;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return P2G_E_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return P2G_E_CUDA;
+    // function attributes belong to one device: set them for every device a context is created on
+    if (ntt_init_device() != 0) return P2G_E_CUDA;
     p2g_ctx* ctx = new p2g_ctx();
     ctx->device = device; ctx->timing = false; ctx->keep_debug = false;
+    ctx->st = nullptr; ctx->pool = nullptr; ctx->pinned = nullptr; ctx->wait_ev = nullptr;
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     memset(&ctx->transcript, 0, sizeof(ctx->transcript));
-    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
-    {
+    bool ok = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) {
         const char* mode = getenv("P2G_SYNC");
         ctx->wait_mode = !mode ? 2 : strcmp(mode, "block") == 0 ? 1 : strcmp(mode, "spin") == 0 ? 0 : 2;
-        if (cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
-            cudaStreamDestroy(ctx->st); delete ctx; return P2G_E_CUDA;
-        }
+        ok = cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
     }
-    {
+    if (ok) {
         cudaMemPoolProps props; memset(&props, 0, sizeof(props));
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
         props.location.type = cudaMemLocationTypeDevice;
         props.location.id = device;
-        if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) { cudaStreamDestroy(ctx->st); delete ctx; return P2G_E_CUDA; }
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        ok = cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess;
+        if (ok) { uint64_t thr = UINT64_MAX; cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr); }
     }
     ctx->pinned_words = 1 << 20;
-    if (cudaMallocHost(&ctx->pinned, ctx->pinned_words * sizeof(gl_t)) != cudaSuccess) { delete ctx; return P2G_E_CUDA; }
+    if (ok) ok = cudaMallocHost(&ctx->pinned, ctx->pinned_words * sizeof(gl_t)) == cudaSuccess;
+    if (!ok) {                                   // release whatever was created before the failure
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+        if (ctx->wait_ev) cudaEventDestroy(ctx->wait_ev);
+        if (ctx->st) cudaStreamDestroy(ctx->st);
+        delete ctx;
+        return P2G_E_CUDA;
+    }
+    { std::lock_guard<std::mutex> lk(g_plan_mu); g_ctx_per_device[device]++; }
     *out = ctx;
     return P2G_OK;
 }
@@ -45,7 +63,15 @@ extern "C" void p2g_ctx_destroy(p2g_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
-    for (auto& kv : ctx->plans) ntt_plan_free(&kv.second);
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        if (--g_ctx_per_device[ctx->device] == 0) {         // last context of this device: drop its plans
+            cudaDeviceSynchronize();
+            for (auto it = g_plans.begin(); it != g_plans.end();) {
+                if (std::get<0>(it->first) == ctx->device) { ntt_plan_free(&it->second); it = g_plans.erase(it); } else ++it;
+            }
+        }
+    }
     cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->wait_ev);
     cudaMemPoolDestroy(ctx->pool);
@@ -57,13 +83,20 @@ extern "C" int32_t p2g_ctx_sync(p2g_ctx* ctx) { CU(ctx_wait(ctx)); return P2G_OK
 extern "C" void* p2g_ctx_stream(p2g_ctx* ctx) { return (void*)ctx->st; }
 
 int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan** out) {
-    auto key = std::make_tuple(kind, log_n, kind == NTT_KIND_LDE ? rate_bits : 0);
-    auto it = ctx->plans.find(key);
-    if (it == ctx->plans.end()) {
+    auto lkey = std::make_tuple(kind, log_n, kind == NTT_KIND_LDE ? rate_bits : 0);
+    auto lit = ctx->plans.find(lkey);                      // per-context cache of pointers: no lock on the hot path
+    if (lit != ctx->plans.end()) { *out = lit->second; return P2G_OK; }
+    if (log_n > P2G_MAX_LOG_N) { ctx->err = "transform larger than 2^17 points is not supported"; return P2G_E_BADARG; }
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto key = std::make_tuple(ctx->device, kind, log_n, kind == NTT_KIND_LDE ? rate_bits : 0);
+    auto it = g_plans.find(key);
+    if (it == g_plans.end()) {
         NttPlan p;
-        if (ntt_plan_build(&p, kind, log_n, rate_bits, ctx->st) != 0) { ctx->err = "ntt_plan_build failed"; return P2G_E_CUDA; }
-        it = ctx->plans.emplace(key, p).first;
+        int rc = ntt_plan_build(&p, kind, log_n, rate_bits, ctx->st);
+        if (rc != 0) { ctx->err = rc == -2 ? "out of device memory for the NTT tables" : "ntt_plan_build failed"; return rc == -2 ? P2G_E_NOMEM : P2G_E_CUDA; }
+        it = g_plans.emplace(key, p).first;
     }
+    ctx->plans[lkey] = &it->second;                         // std::map nodes are address-stable
     *out = &it->second;
     return P2G_OK;
 }
@@ -78,8 +111,15 @@ int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_
     if (blk_count == 0) { blk_first = 0; blk_count = 1u << rate_bits; }
     uint32_t blk_log = 0; while ((1u << blk_log) < blk_count) blk_log++;
     if ((1u << blk_log) != blk_count || blk_first % blk_count || blk_first + blk_count > (1u << rate_bits)) return P2G_E_BADARG;
-    if (!ncols || log_n > 22 || log_n + rate_bits > 26 || cap_height > log_n + blk_log) return P2G_E_BADARG;
+    if (!ncols || log_n > P2G_MAX_LOG_N || log_n + rate_bits > 26 || cap_height > log_n + blk_log) {
+        ctx->err = "unsupported commitment shape (log_n <= 17, cap_height <= log of the leaves held)"; return P2G_E_BADARG;
+    }
+    struct BatchGuard {                 // an early return releases the half-built batch
+        p2g_ctx* ctx; p2g_batch* b;
+        ~BatchGuard() { if (b) p2g_batch_free(ctx, b); }
+    } guard{ctx, nullptr};
     p2g_batch* b = new p2g_batch();
+    guard.b = b;
     b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
     b->blk_first = blk_first; b->blk_log = blk_log;
     b->coeffs = b->lde = b->digests = b->cap = nullptr;
@@ -115,6 +155,7 @@ int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_
         CU(ctx_wait(ctx));
         memcpy(b->cap_host.data(), ctx->pinned, b->cap_host.size() * sizeof(gl_t));
     }
+    guard.b = nullptr;
     *out = b;
     return P2G_OK;
 }
@@ -253,6 +294,7 @@ extern "C" int32_t p2g_hash_no_pad_many(p2g_ctx* ctx, const uint64_t* in_host, u
     if ((rc = ctx_alloc(ctx, &d_out, (size_t)count * 4))) return rc;
     CU(cudaMemcpyAsync(d_in, in_host, (size_t)count * len * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
     hash_no_pad_many_kernel<<<(count + 127) / 128, 128, 0, ctx->st>>>(d_in, count, len, d_out);
+    P2G_COUNT_LAUNCH(1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_host, d_out, (size_t)count * 4 * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
     CU(ctx_wait(ctx));

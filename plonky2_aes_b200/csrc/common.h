@@ -3,11 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "gl64.cuh"
 
-// number of kernels launched by this library since load (reported by bench.py as gpu_launches)
-extern unsigned long long g_p2g_launches;
-#define P2G_COUNT_LAUNCH(k) (g_p2g_launches += (k))
+// number of kernels launched by this library since load (reported by bench.py as gpu_launches);
+// incremented from every prover host thread, hence atomic
+extern std::atomic<unsigned long long> g_p2g_launches;
+#define P2G_COUNT_LAUNCH(k) (g_p2g_launches.fetch_add((k), std::memory_order_relaxed))
 
 #define P2G_MAX_LOG_M 14   // largest sub-transform held in shared memory (2^14 * 8 B = 128 KB)
 
@@ -24,6 +26,12 @@ struct NttPlan {
     gl_t* tw;   // per-pass compact twiddle tables (forward or inverse roots), tw_words entries
     int tw_words;
 };
+// largest fold factor R = n / 2^log_m a plan may have: the table T grows as variants * R * n words
+// (rate 3: 8 MB at n = 2^15, 67 MB at 2^17, 268 MB at 2^18), so larger transforms are refused
+#define P2G_MAX_LOG_R 3
+#define P2G_MAX_LOG_N (P2G_MAX_LOG_M + P2G_MAX_LOG_R)
+// per-device kernel attributes (dynamic shared memory opt-in); called by p2g_ctx_create after cudaSetDevice
+int ntt_init_device();
 int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream_t st);
 void ntt_plan_free(NttPlan* plan);
 // out_mode 0: block (variant,q) writes M contiguous words at out[col*out_stride + bitrev(variant)*n + q*M]

@@ -30,7 +30,7 @@ struct p2g_ctx {
     cudaMemPool_t pool;     // private pool: blocks freed on this stream are never handed to another
                             // context's stream, so proofs in flight on one GPU stay independent
     std::string err;
-    std::map<std::tuple<int, int, int>, NttPlan> plans;
+    std::map<std::tuple<int, int, int>, const NttPlan*> plans;   // pointers into the per-device plan cache (api.cu)
     gl_t* pinned; size_t pinned_words;     // small pinned staging buffer for D2H results
     bool timing;
     p2g_timings timings;

@@ -85,7 +85,8 @@ merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t 
         } else {
             lv = it - absorbs + 1;
             __syncthreads();
-            active = tid < (blockDim.x >> lv);
+            // a block padded to a full warp (fewer than 32 leaves) has more threads than nodes
+            active = tid < (blockDim.x >> lv) && (((size_t)blockIdx.x * blockDim.x) >> lv) + tid < (num_leaves >> lv);
             if (active) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) { s[i] = sh[2 * tid][i]; s[4 + i] = sh[2 * tid + 1][i]; s[8 + i] = 0; }
@@ -201,8 +202,7 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
         {   // levels folded inside the leaf kernel: every folded level halves the busy threads of a block
             // that still pins its registers, so only one level is folded (measured on config 2:
             // 0/1/2/3 levels -> 86.2/86.6/85.9/85.4 proofs/s) and the per-level kernels finish the tree
-            static int cap_levels = -1;
-            if (cap_levels < 0) { const char* e = getenv("P2G_MERKLE_BLOCK_LEVELS"); cap_levels = e ? atoi(e) : 1; }
+            static const int cap_levels = [] { const char* e = getenv("P2G_MERKLE_BLOCK_LEVELS"); return e ? atoi(e) : 1; }();   // thread-safe init
             if ((int)levels_here > cap_levels) levels_here = (uint32_t)cap_levels;
         }
         uint32_t blocks = (uint32_t)((num_leaves + threads - 1) / threads);

@@ -199,8 +199,14 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
     }
 }
 
+int ntt_init_device() {
+    return cudaFuncSetAttribute(ntt_dif_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess ? 0 : -1;
+}
+
+// returns 0, -1 (CUDA error) or -2 (out of device memory)
 int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream_t st) {
-    plan->kind = kind; plan->log_n = log_n;
+    plan->kind = kind; plan->log_n = log_n; plan->T = plan->tw = nullptr;
+    if (log_n > P2G_MAX_LOG_N) return -1;
     plan->log_m = log_n < P2G_MAX_LOG_M ? log_n : P2G_MAX_LOG_M;
     if (log_n == 13) plan->log_m = 13;
     // n = 2^14, 2^15: 2^13-point chunks, two 256-thread blocks per SM, so one block's load / store phases
@@ -245,28 +251,26 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
         plan->tw_words = (int)tw.size();
         (void)wm;
     }
-    if (cudaMalloc(&plan->T, T.size() * sizeof(gl_t)) != cudaSuccess) return -1;
-    if (cudaMalloc(&plan->tw, tw.size() * sizeof(gl_t)) != cudaSuccess) return -1;
-    if (cudaMemcpyAsync(plan->T, T.data(), T.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
-    if (cudaMemcpyAsync(plan->tw, tw.data(), tw.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
-    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;   // host vectors die here
+    if (cudaMalloc(&plan->T, T.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); return -2; }
+    if (cudaMalloc(&plan->tw, tw.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); ntt_plan_free(plan); return -2; }
+    if (cudaMemcpyAsync(plan->T, T.data(), T.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(plan->tw, tw.data(), tw.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {             // host vectors die here
+        ntt_plan_free(plan); return -1;
+    }
     return 0;
 }
-void ntt_plan_free(NttPlan* plan) { cudaFree(plan->T); cudaFree(plan->tw); plan->T = plan->tw = nullptr; }
+void ntt_plan_free(NttPlan* plan) { if (plan->T) cudaFree(plan->T); if (plan->tw) cudaFree(plan->tw); plan->T = plan->tw = nullptr; }
 
 int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out, size_t out_stride,
                int ncols, int out_mode, cudaStream_t st, uint32_t blk_first, uint32_t blk_count) {
-    static bool attr_set = false;
     const size_t M = (size_t)1 << plan->log_m;
     // a 2^13-point chunk with a non-trivial fold (n > 2^13) runs two blocks per SM: 256 threads each and
     // the first pass's table (4096 words) stays in global memory
     const bool two_per_sm = plan->log_m == 13 && plan->log_r > 0;
     const uint32_t tw_skip = two_per_sm ? 4096u : 0u;
     size_t smem = (M + (M >> 4) + 1 + (size_t)plan->tw_words - tw_skip) * sizeof(gl_t);
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(ntt_dif_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-        attr_set = true;
-    }
+    // (the > 48 KB dynamic shared memory opt-in is per device: ntt_init_device, called by p2g_ctx_create)
     uint32_t threads = (uint32_t)(M >> 4);
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;

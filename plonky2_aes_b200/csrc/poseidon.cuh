@@ -225,6 +225,11 @@ __device__ __forceinline__ gl_t pos_readout(double l, double h) {
 #ifndef P2G_PARTIAL_PAIRS
 #define P2G_PARTIAL_PAIRS 1
 #endif
+// always 0, but opaque to the compiler's uniformity analysis
+__device__ __forceinline__ int pos_lane_zero() {
+    long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+    return (int)((unsigned long long)c >> 63);
+}
 // Two consecutive partial rounds in one pass over the state.  With s' = (sbox(s0), s1..s11),
 //     t = M s' + cA,   u = M (sbox(t0), t1..t11) + cB
 // collapses to   u = A s' + col0(M) sbox(t0) + K,   t0 = row0(M) s' + cA_0,
@@ -233,14 +238,18 @@ __device__ __forceinline__ gl_t pos_readout(double l, double h) {
 // the products with 32-bit halves are still exact on the FP64 pipe (row sums < 2^49), and the 11
 // words that skip the S-box are read out of the accumulators and converted back once per TWO rounds:
 // 336 FP64 instructions and 13 readouts per pair instead of 408 and 24.
-__device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair) {
+__device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int zero) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
     const double A[144] = POSEIDON_PAIR_A_INIT;
     double al[12], ah[12];
 #pragma unroll
-    for (int r = 0; r < 12; r++) { al[r] = POSEIDON_PAIRK_LO[12 * pair + r]; ah[r] = POSEIDON_PAIRK_HI[12 * pair + r]; }
+    // pos_lane_zero(): the table index is made to look per-thread so the biases arrive by LDC straight in
+    // vector registers; a uniform index is loaded to uniform registers and then costs two moves per
+    // double (52 of the 753 instructions of this loop body)
+    const int pz = 12 * pair + zero;
+    for (int r = 0; r < 12; r++) { al[r] = POSEIDON_PAIRK_LO[pz + r]; ah[r] = POSEIDON_PAIRK_HI[pz + r]; }
     const int row_a = 5 + 2 * pair;                       // constants between the two rounds
-    double tl = POSEIDON_RCD_LO[12 * row_a], th = POSEIDON_RCD_HI[12 * row_a];
+    double tl = POSEIDON_RCD_LO[12 * row_a + zero], th = POSEIDON_RCD_HI[12 * row_a + zero];
     const gl_t y0 = poseidon_sbox(s[0]);
 #pragma unroll
     for (int jj = 0; jj < 12; jj++) {
@@ -288,8 +297,9 @@ __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
         }
         if (phase == 0) {
 #if P2G_PARTIAL_PAIRS
+            const int zero = pos_lane_zero();
 #pragma unroll 1
-            for (int p = 0; p < 11; p++, k += 2) poseidon_partial_pair(s, p);
+            for (int p = 0; p < 11; p++, k += 2) poseidon_partial_pair(s, p, zero);
 #else
 #pragma unroll 1
             for (int r = 0; r < 22; r++, k++) {

@@ -44,18 +44,23 @@ struct p2g_circuit {
     std::vector<p2g_gate> gates; std::vector<int32_t> lut_lens, lookup_rows; std::vector<uint16_t> lut_data;
     std::vector<gl_t> k_is;
     CircuitDev cd;
-    p2g_batch* cs;            // constants_sigmas commitment
-    gl_t* d_sigmas;           // [R][n] values on H
-    gl_t* d_subgroup;         // g^i
-    gl_t* d_domain;           // x_j = 7 w_N^bitrev(j)
-    gl_t* d_l0inv;            // 1 / (n (x_j - 1))
-    gl_t* d_qtable;           // [8][n]: h_s^(-j)/8
-    gl_t* d_small;            // w8inv_pows[8], shift_n_inv_pows[8]
-    p2g_gate* d_gates;
-    uint8_t* d_row_kind;
-    uint16_t* d_lut_data; int* d_lut_off; int* d_lut_len;
-    size_t proof_words;
-    int final_len;
+    p2g_batch* cs = nullptr;            // constants_sigmas commitment
+    gl_t* d_sigmas = nullptr;           // [R][n] values on H
+    gl_t* d_subgroup = nullptr;         // g^i
+    gl_t* d_domain = nullptr;           // x_j = 7 w_N^bitrev(j)
+    gl_t* d_l0inv = nullptr;            // 1 / (n (x_j - 1))
+    gl_t* d_qtable = nullptr;           // [8][n]: h_s^(-j)/8
+    gl_t* d_small = nullptr;            // w8inv_pows[8], shift_n_inv_pows[8]
+    p2g_gate* d_gates = nullptr;
+    uint8_t* d_row_kind = nullptr;
+    uint16_t* d_lut_data = nullptr; int* d_lut_off = nullptr; int* d_lut_len = nullptr;
+    size_t proof_words = 0;
+    int final_len = 0;
+};
+// releases a circuit whose construction stopped half way (every error return of p2g_circuit_load)
+struct CircuitGuard {
+    p2g_ctx* ctx; p2g_circuit* c; gl_t* tmp;
+    ~CircuitGuard() { if (tmp) ctx_free(ctx, tmp); if (c) p2g_circuit_free(ctx, c); }
 };
 
 static int num_lookup_polys(const p2g_circuit_desc& d) {
@@ -89,8 +94,9 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
     if (!ctx || !desc || !out) return P2G_E_BADARG;
     const p2g_circuit_desc& d = *desc;
     if (d.num_challenges < 1 || d.num_challenges > MAX_CH || d.num_routed_wires > MAX_ROUTED || d.num_luts > 8 ||
-        d.quotient_degree_factor != (1 << d.rate_bits) || d.rate_bits != 3 || d.num_public_inputs != 0 ||
-        d.degree_bits < 2 || d.degree_bits > 20 || d.num_partial_products + 1 > 16 ||
+        d.quotient_degree_factor != (1 << d.rate_bits) || d.rate_bits != 3 || d.num_public_inputs < 0 ||
+        d.pow_bits < 1 || d.pow_bits > 32 || d.cap_height < 0 || d.num_query_rounds < 1 || d.num_query_rounds > 64 ||
+        d.degree_bits < 2 || d.degree_bits > P2G_MAX_LOG_N || d.num_partial_products + 1 > 16 ||
         d.num_routed_wires / 2 > 8 * (d.quotient_degree_factor - 1) || d.quotient_degree_factor - 1 > 8) {
         ctx->err = "unsupported circuit configuration"; return P2G_E_BADARG;
     }
@@ -98,6 +104,7 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
         if (d.gates[g].kind < P2G_GATE_NOOP || d.gates[g].kind > P2G_GATE_POSEIDON) { ctx->err = "unknown gate kind"; return P2G_E_BADARG; }
     CU(cudaSetDevice(ctx->device));
     p2g_circuit* C = new p2g_circuit();
+    CircuitGuard guard{ctx, C, nullptr};
     C->d = d;
     C->gates.assign(d.gates, d.gates + d.num_gates);
     C->lut_lens.assign(d.lut_lens, d.lut_lens + d.num_luts);
@@ -117,9 +124,9 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
     cd.lut_degree = cd.num_sldc ? (cd.lut_slots + cd.num_sldc - 1) / cd.num_sldc : 0;
     cd.num_luts = d.num_luts; cd.num_gates = d.num_gates; cd.num_gate_constraints = d.num_gate_constraints;
     cd.zs_cols = cd.nch * (1 + cd.num_prods + cd.nlp);
-    if (cd.lut_degree > 8) { delete C; ctx->err = "lut_degree > 8"; return P2G_E_BADARG; }
+    if (cd.lut_degree > 8) { ctx->err = "lut_degree > 8"; return P2G_E_BADARG; }
     int nterms = cd.nch + cd.nch * (cd.num_prods + 1) + (cd.num_luts ? cd.nch * (4 + cd.num_luts + 2 * cd.num_sldc) : 0) + cd.num_gate_constraints;
-    if (nterms > 256) { delete C; ctx->err = "too many vanishing terms"; return P2G_E_BADARG; }
+    if (nterms > 256) { ctx->err = "too many vanishing terms"; return P2G_E_BADARG; }
     C->proof_words = proof_len(d);
     const size_t n = (size_t)1 << cd.logn, N = n << cd.rate_bits;
     const int logN = cd.logn + cd.rate_bits;
@@ -128,12 +135,13 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
     const int ncs = cd.NC + cd.R;
     gl_t* d_vals;
     if ((rc = ctx_alloc(ctx, &d_vals, (size_t)ncs * n))) return rc;
+    guard.tmp = d_vals;
     CU(cudaMemcpyAsync(d_vals, d.constants_sigmas, (size_t)ncs * n * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
     if ((rc = commit_dev(ctx, d_vals, ncs, cd.logn, cd.rate_bits, d.cap_height, true, &C->cs, true))) return rc;
     if (cap_out) memcpy(cap_out, C->cs->cap_host.data(), C->cs->cap_host.size() * sizeof(gl_t));
     if ((rc = ctx_alloc(ctx, &C->d_sigmas, (size_t)cd.R * n))) return rc;
     CU(cudaMemcpyAsync(C->d_sigmas, d_vals + (size_t)cd.NC * n, (size_t)cd.R * n * sizeof(gl_t), cudaMemcpyDeviceToDevice, ctx->st));
-    ctx_free(ctx, d_vals);
+    ctx_free(ctx, d_vals); guard.tmp = nullptr;
     // domain tables
     if ((rc = ctx_alloc(ctx, &C->d_subgroup, n))) return rc;
     if ((rc = ctx_alloc(ctx, &C->d_domain, N))) return rc;
@@ -185,12 +193,14 @@ extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, 
     }
     size_t fin = n; for (int l = 0; l < d.num_reduction_arity_bits; l++) fin >>= d.reduction_arity_bits[l];
     C->final_len = (int)fin;
+    guard.c = nullptr;
     *out = C;
     return P2G_OK;
 }
 extern "C" int32_t p2g_circuit_free(p2g_ctx* ctx, p2g_circuit* C) {
     if (!ctx || !C) return P2G_E_BADARG;
-    p2g_batch_free(ctx, C->cs);
+    cudaSetDevice(ctx->device);
+    if (C->cs) p2g_batch_free(ctx, C->cs);
     ctx_free(ctx, C->d_sigmas); ctx_free(ctx, C->d_subgroup); ctx_free(ctx, C->d_domain); ctx_free(ctx, C->d_l0inv); ctx_free(ctx, C->d_qtable);
     ctx_free(ctx, C->d_small); ctx_free(ctx, C->d_row_kind); ctx_free(ctx, C->d_gates);
     ctx_free(ctx, C->d_lut_data); ctx_free(ctx, C->d_lut_off); ctx_free(ctx, C->d_lut_len);
@@ -272,6 +282,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
                           const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap, size_t* proof_words_out) {
     if (!ctx || !C || !d_wires_in || !proof_out) return P2G_E_BADARG;
     if (proof_cap < C->proof_words) return P2G_E_BADARG;
+    if (C->d.num_public_inputs > 0 && !public_inputs) { ctx->err = "public_inputs is NULL"; return P2G_E_BADARG; }
     CU(cudaSetDevice(ctx->device));
     const p2g_circuit_desc& d = C->d;
     const CircuitDev& cd = C->cd;

@@ -118,6 +118,14 @@ class CircuitBuilder:
     def add_virtual_targets(self, n):
         return [self.add_virtual_target() for _ in range(n)]
 
+    def register_public_input(self, t):
+        """CircuitBuilder::register_public_input: the proof carries the value of `t`."""
+        self.public_inputs.append(t)
+
+    def register_public_inputs(self, ts):
+        for t in ts:
+            self.register_public_input(t)
+
     def add_virtual_bool_target_unsafe(self):
         return BoolTarget(self.add_virtual_target())
 
@@ -320,11 +328,12 @@ class CircuitBuilder:
         """CircuitBuilder::build::<PoseidonGoldilocksConfig>() -> CircuitData.  `ctx` is the GPU
         context that will hold the preprocessed (constants, sigmas) commitment."""
         cfg = self.config
-        assert not self.public_inputs, "public inputs need the in-circuit Poseidon gate (not used by the AES gadgets)"
-        # PublicInputGate row: wires 0..4 are tied to the (zero) public-input hash
+        # PublicInputGate row: wires 0..4 are tied to hash_n_to_hash_no_pad(public inputs), computed in
+        # circuit by PoseidonGate rows (upstream build() does the same); no inputs -> the zero hash
+        pi_hash = self.hash_n_to_hash_no_pad(self.public_inputs) if self.public_inputs else [self.zero()] * 4
         pi_row = self.add_gate(GATE_PUBLIC_INPUT)
         for i in range(4):
-            self.connect(wire(pi_row, i), self.zero())
+            self.connect(wire(pi_row, i), pi_hash[i])
         lookup_rows, fixed = self._add_all_lookups()
         # ConstantGate rows (2 constants each)
         items = list(self.constants_to_targets.items())
@@ -456,6 +465,7 @@ class CircuitData:
         self.reduction_arity_bits = _fri_reduction_arity_bits(degree_bits, cfg.fri_config)
 
         # ---- witness program ----
+        self.public_input_targets = list(b.public_inputs)
         self._build_witness_program(b, lookup_rows, fixed)
         self.circuit_digest = np.zeros(4, dtype=np.uint64)
         self.constants_sigmas_cap = None
@@ -487,7 +497,7 @@ class CircuitData:
         d.lut_lens = self._lut_lens.ctypes.data_as(C.POINTER(C.c_int32))
         d.lut_data = self._lut_data.ctypes.data_as(C.POINTER(C.c_uint16))
         d.lookup_rows = self._lookup_rows_arr.ctypes.data_as(C.POINTER(C.c_int32))
-        d.num_public_inputs = 0
+        d.num_public_inputs = len(self.public_input_targets)
         d.k_is = self.k_is.ctypes.data_as(C.POINTER(C.c_uint64))
         d.constants_sigmas = self.constants_sigmas.ctypes.data_as(C.POINTER(C.c_uint64))
         for i in range(4):
@@ -669,6 +679,10 @@ class CircuitData:
             raise ValueError(self._WERR.get(rc, f"witness error {rc}"))
         return out
 
+    def public_inputs_of(self, slots):
+        """values of the registered public inputs in a slot vector (PartitionWitness::get_targets)"""
+        return np.array([slots[self._slot(t)] for t in self.public_input_targets], dtype=np.uint64)
+
     def load_wire_map(self, ctx=None, circuit=None):
         """Uploads the wire map (representative_map analogue) next to a loaded circuit; returns the handle."""
         ctx = ctx or self.ctx
@@ -684,7 +698,7 @@ class CircuitData:
         ctx.check(ctx.lib.p2g_wmap_load(ctx.handle, circuit, wm.ctypes.data, self.ext_slots, pos, val, cnt.value, C.byref(h)))
         return h
 
-    def prove_slots(self, slots, ctx=None, circuit=None, wmap=None):
+    def prove_slots(self, slots, ctx=None, circuit=None, wmap=None, public_inputs=None):
         """Slot vector -> proof; the wire matrix is gathered on the device (PartitionWitness::full_witness)."""
         ctx = ctx or self.ctx
         circuit = circuit or self._gpu_circuit
@@ -698,7 +712,11 @@ class CircuitData:
         out = np.empty(words, dtype=np.uint64)
         got = C.c_size_t()
         slots = np.ascontiguousarray(slots, dtype=np.uint64)
-        rc = ctx.lib.p2g_prove_slots(ctx.handle, circuit, wmap, slots.ctypes.data, None, out.ctypes.data, words, C.byref(got))
+        if public_inputs is None and self.public_input_targets:
+            public_inputs = self.public_inputs_of(slots)
+        pi = np.ascontiguousarray(public_inputs, dtype=np.uint64) if public_inputs is not None and len(public_inputs) else None
+        rc = ctx.lib.p2g_prove_slots(ctx.handle, circuit, wmap, slots.ctypes.data, pi.ctypes.data if pi is not None else None,
+                                     out.ctypes.data, words, C.byref(got))
         if rc == -3:
             raise ValueError("witness does not satisfy the circuit (P2G_E_UNSAT)")
         ctx.check(rc)
@@ -722,7 +740,7 @@ class CircuitData:
         """CircuitData::prove(pw) -> proof (flat u64 words, layout in DESIGN.md)."""
         return self.prove_slots(self.generate_slots(pw))
 
-    def prove_wires(self, wires):
+    def prove_wires(self, wires, public_inputs=None):
         ctx = self.ctx
         if ctx is None or self._gpu_circuit is None:
             raise ffi.P2GError(-1, "circuit not loaded on a GPU context (no CPU fallback)")
@@ -730,7 +748,10 @@ class CircuitData:
         out = np.empty(words, dtype=np.uint64)
         got = C.c_size_t()
         wires = np.ascontiguousarray(wires, dtype=np.uint64)
-        rc = ctx.lib.p2g_prove(ctx.handle, self._gpu_circuit, wires.ctypes.data, None, out.ctypes.data, words, C.byref(got))
+        assert (public_inputs is not None and len(public_inputs) == len(self.public_input_targets)) or not self.public_input_targets
+        pi = np.ascontiguousarray(public_inputs, dtype=np.uint64) if self.public_input_targets else None
+        rc = ctx.lib.p2g_prove(ctx.handle, self._gpu_circuit, wires.ctypes.data, pi.ctypes.data if pi is not None else None,
+                               out.ctypes.data, words, C.byref(got))
         if rc == -3:
             raise ValueError("witness does not satisfy the circuit (P2G_E_UNSAT)")
         ctx.check(rc)

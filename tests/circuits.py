@@ -43,9 +43,13 @@ def aes_block(nk=4, nr=10):
     for a, c in zip(out, ct_t):
         b.connect(a, c)
     data = b.build()
-    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    # keys of test_encrypt_block_test_vector (circuit_aes.rs:619-655): AES-128 / 192 / 256
+    key = bytes.fromhex({4: "2b7e151628aed2a6abf7158809cf4f3c", 6: "8e73b0f7da0e6452c810f32b809079e562f8ead2522c6b7b",
+                         8: "603deb1015ca71be2b73aef0857d77811f352c073b6108d72d9810a30914dff4"}[nk])
     pt = bytes.fromhex("3243f6a8885a308d313198a2e0370734")
-    ct = bytes.fromhex("3925841d02dc09fbdc118597196a0b32")
+    ct = bytes(native.flatten_state(native.encrypt_block(list(pt), native.key_expansion(list(key), nk, nr), nr)))
+    if nk == 4:
+        assert ct == bytes.fromhex("3925841d02dc09fbdc118597196a0b32")      # FIPS-197 App. B
     targets = key_t + pt_t + ct_t
     pw = PartialWitness()
     for t, v in zip(targets, key + pt + ct):
@@ -65,6 +69,23 @@ def aes_gcm(L=16, tag=True):
     pw = PartialWitness()
     tg.set_targets(pw, key, nonce, pt, ct, tagv)
     return data, data.generate_witness(pw), tg
+
+
+@functools.lru_cache(maxsize=None)
+def public_input_circuit():
+    """arithmetic circuit with three registered public inputs (CircuitBuilder::register_public_input):
+    exercises PublicInputGate against a non-zero public-input hash computed by in-circuit PoseidonGate rows"""
+    b = CircuitBuilder()
+    x, y = b.add_virtual_target(), b.add_virtual_target()
+    z = b.mul(x, y)
+    w = b.add(z, x)
+    b.register_public_inputs([x, w, z])
+    data = b.build()
+    pw = PartialWitness()
+    pw.set_target(x, 1234567)
+    pw.set_target(y, 0xFFFFFFFF00000000)
+    slots = data.generate_slots(pw)
+    return data, data.generate_witness(pw), data.public_inputs_of(slots)
 
 
 def gcm_inputs(tg, seed, count):

@@ -195,8 +195,10 @@ class OracleCircuit:
         self.proof_len = orc.lib.orc_proof_len(C.addressof(self.desc))
         self.cap = _view(orc.lib.orc_circuit_cap(self.h), (1 << data.config.fri_config.cap_height, 4))
 
-    def prove(self, wires, debug=False):
+    def prove(self, wires, debug=False, public_inputs=None):
         wires = np.ascontiguousarray(wires, dtype=np.uint64)
+        pi = np.ascontiguousarray(public_inputs, dtype=np.uint64) if self.desc.num_public_inputs else None
+        assert pi is None or pi.size == self.desc.num_public_inputs
         out = np.zeros(self.proof_len, dtype=np.uint64)
         tr = OracleTranscript()
         zs = qc = None
@@ -208,7 +210,7 @@ class OracleCircuit:
             zs = np.zeros((zs_cols, self.data.n), dtype=np.uint64)
             qc = np.zeros((d.num_challenges * d.quotient_degree_factor, self.data.n), dtype=np.uint64)
             zs_p, qc_p = zs.ctypes.data, qc.ctypes.data
-        rc = self.orc.lib.orc_prove_debug(self.h, wires.ctypes.data, None, out.ctypes.data, out.size, C.addressof(tr), zs_p, qc_p)
+        rc = self.orc.lib.orc_prove_debug(self.h, wires.ctypes.data, pi.ctypes.data if pi is not None else None, out.ctypes.data, out.size, C.addressof(tr), zs_p, qc_p)
         if rc < 0:
             raise ValueError(f"oracle prove failed: {rc}")
         assert rc == self.proof_len, (rc, self.proof_len)

@@ -21,7 +21,7 @@ def test_header_symbols_exported():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(ffi.SIGNATURES) == names
-    assert lib.p2g_version() == 1
+    assert lib.p2g_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -125,3 +125,52 @@ def test_coset_sharded_commit_matches_full(gpu_ctx, oracle, ncols, log_n):
             gpu_ctx.check(gpu_ctx.lib.p2g_batch_free(gpu_ctx.handle, h))
         assert np.array_equal(np.concatenate(caps), ob.tree.cap), world
     ob.free()
+
+
+@pytest.mark.parametrize("log_leaves", [1, 2, 3, 4])
+def test_merkle_fewer_leaves_than_a_warp(gpu_ctx, oracle, log_leaves):
+    """2..16 leaves with cap heights below the leaf level: the leaf kernel's block is padded to a full
+    warp and must not fold (or write) nodes that do not exist."""
+    rng = np.random.default_rng(40 + log_leaves)
+    for leaf_len in (3, 9):
+        rows = rng.integers(0, P, size=(1 << log_leaves, leaf_len), dtype=np.uint64)
+        for cap_height in range(0, log_leaves + 1):
+            cap, dig = gpu_ctx.merkle_cap(rows, cap_height)
+            t = oracle.merkle(rows, cap_height)
+            assert np.array_equal(cap, t.cap), (log_leaves, leaf_len, cap_height)
+            assert np.array_equal(dig, t.level(0))
+            t.free()
+    cols = _cols(log_leaves, 5, 1)
+    for cap_height in (0, 1, 2, 3):
+        gb = PolynomialBatch.from_values(gpu_ctx, cols, 3, cap_height)
+        ob = oracle.batch(cols, True, 3, cap_height)
+        _compare(gb, ob)
+        gb.free(); ob.free()
+
+
+def test_unsupported_sizes_are_refused(gpu_ctx):
+    """transforms above 2^17 points would need NTT tables that grow as n^2: refused, not attempted"""
+    import ctypes as C
+    h = C.c_void_p()
+    dummy = np.zeros(8, dtype=np.uint64)
+    rc = gpu_ctx.lib.p2g_commit_from_values(gpu_ctx.handle, dummy.ctypes.data, 1, 18, 3, 4, C.byref(h), None)
+    assert rc == -2
+
+
+def test_contexts_on_two_devices_in_one_process(oracle):
+    """One process driving several GPUs (the Rust side's model): the > 48 KB shared-memory opt-in of the
+    NTT kernel is per device.  Needs 2 GPUs; with one GPU two contexts on it are checked instead."""
+    import torch
+    from plonky2_aes_b200.host.polynomial_batch import Context
+    ndev = torch.cuda.device_count()
+    devs = [0, 1] if ndev >= 2 else [0, 0]
+    cols = _cols(9, 3, 13)                   # log_m = 13: 69 KB of dynamic shared memory
+    ob = oracle.batch(cols, True)
+    ctxs = [Context(d) for d in devs]
+    for c in ctxs:
+        gb = PolynomialBatch.from_values(c, cols)
+        assert np.array_equal(gb.cap, ob.tree.cap)
+        gb.free()
+    for c in ctxs:
+        c.close()
+    ob.free()

@@ -278,3 +278,61 @@ def test_golden_proof_digests_gpu(gpu_ctx):
         assert g.sha(data.constants_sigmas_cap) == ref["constants_sigmas_cap_sha256"], name
         proof = data.prove_wires(wires)
         assert len(proof) == ref["proof_words"] and g.sha(proof) == ref["proof_sha256"], name
+
+
+def test_aes192_block(gpu_ctx, oracle):
+    """AES-192 (NK=6, NR=12) single-block circuit, the middle case of test_encrypt_block_test_vector
+    (/root/reference/aes-gcm/src/circuit_aes.rs:619-655)."""
+    data, wires, _ = circuits.aes_block(6, 12)
+    _check(gpu_ctx, oracle, data, wires).free()
+
+
+def test_public_inputs(gpu_ctx, oracle):
+    """register_public_input: PublicInputGate against a non-zero hash, public inputs at the proof tail."""
+    data, wires, pi = circuits.public_input_circuit()
+    data.load(gpu_ctx)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    o_proof = oc.prove(wires, public_inputs=pi)
+    g_proof = data.prove_wires(wires, pi)
+    assert np.array_equal(g_proof, o_proof)
+    assert list(g_proof[-len(pi):]) == list(pi)
+    assert oc.verify(g_proof) == 0
+    bad = pi.copy(); bad[0] += 1                          # proof for other public inputs: rejected
+    assert oc.verify(data.prove_wires(wires, bad)) != 0
+    assert np.array_equal(data.prove_slots(data.generate_slots(_pw_public(data))), o_proof)
+    oc.free()
+
+
+def _pw_public(data):
+    from plonky2_aes_b200.host.circuit_builder import PartialWitness
+    pw = PartialWitness()
+    x, w, z = data.public_input_targets
+    pw.set_target(x, 1234567)
+    pw.set_target(z, (1234567 * 0xFFFFFFFF00000000) % P)
+    return pw
+
+
+def test_circuit_load_error_paths_do_not_leak(gpu_ctx):
+    """p2g_circuit_load refusing a descriptor (bad lookup rows: detected after the preprocessed commitment
+    was built) must give every device buffer back."""
+    import torch
+    data, _, _ = circuits.aes_gcm(13, True)
+    data.load(gpu_ctx)
+    lib = gpu_ctx.lib
+    d = data.descriptor()
+    rows = np.array(data._lookup_rows_arr, dtype=np.int32).copy()
+    rows[2] = data.n                                       # first_lut_gate + 1 >= n
+    d.lookup_rows = rows.ctypes.data_as(C.POINTER(C.c_int32))
+    h = C.c_void_p()
+    assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d), C.byref(h), None) == -2     # warm the pool
+    gpu_ctx.sync(); torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(5):
+        assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d), C.byref(h), None) == -2
+    gpu_ctx.sync(); torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 >= free0 - (1 << 20), (free0, free1)
+    d2 = data.descriptor(); d2.pow_bits = 0
+    assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d2), C.byref(h), None) == -2
+    d3 = data.descriptor(); d3.degree_bits = 18
+    assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d3), C.byref(h), None) == -2

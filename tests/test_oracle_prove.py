@@ -25,6 +25,16 @@ def test_native_aes_fips197_vectors():
 def test_native_gcm_nist_cavp_vectors():
     # /root/reference/aes-gcm/src/native_gcm.rs:286-330: NIST CAVP AES-128-GCM, 96-bit IV, no AAD
     vecs = [
+        # the four vectors the reference holds (CAVP file lines 7, 4417, 8834, 13237)
+        ("cf063a34d4a9a76c2c86787d3f96db71", "113b9785971864c83b01c787", "", "", "72ac8493e3a5228b5d130a69d2510e42"),
+        ("e98b72a9881a84ca6b76e0f43e68647a", "8b23299fde174053f3d652ba", "28286a321293253c3e0aa2704a278032",
+         "5a3c1cf1985dbb8bed818036fdd5ab42", "23c7ab0f952b7091cd324835043b5eb5"),
+        ("387218b246c1a8257748b56980e50c94", "dd7e014198672be39f95b69d", "48f5b426baca03064554cc2b30",
+         "cdba9e73eaf3d38eceb2b04a8d", "ecf90f4a47c9c626d6fb2c765d201556"),
+        ("bfd414a6212958a607a0f5d3ab48471d", "86d8ea0ab8e40dcc481cd0e2",
+         "a6b76a066e63392c9443e60272ceaeb9d25c991b0f2e55e2804e168c05ea591a",
+         "62171db33193292d930bf6647347652c1ef33316d7feca99d54f1db4fcf513f8", "c28280aa5c6c7a8bd366f28c1cfd1f6e"),
+        # two more from the same CAVP set
         ("11754cd72aec309bf52f7687212e8957", "3c819d9a9bed087615030b65", "", "", "250327c674aaf477aef2675748cf6971"),
         ("7fddb57453c241d03efbed3ac44e371c", "ee283a3fc75575e33efd4887", "d5de42b461646c255c87bd2962d3b9a2",
          "2ccda4a5415cb91e135c2a0f78c9b2fd", "b36d1df9b9d5e596f83e8b7f52971cb3"),
@@ -158,3 +168,26 @@ def test_golden_proof_digests(oracle):
         oc.free()
         seen.add(name)
     assert seen == set(gold)
+
+
+def test_public_inputs_prove_verify(oracle):
+    """register_public_input: the PublicInputGate ties wires 0..4 to the in-circuit hash of the public
+    inputs; the verifier recomputes it from the proof tail."""
+    data, wires, pi = circuits.public_input_circuit()
+    oracle_lib.set_circuit_digest(oracle, data)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    proof = oc.prove(wires, public_inputs=pi)
+    assert list(proof[-3:]) == list(pi)
+    assert oc.verify(proof) == 0
+    bad = proof.copy(); bad[-1] ^= 1
+    assert oc.verify(bad) != 0
+    oc.free()
+
+
+def test_aes192_block_circuit(oracle):
+    """NK=6, NR=12 of test_encrypt_block_test_vector (/root/reference/aes-gcm/src/circuit_aes.rs:631-640)"""
+    data, wires, _ = circuits.aes_block(6, 12)
+    oracle_lib.set_circuit_digest(oracle, data)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    assert oc.verify(oc.prove(wires)) == 0
+    oc.free()
