@@ -71,6 +71,9 @@ int32_t p2w_generate_slots(const p2w_program* p, const int32_t* input_slots, con
                            uint32_t num_inputs, uint64_t* ext_out /*[p2w_ext_slots]*/);
 int32_t p2w_generate_slots_many(const p2w_program* p, const int32_t* input_slots, const uint64_t* input_vals,
                                 uint32_t num_inputs, uint32_t count, uint64_t* ext_out);
+/* threads of the *_many entry points; 0 = OpenMP default (OMP_NUM_THREADS / all cores) */
+void p2w_set_num_threads(int32_t n);
+int32_t p2w_num_threads(void);
 /* p2w_generate for `count` independent witnesses laid out back to back (OpenMP over witnesses) */
 int32_t p2w_generate_many(const p2w_program* p, const int32_t* input_slots, const uint64_t* input_vals,
                           uint32_t num_inputs, uint32_t count, uint64_t* wires_out);

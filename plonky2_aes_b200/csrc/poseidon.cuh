@@ -285,7 +285,16 @@ __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonic
 // lazy in (any u64), lazy out.  Dense partial rounds: the sparse ("fast") form was measured at
 // the same throughput (profiles/r1_poseidon_kernel_ncu_summary.txt: 677 vs 673 M perm/s) and
 // costs an 11x11 initial matrix plus 5 KB of constants, so the simpler form is kept.
-__device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
+// Phase pairing.  A permutation is an integer-heavy stretch (4 + 4 full rounds: 96 S-boxes, ALU / IMAD
+// pipes) around an FP64-heavy stretch (11 merged partial-round pairs: 3700 DFMA).  Warps that start
+// together stay in the same stretch, so the two pipe groups take turns instead of overlapping (measured:
+// FP64 half alone 2.53 G perm/s, integer half alone 1.66 G, together 1.37 G ~ the serial sum).  With
+// PAIRED, two warps of one SM sub-partition meet at a named barrier at every stretch boundary, one of
+// them a stretch behind (pos_pair_begin / pos_pair_end), so one is always in its integer stretch
+// while the other is in its FP64 stretch.
+__device__ __forceinline__ void pos_bar_sync(uint32_t bar_id) { asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory"); }
+// bar_id: named barrier (1..15) shared by the two warps of a pair, 0 = unpaired (warp-uniform value)
+__device__ __forceinline__ void poseidon_permute_lazy_b(gl_t s[12], uint32_t bar_id) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_dev(s[i], POSEIDON_RC_DEV[i]);
     int k = 0;
@@ -296,6 +305,7 @@ __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
             poseidon_round<true>(s, k + 1);
         }
         if (phase == 0) {
+            if (bar_id) pos_bar_sync(bar_id);
 #if P2G_PARTIAL_PAIRS
             const int zero = pos_lane_zero();
 #pragma unroll 1
@@ -306,9 +316,15 @@ __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
                 poseidon_round<false>(s, k + 1);
             }
 #endif
+            if (bar_id) pos_bar_sync(bar_id);
         }
     }
 }
+// the warp that runs a stretch behind waits once before its first permutation, its partner once after
+// its last one, so both execute the same number of barriers
+__device__ __forceinline__ void pos_pair_begin(uint32_t bar_id, bool behind) { if (behind) pos_bar_sync(bar_id); }
+__device__ __forceinline__ void pos_pair_end(uint32_t bar_id, bool behind) { if (!behind) pos_bar_sync(bar_id); }
+__device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) { poseidon_permute_lazy_b(s, 0); }
 __device__ __forceinline__ void poseidon_permute(gl_t s[12]) {
     poseidon_permute_lazy(s);
 #pragma unroll
@@ -414,6 +430,10 @@ inline void poseidon_permute(gl_t s[12]) {
     }
 }
 inline void poseidon_permute_lazy(gl_t s[12]) { poseidon_permute(s); }
+// host pass of the device kernels only (never executed)
+inline void poseidon_permute_lazy_b(gl_t s[12], uint32_t) { poseidon_permute(s); }
+inline void pos_pair_begin(uint32_t, bool) {}
+inline void pos_pair_end(uint32_t, bool) {}
 #endif
 
 // two_to_one(l, r): Poseidon([l, r, 0, 0, 0, 0])[0..4]

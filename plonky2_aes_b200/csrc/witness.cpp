@@ -5,6 +5,7 @@
 #include <vector>
 #include <string.h>
 #include <stdlib.h>
+#include <omp.h>
 
 static const uint64_t W_RC[360] = {
 #include "poseidon_rc.inc"
@@ -219,11 +220,16 @@ extern "C" int32_t p2w_generate(const p2w_program* p, const int32_t* in_slots, c
     return 0;
 }
 
+// OpenMP threads used by the *_many entry points (launchers such as torchrun export OMP_NUM_THREADS=1)
+static int g_p2w_threads = 0;
+extern "C" void p2w_set_num_threads(int32_t n) { g_p2w_threads = n > 0 ? n : 0; }
+extern "C" int32_t p2w_num_threads(void) { return g_p2w_threads > 0 ? g_p2w_threads : omp_get_max_threads(); }
+
 extern "C" int32_t p2w_generate_slots_many(const p2w_program* p, const int32_t* in_slots, const uint64_t* in_vals, uint32_t num_inputs,
                                            uint32_t count, uint64_t* ext_out) {
     if (!p || !ext_out) return P2W_E_BADARG;
     int32_t rc_all = 0;
-#pragma omp parallel for schedule(dynamic)
+#pragma omp parallel for schedule(dynamic) num_threads(p2w_num_threads())
     for (int64_t w = 0; w < (int64_t)count; w++) {
         int32_t rc = p2w_generate_slots(p, in_slots, in_vals + (size_t)w * num_inputs, num_inputs, ext_out + (size_t)w * p->ext_total);
         if (rc) {
@@ -238,7 +244,7 @@ extern "C" int32_t p2w_generate_many(const p2w_program* p, const int32_t* in_slo
                                      uint32_t count, uint64_t* wires) {
     const size_t cells = (size_t)p->d.num_wires << p->d.log_n;
     int32_t rc_all = 0;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(p2w_num_threads())
     for (uint32_t w = 0; w < count; w++) {
         int32_t rc = p2w_generate(p, in_slots, in_vals + (size_t)w * num_inputs, num_inputs, wires + w * cells);
         if (rc) {

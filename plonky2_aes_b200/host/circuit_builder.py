@@ -600,6 +600,8 @@ class CircuitData:
         lib.p2w_program_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.p2w_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.p2w_generate_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.p2w_set_num_threads.argtypes = [C.c_int32]
+        lib.p2w_set_num_threads.restype = None
         lib.p2w_ext_slots.argtypes = [C.c_void_p]
         lib.p2w_ext_slots.restype = C.c_uint32
         lib.p2w_wire_map.argtypes = [C.c_void_p, C.c_void_p]

@@ -81,6 +81,7 @@ def public_input_circuit():
     w = b.add(z, x)
     b.register_public_inputs([x, w, z])
     data = b.build()
+    data.test_y_target = y
     pw = PartialWitness()
     pw.set_target(x, 1234567)
     pw.set_target(y, 0xFFFFFFFF00000000)

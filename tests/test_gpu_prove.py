@@ -308,7 +308,8 @@ def _pw_public(data):
     pw = PartialWitness()
     x, w, z = data.public_input_targets
     pw.set_target(x, 1234567)
-    pw.set_target(z, (1234567 * 0xFFFFFFFF00000000) % P)
+    pw.set_target(z, (1234567 * 0xFFFFFFFF00000000) % P)     # consistent with y below: no conflict
+    pw.set_target(data.test_y_target, 0xFFFFFFFF00000000)
     return pw
 
 
