@@ -182,10 +182,6 @@ int32_t p2g_fri_fold(p2g_ctx* ctx, const uint64_t* values_host /*[N][2]*/, uint3
 /* chained Poseidon permutations without memory traffic: the INT-pipe peak used as roofline
  * denominator for the Merkle kernels.  Returns permutations per second. */
 int32_t p2g_poseidon_peak(p2g_ctx* ctx, uint32_t iters, double* perms_per_sec);
-/* same with the warp scheduling variant chosen: 0 plain, 1 phase-paired warps (w, w+4) -- the form the Merkle
- * leaf kernel uses --, 2 paired warps (w, w+1) (control).  checksum (may be NULL): digest of the results,
- * equal for every mode. */
-int32_t p2g_poseidon_peak_mode(p2g_ctx* ctx, uint32_t iters, int32_t mode, double* perms_per_sec, uint64_t* checksum);
 /* Device field arithmetic exposed for parity tests (plonky2 field/src/goldilocks_field.rs Add / Sub /
  * Mul and to_canonical_u64): for i < n,
  *   out[0][i] = a+b, out[1][i] = a-b, out[2][i] = a*b   (a, b canonical),

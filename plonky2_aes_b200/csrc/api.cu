@@ -303,26 +303,17 @@ extern "C" int32_t p2g_hash_no_pad_many(p2g_ctx* ctx, const uint64_t* in_host, u
 }
 
 extern "C" int32_t p2g_poseidon_peak(p2g_ctx* ctx, uint32_t iters, double* perms_per_sec) {
-    return p2g_poseidon_peak_mode(ctx, iters, 0, perms_per_sec, nullptr);
-}
-extern "C" int32_t p2g_poseidon_peak_mode(p2g_ctx* ctx, uint32_t iters, int32_t mode, double* perms_per_sec, uint64_t* checksum) {
-    if (!ctx || !perms_per_sec || !iters || mode < 0 || mode > 2) return P2G_E_BADARG;
+    if (!ctx || !perms_per_sec || !iters) return P2G_E_BADARG;
     CU(cudaSetDevice(ctx->device));
     const uint32_t nthreads = 148 * 2048;   // every SM full of resident warps
     gl_t* d_out; int rc;
     if ((rc = ctx_alloc(ctx, &d_out, nthreads))) return rc;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    poseidon_bench_launch(d_out, nthreads, 2, ctx->st, mode);   // warm-up
+    poseidon_bench_launch(d_out, nthreads, 2, ctx->st);   // warm-up
     CU(cudaEventRecord(e0, ctx->st));
-    if (poseidon_bench_launch(d_out, nthreads, iters, ctx->st, mode)) { ctx->err = "poseidon bench launch"; return P2G_E_CUDA; }
+    if (poseidon_bench_launch(d_out, nthreads, iters, ctx->st)) { ctx->err = "poseidon bench launch"; return P2G_E_CUDA; }
     CU(cudaEventRecord(e1, ctx->st));
-    if (checksum) {                        // xor of the first 4096 results: identical for every mode
-        CU(cudaMemcpyAsync(ctx->pinned, d_out, 4096 * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
-        CU(ctx_wait(ctx));
-        uint64_t x = 0; for (int i = 0; i < 4096; i++) x ^= ctx->pinned[i] * (uint64_t)(2 * i + 1);
-        *checksum = x;
-    }
     CU(ctx_wait(ctx));
     float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
     *perms_per_sec = (double)nthreads * iters / (ms * 1e-3);

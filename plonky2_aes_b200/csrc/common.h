@@ -53,4 +53,4 @@ size_t merkle_level_offset(uint32_t log_leaves, uint32_t level);  // in words
 
 // poseidon microbenchmark (roofline denominator for the INT pipe): runs `iters` chained
 // permutations per thread
-int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st, int mode = 0);
+int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st);

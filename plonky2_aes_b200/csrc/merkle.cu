@@ -41,14 +41,9 @@ __device__ __forceinline__ gl_t* level_ptr(gl_t* digests, gl_t* cap, uint32_t lo
 template <bool COL_MAJOR>
 __global__ void __launch_bounds__(MERKLE_BLOCK, POS_MINB)
 merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t leaf_len, uint32_t log_leaves,
-                     uint32_t L, uint32_t levels_here, gl_t* __restrict__ digests, gl_t* __restrict__ cap, int paired) {
+                     uint32_t L, uint32_t levels_here, gl_t* __restrict__ digests, gl_t* __restrict__ cap) {
     __shared__ gl_t sh[MERKLE_BLOCK][4];
     const uint32_t tid = threadIdx.x;
-    // phase pairing of the leaf sponge (poseidon.cuh): warps w and w + 4 share an SM sub-partition; the host
-    // sets `paired` only when every block has 8 full warps of valid leaves and at least one absorption
-    const uint32_t pair_bar = paired ? 1 + ((tid >> 5) & 3) : 0;
-    const bool pair_behind = (tid >> 7) & 1;
-    if (pair_bar) pos_pair_begin(pair_bar, pair_behind);
     const size_t j = (size_t)blockIdx.x * blockDim.x + tid;
     const size_t num_leaves = (size_t)1 << log_leaves;
     const bool leaf_ok = j < num_leaves;
@@ -98,9 +93,8 @@ merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t 
             }
             __syncthreads();
         }
-        if (active) poseidon_permute_lazy_b(s, it < absorbs ? pair_bar : 0);
+        if (active) poseidon_permute_lazy(s);
         if (it + 1 == absorbs) {                   // leaf digest complete
-            if (pair_bar) pos_pair_end(pair_bar, pair_behind);
 #pragma unroll
             for (int i = 0; i < 4; i++) s[i] = gl_canon(s[i]);
             if (leaf_ok) {
@@ -212,12 +206,10 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
             if ((int)levels_here > cap_levels) levels_here = (uint32_t)cap_levels;
         }
         uint32_t blocks = (uint32_t)((num_leaves + threads - 1) / threads);
-        static const int pair_on = [] { const char* e = getenv("P2G_POS_PAIR"); return e ? atoi(e) : 1; }();
-        const int paired = pair_on && threads == 256 && (num_leaves % 256) == 0 && leaf_len > 4;
         if (col_major)
-            merkle_leaves_kernel<true><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap, paired);
+            merkle_leaves_kernel<true><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
         else
-            merkle_leaves_kernel<false><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap, paired);
+            merkle_leaves_kernel<false><<<blocks, threads, 0, st>>>(data, col_stride, leaf_len, log_leaves, L, levels_here, digests, cap);
         P2G_COUNT_LAUNCH(1);
         lv = levels_here;
     }
@@ -239,35 +231,20 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
 }
 
 // ---- INT-pipe roofline microbenchmark: chained permutations, no memory traffic ------------
-// MODE 0: plain; 1: warps (w, w + 4) phase-paired (same SM sub-partition); 2: warps (w, w + 1) paired
-// (different sub-partitions: the control experiment -- pairing can only help where the pipes are shared)
-template <int MODE>
 __global__ void __launch_bounds__(POS_BLOCK, POS_MINB)
 poseidon_bench_kernel(gl_t* out, uint32_t iters) {
     gl_t s[12];
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = (gl_t)g * 12 + i;
-    if (MODE == 0) {
-        for (uint32_t k = 0; k < iters; k++) poseidon_permute_lazy(s);
-    } else {
-        const uint32_t w = threadIdx.x >> 5;
-        const uint32_t bar = 1 + (MODE == 1 ? (w & 3) : (w >> 1));
-        const bool behind = MODE == 1 ? (w >> 2) & 1 : w & 1;
-        pos_pair_begin(bar, behind);
-        for (uint32_t k = 0; k < iters; k++) poseidon_permute_lazy_b(s, bar);
-        pos_pair_end(bar, behind);
-    }
+    for (uint32_t k = 0; k < iters; k++) poseidon_permute_lazy(s);
     gl_t acc = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) acc ^= s[i];
     out[g] = acc;
 }
-int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st, int mode) {
-    static_assert(POS_BLOCK == 256, "the pairing of the bench kernel assumes 8 warps per block");
-    if (mode == 1) poseidon_bench_kernel<1><<<nthreads_total / POS_BLOCK, POS_BLOCK, 0, st>>>(out, iters);
-    else if (mode == 2) poseidon_bench_kernel<2><<<nthreads_total / POS_BLOCK, POS_BLOCK, 0, st>>>(out, iters);
-    else poseidon_bench_kernel<0><<<nthreads_total / POS_BLOCK, POS_BLOCK, 0, st>>>(out, iters);
+int poseidon_bench_launch(gl_t* out, uint32_t nthreads_total, uint32_t iters, cudaStream_t st) {
+    poseidon_bench_kernel<<<nthreads_total / POS_BLOCK, POS_BLOCK, 0, st>>>(out, iters);
     P2G_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -73,9 +73,38 @@ __device__ __forceinline__ void acc_mul(Acc160& A, gl_t a, gl_t b) {
 __device__ __forceinline__ gl_t acc_fold(const Acc160& A) { return gl_fold5(A.w[0], A.w[1], A.w[2], A.w[3], A.w[4]); }
 // P2G_DIAG_NO_SBOX / P2G_DIAG_NO_MDS: timing diagnostics only (tools/poseidon_overlap.sh) -- they remove the
 // integer or the FP64 half of every round to measure how much the two halves overlap; results are wrong.
+// S-box multiply, variant 2 (P2G_SBOX_V): the 128-bit product is left to the compiler -- ptxas turns
+// mul.lo.u64 + mul.hi.u64 into four IMAD.WIDE whose 64-bit addend and carry (IMAD.WIDE.U32.X) absorb the
+// partial-product additions, 7 instructions instead of 4 + 6 -- and the fold runs through one more wide
+// MAD:  t = lo + h0 * (2^32 - 1)  (65 bits),  t -= h1,  then the top word k in {-1, 0, 1} is folded back as
+// k * (2^32 - 1).  73 instead of 83 instructions per S-box.  Lazy in, lazy out.
+__device__ __forceinline__ gl_t pmul_v2(gl_t a, gl_t b) {
+    typedef unsigned __int128 u128;
+    const u128 p = (u128)a * b;
+    const uint64_t lo = (uint64_t)p, hi = (uint64_t)(p >> 64);
+    u128 t = (u128)(uint32_t)hi * 0xFFFFFFFFull + lo;
+    t -= (uint32_t)(hi >> 32);
+    const uint64_t k = (uint64_t)(t >> 64);              // 0, 1 or 2^64 - 1
+    return (uint64_t)t + (k << 32) - k;                   // cannot wrap: see the bounds in DESIGN.md
+}
+__device__ __forceinline__ gl_t pmul_v1(gl_t a, gl_t b) {
+    typedef unsigned __int128 u128;
+    const u128 p = (u128)a * b;
+    uint32_t l0, l1, h0, h1; gl_unpack((uint64_t)p, l0, l1); gl_unpack((uint64_t)(p >> 64), h0, h1);
+    return gl_fold4(l0, l1, h0, h1);
+}
+#ifndef P2G_SBOX_V
+#define P2G_SBOX_V 1
+#endif
 __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 #ifdef P2G_DIAG_NO_SBOX
     return x + 1;
+#elif P2G_SBOX_V == 2
+    gl_t x2 = pmul_v2(x, x), x4 = pmul_v2(x2, x2), x3 = pmul_v2(x, x2);
+    return pmul_v2(x3, x4);
+#elif P2G_SBOX_V == 1
+    gl_t x2 = pmul_v1(x, x), x4 = pmul_v1(x2, x2), x3 = pmul_v1(x, x2);
+    return pmul_v1(x3, x4);
 #else
     gl_t x2 = psqr(x), x4 = psqr(x2), x3 = pmul(x, x2);
     return pmul(x3, x4);
@@ -285,16 +314,7 @@ __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonic
 // lazy in (any u64), lazy out.  Dense partial rounds: the sparse ("fast") form was measured at
 // the same throughput (profiles/r1_poseidon_kernel_ncu_summary.txt: 677 vs 673 M perm/s) and
 // costs an 11x11 initial matrix plus 5 KB of constants, so the simpler form is kept.
-// Phase pairing.  A permutation is an integer-heavy stretch (4 + 4 full rounds: 96 S-boxes, ALU / IMAD
-// pipes) around an FP64-heavy stretch (11 merged partial-round pairs: 3700 DFMA).  Warps that start
-// together stay in the same stretch, so the two pipe groups take turns instead of overlapping (measured:
-// FP64 half alone 2.53 G perm/s, integer half alone 1.66 G, together 1.37 G ~ the serial sum).  With
-// PAIRED, two warps of one SM sub-partition meet at a named barrier at every stretch boundary, one of
-// them a stretch behind (pos_pair_begin / pos_pair_end), so one is always in its integer stretch
-// while the other is in its FP64 stretch.
-__device__ __forceinline__ void pos_bar_sync(uint32_t bar_id) { asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory"); }
-// bar_id: named barrier (1..15) shared by the two warps of a pair, 0 = unpaired (warp-uniform value)
-__device__ __forceinline__ void poseidon_permute_lazy_b(gl_t s[12], uint32_t bar_id) {
+__device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_add_lazy_dev(s[i], POSEIDON_RC_DEV[i]);
     int k = 0;
@@ -305,7 +325,6 @@ __device__ __forceinline__ void poseidon_permute_lazy_b(gl_t s[12], uint32_t bar
             poseidon_round<true>(s, k + 1);
         }
         if (phase == 0) {
-            if (bar_id) pos_bar_sync(bar_id);
 #if P2G_PARTIAL_PAIRS
             const int zero = pos_lane_zero();
 #pragma unroll 1
@@ -316,15 +335,9 @@ __device__ __forceinline__ void poseidon_permute_lazy_b(gl_t s[12], uint32_t bar
                 poseidon_round<false>(s, k + 1);
             }
 #endif
-            if (bar_id) pos_bar_sync(bar_id);
         }
     }
 }
-// the warp that runs a stretch behind waits once before its first permutation, its partner once after
-// its last one, so both execute the same number of barriers
-__device__ __forceinline__ void pos_pair_begin(uint32_t bar_id, bool behind) { if (behind) pos_bar_sync(bar_id); }
-__device__ __forceinline__ void pos_pair_end(uint32_t bar_id, bool behind) { if (!behind) pos_bar_sync(bar_id); }
-__device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) { poseidon_permute_lazy_b(s, 0); }
 __device__ __forceinline__ void poseidon_permute(gl_t s[12]) {
     poseidon_permute_lazy(s);
 #pragma unroll
@@ -430,10 +443,6 @@ inline void poseidon_permute(gl_t s[12]) {
     }
 }
 inline void poseidon_permute_lazy(gl_t s[12]) { poseidon_permute(s); }
-// host pass of the device kernels only (never executed)
-inline void poseidon_permute_lazy_b(gl_t s[12], uint32_t) { poseidon_permute(s); }
-inline void pos_pair_begin(uint32_t, bool) {}
-inline void pos_pair_end(uint32_t, bool) {}
 #endif
 
 // two_to_one(l, r): Poseidon([l, r, 0, 0, 0, 0])[0..4]

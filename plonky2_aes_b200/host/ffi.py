@@ -95,7 +95,6 @@ SIGNATURES = {
     "p2g_pow_grind": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "p2g_fri_fold": (C.c_int32, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _vp]),
     "p2g_poseidon_peak": (C.c_int32, [_vp, C.c_uint32, C.POINTER(C.c_double)]),
-    "p2g_poseidon_peak_mode": (C.c_int32, [_vp, C.c_uint32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "p2g_field_ops": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "p2g_wmap_load": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, C.c_uint32, C.POINTER(_vp)]),
     "p2g_wmap_free": (C.c_int32, [_vp, _vp]),
