@@ -72,7 +72,7 @@ def by_pipe(c):
 
 def main():
     model = {}
-    f = sass(r"poseidon_bench_kernelILi0")
+    f = sass(r"poseidon_bench_kernel")
     (name, code), = f.items()
     inner, _ = loops(code)
     assert len(inner) == 2, inner
