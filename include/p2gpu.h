@@ -124,6 +124,20 @@ int32_t p2g_circuit_free(p2g_ctx* ctx, p2g_circuit* c);
 /* number of u64 words of a serialised proof for this circuit */
 size_t p2g_proof_words(const p2g_circuit* c);
 
+/* ---- ProofWithPublicInputs::to_bytes / from_bytes (plonky2 util/serialization/mod.rs) -----------------
+ * Converts between the flat proof words p2g_prove returns (layout: DESIGN.md section 5) and upstream's byte
+ * format, so the Rust side finishes with `ProofWithPublicInputs::from_bytes(bytes, common_data)`:
+ * little-endian u64 field elements in upstream's write order (caps; openings with the two lookup vectors
+ * after plonk_zs_next; FRI caps; per query the initial-tree rows and steps, every Merkle path preceded by its
+ * length as one u8; final polynomial; pow witness; the public-input count as u64, then the public inputs).
+ * Host-only: needs no context and no device.  from_bytes rejects non-canonical elements, wrong path lengths
+ * and trailing bytes with P2G_E_BADARG. */
+size_t p2g_proof_bytes_len(const p2g_circuit_desc* desc);
+int32_t p2g_proof_to_bytes(const p2g_circuit_desc* desc, const uint64_t* words, size_t nwords, uint8_t* out, size_t cap_bytes,
+                           size_t* len_out);
+int32_t p2g_proof_from_bytes(const p2g_circuit_desc* desc, const uint8_t* bytes, size_t len, uint64_t* words_out,
+                             size_t cap_words, size_t* words_len);
+
 /* ---- the whole hot path: prove_with_partition_witness (plonk/prover.rs) ----------------------
  * wires: [num_wires][n] host, column-major full witness; public_inputs: num_public_inputs words.
  * proof_out: flat u64 proof (layout in DESIGN.md, identical to the oracle's). */

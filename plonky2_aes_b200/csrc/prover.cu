@@ -90,6 +90,115 @@ static size_t proof_len(const p2g_circuit_desc& d) {
     return len + per_q * d.num_query_rounds + 2 * fin + 1 + d.num_public_inputs;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ProofWithPublicInputs::to_bytes / from_bytes (util/serialization/mod.rs): the flat proof words
+//  <-> upstream's wire format.  Pure host code, needs no device.
+// Walks the proof in WORD order and reports for every segment where it goes in BYTE order.
+// ---------------------------------------------------------------------------------------------
+struct ProofSeg { size_t word_pos, words; int kind; };        // kind 0: field words, 1: Merkle path length (u8)
+static void proof_segments(const p2g_circuit_desc& d, std::vector<ProofSeg>& word_order, std::vector<int>& byte_order) {
+    const size_t cap = (size_t)4 << d.cap_height;
+    const int nlp = num_lookup_polys(d), nch = d.num_challenges;
+    const int NC = d.num_selectors + d.num_lookup_selectors + d.num_constants;
+    const int logN = d.degree_bits + d.rate_bits;
+    const int zs_cols = nch * (1 + d.num_partial_products + nlp);
+    size_t pos = 0;
+    auto seg = [&](size_t words, int kind) { word_order.push_back({pos, words, kind}); pos += words; return (int)word_order.size() - 1; };
+    for (int i = 0; i < 3; i++) byte_order.push_back(seg(cap, 0));
+    // openings, word order: constants, plonk_sigmas, wires, plonk_zs, plonk_zs_next, partial_products,
+    // quotient_polys, lookup_zs, lookup_zs_next; upstream writes the two lookup vectors right after plonk_zs_next
+    const size_t ow[9] = {(size_t)NC, (size_t)d.num_routed_wires, (size_t)d.num_wires, (size_t)nch, (size_t)nch,
+                          (size_t)nch * d.num_partial_products, (size_t)nch * d.quotient_degree_factor, (size_t)nch * nlp, (size_t)nch * nlp};
+    int os[9];
+    for (int i = 0; i < 9; i++) os[i] = seg(2 * ow[i], 0);
+    const int oorder[9] = {0, 1, 2, 3, 4, 7, 8, 5, 6};
+    for (int i = 0; i < 9; i++) byte_order.push_back(os[oorder[i]]);
+    for (int l = 0; l < d.num_reduction_arity_bits; l++) byte_order.push_back(seg(cap, 0));
+    const int cols[4] = {NC + d.num_routed_wires, d.num_wires, zs_cols, nch * d.quotient_degree_factor};
+    for (int q = 0; q < d.num_query_rounds; q++) {
+        for (int o = 0; o < 4; o++) {
+            byte_order.push_back(seg((size_t)cols[o], 0));
+            byte_order.push_back(seg(1, 1));
+            byte_order.push_back(seg(4 * (size_t)(logN - d.cap_height), 0));
+        }
+        int lg = logN;
+        for (int l = 0; l < d.num_reduction_arity_bits; l++) {
+            const int ab = d.reduction_arity_bits[l];
+            lg -= ab;
+            byte_order.push_back(seg((size_t)2 << ab, 0));
+            byte_order.push_back(seg(1, 1));
+            byte_order.push_back(seg(4 * (size_t)(lg - d.cap_height), 0));
+        }
+    }
+    size_t fin = (size_t)1 << d.degree_bits;
+    for (int l = 0; l < d.num_reduction_arity_bits; l++) fin >>= d.reduction_arity_bits[l];
+    byte_order.push_back(seg(2 * fin, 0));
+    byte_order.push_back(seg(1, 0));                                   // pow_witness
+    byte_order.push_back(seg((size_t)d.num_public_inputs, 0));        // preceded by its length (usize = u64 LE)
+}
+static bool proof_desc_ok(const p2g_circuit_desc* d) {
+    return d && d->degree_bits >= 0 && d->degree_bits <= 30 && d->rate_bits >= 0 && d->rate_bits <= 8 && d->cap_height >= 0 &&
+           d->cap_height <= d->degree_bits + d->rate_bits && d->num_reduction_arity_bits >= 0 && d->num_reduction_arity_bits <= 16 &&
+           d->num_query_rounds >= 0 && d->num_public_inputs >= 0 && d->num_challenges >= 1 && d->quotient_degree_factor >= 2;
+}
+extern "C" size_t p2g_proof_bytes_len(const p2g_circuit_desc* d) {
+    if (!proof_desc_ok(d)) return 0;
+    std::vector<ProofSeg> segs; std::vector<int> order;
+    proof_segments(*d, segs, order);
+    size_t len = 8;                                                    // public-input count
+    for (const auto& s : segs) len += s.kind == 1 ? 1 : 8 * s.words;
+    return len;
+}
+extern "C" int32_t p2g_proof_to_bytes(const p2g_circuit_desc* d, const uint64_t* words, size_t nwords, uint8_t* out, size_t cap,
+                                      size_t* len_out) {
+    if (!proof_desc_ok(d) || !words || !out) return P2G_E_BADARG;
+    std::vector<ProofSeg> segs; std::vector<int> order;
+    proof_segments(*d, segs, order);
+    if (nwords != segs.back().word_pos + segs.back().words || cap < p2g_proof_bytes_len(d)) return P2G_E_BADARG;
+    uint8_t* o = out;
+    auto put64 = [&](uint64_t v) { for (int b = 0; b < 8; b++) *o++ = (uint8_t)(v >> (8 * b)); };
+    for (size_t k = 0; k < order.size(); k++) {
+        const ProofSeg& s = segs[order[k]];
+        if (k + 1 == order.size()) put64((uint64_t)d->num_public_inputs);
+        if (s.kind == 1) {
+            if (words[s.word_pos] > 255) return P2G_E_BADARG;
+            *o++ = (uint8_t)words[s.word_pos];
+        } else {
+            for (size_t i = 0; i < s.words; i++) put64(words[s.word_pos + i]);
+        }
+    }
+    if (len_out) *len_out = (size_t)(o - out);
+    return P2G_OK;
+}
+extern "C" int32_t p2g_proof_from_bytes(const p2g_circuit_desc* d, const uint8_t* bytes, size_t len, uint64_t* words_out,
+                                        size_t cap_words, size_t* words_len) {
+    if (!proof_desc_ok(d) || !bytes || !words_out) return P2G_E_BADARG;
+    std::vector<ProofSeg> segs; std::vector<int> order;
+    proof_segments(*d, segs, order);
+    const size_t nwords = segs.back().word_pos + segs.back().words;
+    if (len != p2g_proof_bytes_len(d) || cap_words < nwords) return P2G_E_BADARG;
+    const uint8_t* p = bytes;
+    auto get64 = [&]() { uint64_t v = 0; for (int b = 0; b < 8; b++) v |= (uint64_t)*p++ << (8 * b); return v; };
+    for (size_t k = 0; k < order.size(); k++) {
+        const ProofSeg& s = segs[order[k]];
+        if (k + 1 == order.size() && get64() != (uint64_t)d->num_public_inputs) return P2G_E_BADARG;
+        if (s.kind == 1) {
+            words_out[s.word_pos] = *p++;
+            // the path length is implied by the circuit: anything else is a malformed proof
+            const size_t expect = segs[order[k + 1]].words / 4;
+            if (words_out[s.word_pos] != expect) return P2G_E_BADARG;
+        } else {
+            for (size_t i = 0; i < s.words; i++) {
+                const uint64_t v = get64();
+                if (v >= GL_P) return P2G_E_BADARG;                    // upstream: non-canonical field element
+                words_out[s.word_pos + i] = v;
+            }
+        }
+    }
+    if (words_len) *words_len = nwords;
+    return P2G_OK;
+}
+
 extern "C" int32_t p2g_circuit_load(p2g_ctx* ctx, const p2g_circuit_desc* desc, p2g_circuit** out, uint64_t* cap_out) {
     if (!ctx || !desc || !out) return P2G_E_BADARG;
     const p2g_circuit_desc& d = *desc;

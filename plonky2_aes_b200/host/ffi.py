@@ -83,6 +83,9 @@ SIGNATURES = {
     "p2g_circuit_load": (C.c_int32, [_vp, C.POINTER(CircuitDesc), C.POINTER(_vp), _vp]),
     "p2g_circuit_free": (C.c_int32, [_vp, _vp]),
     "p2g_proof_words": (C.c_size_t, [_vp]),
+    "p2g_proof_bytes_len": (C.c_size_t, [_vp]),
+    "p2g_proof_to_bytes": (C.c_int32, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "p2g_proof_from_bytes": (C.c_int32, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2g_prove": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2g_prove_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2g_last_transcript": (C.c_int32, [_vp, C.POINTER(Transcript)]),

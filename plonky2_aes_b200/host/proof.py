@@ -1,10 +1,14 @@
 """Proof container: named views over the flat u64 proof words and the byte
 serialisation of plonky2's `ProofWithPublicInputs::to_bytes` / `from_bytes`
-(util/serialization/mod.rs of the pinned dependency, as recalled: little-endian u64 field
-elements in struct order, no length prefixes except a `u8` in front of every Merkle path).
+(util/serialization/mod.rs of the pinned dependency; the byte format itself is implemented once, in the C ABI:
+p2g_proof_to_bytes / p2g_proof_from_bytes, include/p2gpu.h).
 The reference never calls the serialiser; it is provided for shipping
 proofs off the box."""
+import ctypes as C
+
 import numpy as np
+
+from .ffi import P2GError, load_library
 
 
 def _layout(d):
@@ -70,25 +74,25 @@ class Proof:
         return int(self["fri.pow_witness"][0])
 
     def to_bytes(self):
-        out = bytearray()
-        for name, (pos, cnt, kind) in self.segments.items():
-            seg = self.words[pos:pos + cnt]
-            if kind == "len":
-                out += bytes([int(seg[0])])
-            else:
-                out += seg.astype("<u8").tobytes()
-        return bytes(out)
+        """ProofWithPublicInputs::to_bytes through the C ABI (p2g_proof_to_bytes; host-only code of libp2gpu.so)"""
+        lib = load_library()
+        n = lib.p2g_proof_bytes_len(C.byref(self.desc))
+        out = np.empty(n, dtype=np.uint8)
+        got = C.c_size_t()
+        rc = lib.p2g_proof_to_bytes(C.byref(self.desc), self.words.ctypes.data, self.words.size, out.ctypes.data, n, C.byref(got))
+        if rc != 0:
+            raise P2GError(rc, "p2g_proof_to_bytes")
+        return out[:got.value].tobytes()
 
     @classmethod
     def from_bytes(cls, data, desc):
-        words, off = [], 0
-        for _, cnt, kind in _layout(desc):
-            if kind == "len":
-                words.append(np.array([data[off]], dtype=np.uint64))
-                off += 1
-            else:
-                words.append(np.frombuffer(data, dtype="<u8", count=cnt, offset=off).astype(np.uint64))
-                off += 8 * cnt
-        if off != len(data):
-            raise ValueError("trailing bytes in proof")
-        return cls(np.concatenate(words) if words else np.zeros(0, dtype=np.uint64), desc)
+        """ProofWithPublicInputs::from_bytes(bytes, common_data): raises on malformed input"""
+        lib = load_library()
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        nwords = sum(cnt for _, cnt, _ in _layout(desc))
+        words = np.empty(nwords, dtype=np.uint64)
+        got = C.c_size_t()
+        rc = lib.p2g_proof_from_bytes(C.byref(desc), buf.ctypes.data, buf.size, words.ctypes.data, nwords, C.byref(got))
+        if rc != 0:
+            raise ValueError("malformed proof bytes")
+        return cls(words[:got.value], desc)

@@ -138,11 +138,29 @@ def test_proof_views_and_byte_round_trip(oracle):
     assert pr.pow_witness == tr.pow_witness
     assert pr["wires_cap"].size == 64 and pr["openings.wires"].size == 270
     assert int(pr["fri.query[0].initial[1].path_len"][0]) == data.degree_bits + 3 - 4
-    raw = pr.to_bytes()
+    raw = pr.to_bytes()                                  # p2g_proof_to_bytes (C ABI, host-only)
     n_paths = data.config.fri_config.num_query_rounds * (4 + len(data.reduction_arity_bits))
-    assert len(raw) == 8 * (len(words) - n_paths) + n_paths
+    assert len(raw) == 8 * (len(words) - n_paths) + n_paths + 8        # + the public-input count (u64)
+    # independent restatement of upstream's write order (util/serialization/mod.rs): caps; openings with
+    # lookup_zs / lookup_zs_next right after plonk_zs_next; FRI caps; queries (u8 path lengths); final poly;
+    # pow witness; number of public inputs; public inputs
+    names = list(pr.segments)
+    op = [s for s in names if s.startswith("openings.")]
+    assert [s.split(".")[1] for s in op] == ["constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next",
+                                              "partial_products", "quotient_polys", "lookup_zs", "lookup_zs_next"]
+    order = names[:3] + op[:5] + op[7:9] + op[5:7] + [s for s in names[3:] if not s.startswith("openings.")]
+    exp = bytearray()
+    for s in order:
+        pos, cnt, kind = pr.segments[s]
+        if s == "public_inputs":
+            exp += (cnt).to_bytes(8, "little")
+        exp += bytes([int(words[pos])]) if kind == "len" else words[pos:pos + cnt].astype("<u8").tobytes()
+    assert raw == bytes(exp)
     back = Proof.from_bytes(raw, data.descriptor())
     assert np.array_equal(back.words, words) and oc.verify(back.words) == 0
+    for bad in (raw[:-1], raw + b"\0", raw[:200] + b"\xff" * 8 + raw[208:]):       # truncated, trailing, non-canonical
+        with pytest.raises(ValueError):
+            Proof.from_bytes(bad, data.descriptor())
     oc.free()
 
 
