@@ -19,6 +19,7 @@
 #define P2GPU_H
 #include <stdint.h>
 #include <stddef.h>
+#include "p2witness.h"   /* p2w_program_desc: the generator program p2g_wprog_load takes */
 
 #ifdef __cplusplus
 extern "C" {
@@ -168,6 +169,25 @@ int32_t p2g_prove_slots(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, c
                         const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
 /* the gathered wire matrix of the last p2g_prove_slots call is not kept; this fills one for tests */
 int32_t p2g_wmap_fill(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_host, uint64_t* wires_out_host);
+/* Witness generation on the device: generate_partial_witness + set_lookup_wires
+ * (plonky2 iop/generator.rs, plonk/prover.rs) for the ArithmeticGate / LookupGate / equality / ConstantGate /
+ * PoseidonGate generators, from the same program description libp2witness.so interprets on the host.  The program
+ * is level-scheduled at load; one warp evaluates one witness.  `input_slots`: the partitions the caller sets
+ * (PartialWitness::set_target), fixed per program; every call then passes their values in the same order.
+ * p2g_prove_inputs = generators + full_witness + prove, with a few hundred input values as the only H2D traffic;
+ * the proof equals p2g_prove on the host-generated wire matrix.  Generator failures return the P2W_E_* code of
+ * include/p2witness.h (P2W_E_CONFLICT: a preset partition disagrees with the generated value -- how the reference's
+ * prove() rejects a wrong ciphertext, /root/reference/aes-gcm/src/circuit_aes.rs:403-405; P2W_E_LOOKUP). */
+typedef struct p2g_wprog p2g_wprog;
+int32_t p2g_wprog_load(p2g_ctx* ctx, const p2w_program_desc* prog, const int32_t* input_slots, uint32_t num_inputs, p2g_wprog** out);
+int32_t p2g_wprog_free(p2g_ctx* ctx, p2g_wprog* p);
+uint32_t p2g_wprog_ext_slots(const p2g_wprog* p);   /* = p2w_ext_slots of the same program */
+uint32_t p2g_wprog_levels(const p2g_wprog* p);      /* dependency depth of the program */
+/* `count` witnesses: input_vals [count][num_inputs] (host) -> extended slot vectors [count][ext_slots] (host) */
+int32_t p2g_wprog_generate(p2g_ctx* ctx, const p2g_wprog* p, const uint64_t* input_vals, uint32_t count, uint64_t* ext_out);
+int32_t p2g_prove_inputs(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const p2g_wprog* prog,
+                         const uint64_t* input_vals_host /*[num_inputs]*/, const uint64_t* public_inputs, uint64_t* proof_out,
+                         size_t proof_cap_words, size_t* proof_words_out);
 int32_t p2g_last_transcript(p2g_ctx* ctx, p2g_transcript* out);
 int32_t p2g_last_zs_values(p2g_ctx* ctx, uint64_t* out /*[num_zs_cols][n]*/);
 int32_t p2g_last_quotient_chunks(p2g_ctx* ctx, uint64_t* out /*[num_challenges*qdf][n]*/);

@@ -838,17 +838,62 @@ extern "C" int32_t p2g_wmap_free(p2g_ctx* ctx, p2g_wmap* m) {
     delete m;
     return P2G_OK;
 }
-// slots (host) -> wire matrix (device, from the context's pool)
-static int wmap_gather(p2g_ctx* ctx, const p2g_wmap* m, const uint64_t* slots_host, gl_t** d_wires_out) {
-    int rc; gl_t *d_slots, *d_wires;
-    if ((rc = ctx_alloc(ctx, &d_slots, m->num_slots))) return rc;
+// slots (device) -> wire matrix (device, from the context's pool)
+static int wmap_gather_dev(p2g_ctx* ctx, const p2g_wmap* m, const gl_t* d_slots, gl_t** d_wires_out) {
+    int rc; gl_t* d_wires;
     if ((rc = ctx_alloc(ctx, &d_wires, m->cells))) return rc;
-    CU(cudaMemcpyAsync(d_slots, slots_host, (size_t)m->num_slots * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
     P2G_COUNT_LAUNCH(1); wire_gather_kernel<<<(unsigned)((m->cells + 255) / 256), 256, 0, ctx->st>>>(m->d_map, d_slots, m->cells, d_wires);
     if (m->num_fixed) { P2G_COUNT_LAUNCH(1); wire_fixed_kernel<<<(m->num_fixed + 255) / 256, 256, 0, ctx->st>>>(m->d_fixed_pos, m->d_fixed_val, m->num_fixed, d_wires); }
-    CU(cudaGetLastError());
-    ctx_free(ctx, d_slots);                 // stream-ordered: released after the gather
+    if (cudaGetLastError() != cudaSuccess) { ctx_free(ctx, d_wires); ctx->err = "wire gather launch"; return P2G_E_CUDA; }
     *d_wires_out = d_wires;
+    return P2G_OK;
+}
+// slots (host) -> wire matrix (device)
+static int wmap_gather(p2g_ctx* ctx, const p2g_wmap* m, const uint64_t* slots_host, gl_t** d_wires_out) {
+    int rc; gl_t* d_slots;
+    if ((rc = ctx_alloc(ctx, &d_slots, m->num_slots))) return rc;
+    if (cudaMemcpyAsync(d_slots, slots_host, (size_t)m->num_slots * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st) != cudaSuccess) {
+        ctx_free(ctx, d_slots); ctx->err = "slot upload"; return P2G_E_CUDA;
+    }
+    rc = wmap_gather_dev(ctx, m, d_slots, d_wires_out);
+    ctx_free(ctx, d_slots);                 // stream-ordered: released after the gather
+    return rc;
+}
+// ---- witness generation on the device in front of the prover (witgen.cu) ---------------------------
+int wprog_launch(p2g_ctx* ctx, const p2g_wprog* p, const gl_t* d_in, uint32_t count, gl_t* d_ext, int32_t* d_err);
+uint32_t wprog_ext_total(const p2g_wprog* p);
+uint32_t wprog_num_inputs(const p2g_wprog* p);
+extern "C" int32_t p2g_prove_inputs(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const p2g_wprog* prog,
+                                    const uint64_t* input_vals_host, const uint64_t* public_inputs, uint64_t* proof_out,
+                                    size_t proof_cap_words, size_t* proof_words_out) {
+    if (!ctx || !c || !m || !prog || !input_vals_host) return P2G_E_BADARG;
+    if (m->cells != ((size_t)c->cd.W << c->cd.logn) || m->num_slots != wprog_ext_total(prog)) {
+        ctx->err = "wire map / witness program belong to another circuit"; return P2G_E_BADARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t ni = wprog_num_inputs(prog);
+    Scratch S(ctx);
+    gl_t *d_in, *d_ext, *d_wires = nullptr; int32_t* d_err; int rc;
+    if ((rc = S.alloc(&d_in, ni))) return rc;
+    if ((rc = S.alloc(&d_ext, m->num_slots))) return rc;
+    CU(S.alloc_bytes((void**)&d_err, sizeof(int32_t)));
+    CU(cudaMemcpyAsync(d_in, input_vals_host, (size_t)ni * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = wprog_launch(ctx, prog, d_in, 1, d_ext, d_err))) return rc;
+    if ((rc = wmap_gather_dev(ctx, m, d_ext, &d_wires))) return rc;
+    S.ptrs.push_back(d_wires);
+    S.free(d_in); S.free(d_ext);
+    rc = prove_impl(ctx, c, d_wires, false, public_inputs, proof_out, proof_cap_words, proof_words_out);
+    if (rc) return rc;
+    // generator errors (a looked-up value outside its table, a preset partition that disagrees with the
+    // computed value) are flagged by the kernel; the proof of such a witness is discarded
+    int32_t* flag = (int32_t*)ctx->pinned;
+    CU(cudaMemcpyAsync(flag, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(ctx_wait(ctx));
+    if (*flag) {
+        ctx->err = (*flag & 4) ? "partition set twice with different values (P2W_E_CONFLICT)"
+                 : (*flag & 2) ? "lookup input not in table (P2W_E_LOOKUP)" : "non-canonical input value";
+        return (*flag & 4) ? -10 : (*flag & 2) ? -11 : P2G_E_BADARG;
+    }
     return P2G_OK;
 }
 extern "C" int32_t p2g_prove_slots(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_host,

@@ -651,6 +651,7 @@ class CircuitData:
                      self._w_lookup_counts.ctypes.data, self._w_lookup_slots.ctypes.data, self._w_lookup_padding.ctypes.data,
                      self._w_mult_pos.ctypes.data, self._w_num_poseidon, self._w_poseidon.ctypes.data)
             self._wlib = self._witness_lib()
+            self._wdesc = d            # p2w_program_desc (include/p2witness.h); also what p2g_wprog_load takes
             h = C.c_void_p()
             rc = self._wlib.p2w_program_create(C.byref(d), C.byref(h))
             assert rc == 0
@@ -724,6 +725,47 @@ class CircuitData:
         h = C.c_void_p()
         ctx.check(ctx.lib.p2g_wmap_load(ctx.handle, circuit, wm.ctypes.data, self.ext_slots, pos, val, cnt.value, C.byref(h)))
         return h
+
+    # ---- input form: the device runs the generators too (p2g_wprog_load / p2g_prove_inputs) ---------
+    def load_witness_program(self, ctx, targets):
+        """Uploads the level-scheduled generator program for witnesses given by the values of `targets`
+        (the PartialWitness::set_target calls of the caller, fixed per program); returns the handle."""
+        self._program()
+        slots = np.array([self._slot(t) for t in targets], dtype=np.int32)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.p2g_wprog_load(ctx.handle, C.byref(self._wdesc), slots.ctypes.data, len(slots), C.byref(h)))
+        assert ctx.lib.p2g_wprog_ext_slots(h) == self.ext_slots
+        return h
+
+    def generate_slots_device(self, ctx, wprog, values):
+        """device twin of generate_slots_many: [count][len(targets)] input values -> [count][ext_slots]"""
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        out = np.empty((values.shape[0], self.ext_slots), dtype=np.uint64)
+        rc = ctx.lib.p2g_wprog_generate(ctx.handle, wprog, values.ctypes.data, values.shape[0], out.ctypes.data)
+        if rc in self._WERR:
+            raise ValueError(self._WERR[rc])
+        ctx.check(rc)
+        return out
+
+    def prove_inputs(self, values, wprog, ctx=None, circuit=None, wmap=None, public_inputs=None):
+        """input values -> proof: generators, full_witness and the prover all on the device"""
+        ctx = ctx or self.ctx
+        circuit = circuit or self._gpu_circuit
+        if wmap is None:
+            if getattr(self, "_wmap", None) is None:
+                self._wmap = self.load_wire_map(ctx, circuit)
+            wmap = self._wmap
+        words = self.proof_words
+        out = np.empty(words, dtype=np.uint64)
+        got = C.c_size_t()
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        pi = np.ascontiguousarray(public_inputs, dtype=np.uint64) if public_inputs is not None and len(public_inputs) else None
+        rc = ctx.lib.p2g_prove_inputs(ctx.handle, circuit, wmap, wprog, values.ctypes.data, pi.ctypes.data if pi is not None else None,
+                                      out.ctypes.data, words, C.byref(got))
+        if rc in self._WERR:
+            raise ValueError(self._WERR[rc])
+        ctx.check(rc)
+        return out[:got.value]
 
     def prove_slots(self, slots, ctx=None, circuit=None, wmap=None, public_inputs=None):
         """Slot vector -> proof; the wire matrix is gathered on the device (PartitionWitness::full_witness)."""

@@ -337,3 +337,57 @@ def test_circuit_load_error_paths_do_not_leak(gpu_ctx):
     assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d2), C.byref(h), None) == -2
     d3 = data.descriptor(); d3.degree_bits = 18
     assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d3), C.byref(h), None) == -2
+
+
+def test_device_witness_generation(gpu_ctx, oracle):
+    """p2g_wprog_load / p2g_wprog_generate / p2g_prove_inputs: the level-scheduled generator program on the
+    device gives the host generators' extended slot vector bit for bit (AES-GCM: arithmetic, lookup and
+    equality generators + multiplicities; Feistel: PoseidonGate generator), the proof from input values
+    equals the proof from the host-filled wire matrix, and generator failures come back as P2W_E_* codes."""
+    lib = gpu_ctx.lib
+    data, wires, tg = circuits.aes_gcm(13, True)
+    data.load(gpu_ctx)
+    targets = tg.input_targets()
+    wp = data.load_witness_program(gpu_ctx, targets)
+    assert lib.p2g_wprog_levels(wp) > 100
+    vals = circuits.gcm_inputs(tg, 11, 5)
+    host = data.generate_slots_many(targets, vals)
+    dev = data.generate_slots_device(gpu_ctx, wp, vals)
+    assert np.array_equal(dev, host)
+    oc = oracle_lib.OracleCircuit(oracle, data)
+    w = data.generate_witnesses(targets, vals[:1])[0]
+    p_host = data.prove_wires(w)
+    p_dev = data.prove_inputs(vals[0], wp)
+    assert np.array_equal(p_dev, p_host) and oc.verify(p_dev) == 0
+    bad = vals[:1].copy(); bad[0, -1] ^= 1                     # wrong tag byte: the computed tag disagrees
+    with pytest.raises(ValueError, match="set twice"):
+        data.generate_slots_device(gpu_ctx, wp, bad)
+    with pytest.raises(ValueError, match="set twice"):
+        data.prove_inputs(bad[0], wp)
+    bad = vals[:1].copy(); bad[0, 0] = 300                     # a "byte" outside the byte table
+    with pytest.raises(ValueError, match="lookup"):
+        data.generate_slots_device(gpu_ctx, wp, bad)
+    gpu_ctx.check(lib.p2g_wprog_free(gpu_ctx.handle, wp))
+    oc.free()
+    # PoseidonGate generator + preset outputs that are checked, not written
+    data, wires, (st, ks, out, state, keys, exp) = circuits.feistel_poseidon()
+    data.load(gpu_ctx)
+    targets = list(st) + [t for k in ks for t in k] + list(out)
+    v = np.array([list(state) + [x for k in keys for x in k] + list(exp)], dtype=np.uint64)
+    wp = data.load_witness_program(gpu_ctx, targets)
+    assert np.array_equal(data.generate_slots_device(gpu_ctx, wp, v), data.generate_slots_many(targets, v))
+    v[0, -1] = (int(v[0, -1]) + 1) % P
+    with pytest.raises(ValueError, match="set twice"):
+        data.generate_slots_device(gpu_ctx, wp, v)
+    gpu_ctx.check(lib.p2g_wprog_free(gpu_ctx.handle, wp))
+    # a program whose inputs are incomplete is refused at load (the host generators would stop with P2W_E_UNSET)
+    data, _, tg = circuits.aes_gcm(13, True)
+    h = C.c_void_p()
+    data._program()
+    slots = np.array([data._slot(t) for t in tg.input_targets()[:-20]], dtype=np.int32)
+    rc = lib.p2g_wprog_load(gpu_ctx.handle, C.byref(data._wdesc), slots.ctypes.data, len(slots), C.byref(h))
+    assert rc in (0, -2)          # without the ciphertext / tag inputs the program computes them instead of checking
+    if rc == 0:
+        lib.p2g_wprog_free(gpu_ctx.handle, h)
+    slots = slots[:10]            # without the plaintext the AES rounds read partitions nobody sets
+    assert lib.p2g_wprog_load(gpu_ctx.handle, C.byref(data._wdesc), slots.ctypes.data, len(slots), C.byref(h)) == -2

@@ -7,10 +7,10 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/plonky2_aes_b200/csrc
 obj=$(mktemp -d)
 mkdir -p $root/plonky2_aes_b200/variants
-for f in api ntt merkle prover; do
+for f in api ntt merkle prover witgen; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -c $src/$f.cu -o $obj/$f.o &
 done
 wait
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $root/plonky2_aes_b200/variants/libp2gpu_$name.so $obj/api.o $obj/ntt.o $obj/merkle.o $obj/prover.o -lcudart
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $root/plonky2_aes_b200/variants/libp2gpu_$name.so $obj/api.o $obj/ntt.o $obj/merkle.o $obj/prover.o $obj/witgen.o -lcudart
 rm -rf $obj
 echo built plonky2_aes_b200/variants/libp2gpu_$name.so
