@@ -185,6 +185,13 @@ uint32_t p2g_wprog_ext_slots(const p2g_wprog* p);   /* = p2w_ext_slots of the sa
 uint32_t p2g_wprog_levels(const p2g_wprog* p);      /* dependency depth of the program */
 /* `count` witnesses: input_vals [count][num_inputs] (host) -> extended slot vectors [count][ext_slots] (host) */
 int32_t p2g_wprog_generate(p2g_ctx* ctx, const p2g_wprog* p, const uint64_t* input_vals, uint32_t count, uint64_t* ext_out);
+/* batch form, witnesses stay in HBM: ext_dev [count][ext_slots] and flags_dev [count] are caller-owned DEVICE buffers;
+ * asynchronous (ordered on the context's stream).  flags: 0 ok, bit 0 non-canonical input, bit 1 lookup miss, bit 2
+ * conflict.  p2g_prove_slots_dev takes one such vector (device pointer) where p2g_prove_slots takes a host one. */
+int32_t p2g_wprog_generate_dev(p2g_ctx* ctx, const p2g_wprog* p, const uint64_t* input_vals_host, uint32_t count,
+                               uint64_t* ext_dev, int32_t* flags_dev);
+int32_t p2g_prove_slots_dev(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_dev,
+                            const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
 int32_t p2g_prove_inputs(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const p2g_wprog* prog,
                          const uint64_t* input_vals_host /*[num_inputs]*/, const uint64_t* public_inputs, uint64_t* proof_out,
                          size_t proof_cap_words, size_t* proof_words_out);

@@ -890,9 +890,9 @@ extern "C" int32_t p2g_prove_inputs(p2g_ctx* ctx, const p2g_circuit* c, const p2
     CU(cudaMemcpyAsync(flag, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st));
     CU(ctx_wait(ctx));
     if (*flag) {
-        ctx->err = (*flag & 4) ? "partition set twice with different values (P2W_E_CONFLICT)"
-                 : (*flag & 2) ? "lookup input not in table (P2W_E_LOOKUP)" : "non-canonical input value";
-        return (*flag & 4) ? -10 : (*flag & 2) ? -11 : P2G_E_BADARG;
+        ctx->err = (*flag & 2) ? "lookup input not in table (P2W_E_LOOKUP)"
+                 : (*flag & 4) ? "partition set twice with different values (P2W_E_CONFLICT)" : "non-canonical input value";
+        return (*flag & 2) ? -11 : (*flag & 4) ? -10 : P2G_E_BADARG;
     }
     return P2G_OK;
 }
@@ -903,6 +903,17 @@ extern "C" int32_t p2g_prove_slots(p2g_ctx* ctx, const p2g_circuit* c, const p2g
     CU(cudaSetDevice(ctx->device));
     gl_t* d_wires; int rc;
     if ((rc = wmap_gather(ctx, m, slots_host, &d_wires))) return rc;
+    rc = prove_impl(ctx, c, d_wires, false, public_inputs, proof_out, proof_cap_words, proof_words_out);
+    ctx_free(ctx, d_wires);
+    return rc;
+}
+extern "C" int32_t p2g_prove_slots_dev(p2g_ctx* ctx, const p2g_circuit* c, const p2g_wmap* m, const uint64_t* slots_dev,
+                                       const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {
+    if (!ctx || !c || !m || !slots_dev) return P2G_E_BADARG;
+    if (m->cells != ((size_t)c->cd.W << c->cd.logn)) { ctx->err = "wire map belongs to another circuit"; return P2G_E_BADARG; }
+    CU(cudaSetDevice(ctx->device));
+    gl_t* d_wires; int rc;
+    if ((rc = wmap_gather_dev(ctx, m, slots_dev, &d_wires))) return rc;
     rc = prove_impl(ctx, c, d_wires, false, public_inputs, proof_out, proof_cap_words, proof_words_out);
     ctx_free(ctx, d_wires);
     return rc;

@@ -30,10 +30,10 @@ enum { WG_CHECK0 = 0x80, WG_CHECK1 = 0x40 };   // output 0 / output 1 is already
 struct p2g_wprog {
     uint32_t num_slots, ext_total, ext_mult, ext_pos, num_ops, num_levels, num_inputs, num_luts, num_poseidon, lut_entries;
     uint32_t lookups_total;
-    uint8_t* d_kind; int32_t* d_s; gl_t* d_c; uint32_t* d_level_off;     // d_s: [5][num_ops], d_c: [2][num_ops]
+    struct WgOp* d_ops; uint32_t* d_level_off;                            // level-sorted packed records
     int32_t* d_in_slots;
     int32_t* d_key2entry;      // [num_luts][65536]: entry index of a key or -1
-    uint16_t* d_lut_out;       // output of every entry, all LUTs concatenated
+    int32_t* d_key2out;        // [num_luts][65536]: output of a key or -1 (LookupGenerator in one load)
     int32_t* d_lut_off;        // first entry of each LUT (num_luts + 1)
     int32_t* d_lookup_slots; int32_t* d_lookup_off; int32_t* d_lookup_padding;
     int32_t* d_poseidon_rows;
@@ -41,10 +41,13 @@ struct p2g_wprog {
     uint32_t err_cap;
 };
 
+// one generator: 48 bytes, read as three 16-byte words.  kf = kind | WG_CHECK flags; s[4] = outputs / inputs as in
+// p2w_program_desc.ops[1..4]; lut = ops[5]
+struct __align__(16) WgOp { uint32_t kf; int32_t s[4]; int32_t lut; uint32_t pad[2]; gl_t c[2]; };
 struct WgProg {
     uint32_t num_slots, ext_total, ext_mult, ext_pos, num_ops, num_levels, num_inputs, num_luts, num_poseidon;
-    const uint8_t* kind; const int32_t* s; const gl_t* c; const uint32_t* level_off;
-    const int32_t* in_slots; const int32_t* key2entry; const uint16_t* lut_out; const int32_t* lut_off;
+    const WgOp* ops; const uint32_t* level_off;
+    const int32_t* in_slots; const int32_t* key2entry; const int32_t* key2out; const int32_t* lut_off;
     const int32_t* lookup_slots; const int32_t* lookup_off; const int32_t* lookup_padding; const int32_t* poseidon_rows;
 };
 
@@ -112,31 +115,41 @@ witgen_kernel(WgProg P, const gl_t* __restrict__ in_vals, uint32_t count, gl_t* 
         ext[P.in_slots[i]] = v;
     }
     __syncwarp();
-    const uint32_t K = P.num_ops;
+    // The record of the op this lane runs in the NEXT level is fetched before the current level's values are
+    // awaited: a level then costs the round trips of its operand loads only (levels hold ~16 independent ops,
+    // the chain of 6 801 levels is what takes the time).
+    uint32_t k0 = P.level_off[0], k1 = P.num_levels ? P.level_off[1] : 0;
+    WgOp nxt;
+    if (k0 + lane < k1) nxt = P.ops[k0 + lane];
 #pragma unroll 1
     for (uint32_t L = 0; L < P.num_levels; L++) {
-        const uint32_t k0 = P.level_off[L], k1 = P.level_off[L + 1];
+        const uint32_t c0 = k0, c1 = k1;
+        WgOp op = nxt;
+        if (L + 1 < P.num_levels) {
+            k0 = c1; k1 = P.level_off[L + 2];
+            if (k0 + lane < k1) nxt = P.ops[k0 + lane];
+        }
 #pragma unroll 1
-        for (uint32_t k = k0 + lane; k < k1; k += 32) {
-            const uint32_t kf = P.kind[k], kind = kf & 7;
-            const int32_t s0 = P.s[k];
+        for (uint32_t k = c0 + lane; k < c1; k += 32) {
+            if (k != c0 + lane) op = P.ops[k];             // levels wider than a warp: the rest is read here
+            const uint32_t kf = op.kf, kind = kf & 7;
+            const int32_t s0 = op.s[0];
             gl_t r0 = 0, r1 = 0;
             bool two = false;
             if (kind == P2W_OP_ARITH) {
-                const gl_t a = ext[P.s[K + k]], b = ext[P.s[2 * K + k]], c = ext[P.s[3 * K + k]];
-                r0 = gl_add(gl_mul(P.c[k], gl_mul(a, b)), gl_mul(P.c[K + k], c));
+                const gl_t a = ext[op.s[1]], b = ext[op.s[2]], c = ext[op.s[3]];
+                r0 = gl_add(gl_mul(op.c[0], gl_mul(a, b)), gl_mul(op.c[1], c));
             } else if (kind == P2W_OP_LOOKUP) {
-                const gl_t x = ext[P.s[K + k]];
-                const int32_t lut = P.s[4 * K + k];
-                const int32_t e = x <= 0xFFFF ? P.key2entry[(size_t)lut * 65536 + (uint32_t)x] : -1;
-                if (e < 0) bad |= 2; else r0 = P.lut_out[P.lut_off[lut] + e];
+                const gl_t x = ext[op.s[1]];
+                const int32_t o = x <= 0xFFFF ? P.key2out[(size_t)op.lut * 65536 + (uint32_t)x] : -1;
+                if (o < 0) bad |= 2; else r0 = (gl_t)o;
             } else if (kind == P2W_OP_EQ) {
-                const gl_t diff = gl_sub(ext[P.s[2 * K + k]], ext[P.s[3 * K + k]]);
+                const gl_t diff = gl_sub(ext[op.s[2]], ext[op.s[3]]);
                 r0 = diff == 0 ? 1 : 0;
                 r1 = diff == 0 ? 0 : gl_inv(diff);
                 two = true;
             } else if (kind == P2W_OP_CONST) {
-                r0 = P.c[k];
+                r0 = op.c[0];
             } else {                                       // P2W_OP_POSEIDON: s0 = row index
                 const int32_t* pr = P.poseidon_rows + (size_t)25 * s0;
                 gl_t in[12], trace[123];
@@ -151,7 +164,7 @@ witgen_kernel(WgProg P, const gl_t* __restrict__ in_vals, uint32_t count, gl_t* 
                 continue;
             }
             if (kf & WG_CHECK0) { if (ext[s0] != r0) bad |= 4; } else ext[s0] = r0;
-            if (two) { const int32_t s1 = P.s[K + k]; if (kf & WG_CHECK1) { if (ext[s1] != r1) bad |= 4; } else ext[s1] = r1; }
+            if (two) { const int32_t s1 = op.s[1]; if (kf & WG_CHECK1) { if (ext[s1] != r1) bad |= 4; } else ext[s1] = r1; }
         }
         __syncwarp();
     }
@@ -180,8 +193,8 @@ extern "C" int32_t p2g_wprog_free(p2g_ctx* ctx, p2g_wprog* p) {
     if (!ctx || !p) return P2G_E_BADARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
-    cudaFree(p->d_kind); cudaFree(p->d_s); cudaFree(p->d_c); cudaFree(p->d_level_off); cudaFree(p->d_in_slots);
-    cudaFree(p->d_key2entry); cudaFree(p->d_lut_out); cudaFree(p->d_lut_off); cudaFree(p->d_lookup_slots);
+    cudaFree(p->d_ops); cudaFree(p->d_level_off); cudaFree(p->d_in_slots);
+    cudaFree(p->d_key2entry); cudaFree(p->d_key2out); cudaFree(p->d_lut_off); cudaFree(p->d_lookup_slots);
     cudaFree(p->d_lookup_off); cudaFree(p->d_lookup_padding); cudaFree(p->d_poseidon_rows); cudaFree(p->d_err);
     delete p;
     return P2G_OK;
@@ -256,23 +269,26 @@ extern "C" int32_t p2g_wprog_load(p2g_ctx* ctx, const p2w_program_desc* d, const
     std::vector<uint32_t> offs((size_t)max_level + 1);
     for (int32_t l = 1; l <= max_level; l++) offs[l - 1] = level_off[l];
     offs[max_level] = K;
-    std::vector<uint8_t> kind_s(K); std::vector<int32_t> s_s((size_t)5 * K); std::vector<gl_t> c_s((size_t)2 * K);
+    std::vector<WgOp> ops_s(K);
     for (uint32_t j = 0; j < K; j++) {
         const uint32_t k = order[j];
-        kind_s[j] = kind[k];
-        for (int f = 0; f < 5; f++) s_s[(size_t)f * K + j] = d->ops[(size_t)6 * k + 1 + f];
-        c_s[j] = d->op_consts[(size_t)2 * k]; c_s[(size_t)K + j] = d->op_consts[(size_t)2 * k + 1];
-        if (c_s[j] >= GL_P || c_s[(size_t)K + j] >= GL_P) { ctx->err = "non-canonical op constant"; return P2G_E_BADARG; }
+        WgOp& o = ops_s[j];
+        memset(&o, 0, sizeof(o));
+        o.kf = kind[k];
+        for (int f = 0; f < 4; f++) o.s[f] = d->ops[(size_t)6 * k + 1 + f];
+        o.lut = d->ops[(size_t)6 * k + 5];
+        o.c[0] = d->op_consts[(size_t)2 * k]; o.c[1] = d->op_consts[(size_t)2 * k + 1];
+        if (o.c[0] >= GL_P || o.c[1] >= GL_P) { ctx->err = "non-canonical op constant"; return P2G_E_BADARG; }
     }
     // ---- lookup tables ----
-    std::vector<int32_t> key2entry((size_t)d->num_luts * 65536, -1), lut_off(d->num_luts + 1, 0), lookup_off(d->num_luts + 1, 0);
-    std::vector<uint16_t> lut_out(lut_entries);
+    std::vector<int32_t> key2entry((size_t)d->num_luts * 65536, -1), key2out((size_t)d->num_luts * 65536, -1),
+        lut_off(d->num_luts + 1, 0), lookup_off(d->num_luts + 1, 0);
     for (uint32_t l = 0; l < d->num_luts; l++) {
         lut_off[l + 1] = lut_off[l] + d->lut_lens[l];
         lookup_off[l + 1] = lookup_off[l] + d->lookup_counts[l];
         for (int32_t e = d->lut_lens[l] - 1; e >= 0; e--) {          // first occurrence of a key wins (as on the host)
             key2entry[(size_t)l * 65536 + d->lut_data[2 * ((size_t)lut_off[l] + e)]] = e;
-            lut_out[(size_t)lut_off[l] + e] = d->lut_data[2 * ((size_t)lut_off[l] + e) + 1];
+            key2out[(size_t)l * 65536 + d->lut_data[2 * ((size_t)lut_off[l] + e)]] = d->lut_data[2 * ((size_t)lut_off[l] + e) + 1];
         }
     }
     p2g_wprog* p = new p2g_wprog();
@@ -283,8 +299,9 @@ extern "C" int32_t p2g_wprog_load(p2g_ctx* ctx, const p2w_program_desc* d, const
     std::vector<int32_t> in_s(input_slots, input_slots + num_inputs), lk(d->lookup_slots, d->lookup_slots + lookups_total),
         pad(d->lookup_padding, d->lookup_padding + d->num_luts),
         prow(d->num_poseidon ? d->poseidon_rows : nullptr, d->num_poseidon ? d->poseidon_rows + (size_t)25 * d->num_poseidon : nullptr);
-    bool ok = up(&p->d_kind, kind_s, ctx->st) && up(&p->d_s, s_s, ctx->st) && up(&p->d_c, c_s, ctx->st) && up(&p->d_level_off, offs, ctx->st) &&
-              up(&p->d_in_slots, in_s, ctx->st) && up(&p->d_key2entry, key2entry, ctx->st) && up(&p->d_lut_out, lut_out, ctx->st) &&
+    offs.push_back(K);            // the kernel reads level_off[L + 2] while it prefetches
+    bool ok = up(&p->d_ops, ops_s, ctx->st) && up(&p->d_level_off, offs, ctx->st) &&
+              up(&p->d_in_slots, in_s, ctx->st) && up(&p->d_key2entry, key2entry, ctx->st) && up(&p->d_key2out, key2out, ctx->st) &&
               up(&p->d_lut_off, lut_off, ctx->st) && up(&p->d_lookup_slots, lk, ctx->st) && up(&p->d_lookup_off, lookup_off, ctx->st) &&
               up(&p->d_lookup_padding, pad, ctx->st) && up(&p->d_poseidon_rows, prow, ctx->st);
     if (ok) ok = ctx_wait(ctx) == cudaSuccess;          // the host vectors die at the end of this function
@@ -303,8 +320,8 @@ int wprog_launch(p2g_ctx* ctx, const p2g_wprog* p, const gl_t* d_in, uint32_t co
     WgProg P;
     P.num_slots = p->num_slots; P.ext_total = p->ext_total; P.ext_mult = p->ext_mult; P.ext_pos = p->ext_pos; P.num_ops = p->num_ops;
     P.num_levels = p->num_levels; P.num_inputs = p->num_inputs; P.num_luts = p->num_luts; P.num_poseidon = p->num_poseidon;
-    P.kind = p->d_kind; P.s = p->d_s; P.c = p->d_c; P.level_off = p->d_level_off; P.in_slots = p->d_in_slots;
-    P.key2entry = p->d_key2entry; P.lut_out = p->d_lut_out; P.lut_off = p->d_lut_off; P.lookup_slots = p->d_lookup_slots;
+    P.ops = p->d_ops; P.level_off = p->d_level_off; P.in_slots = p->d_in_slots;
+    P.key2entry = p->d_key2entry; P.key2out = p->d_key2out; P.lut_off = p->d_lut_off; P.lookup_slots = p->d_lookup_slots;
     P.lookup_off = p->d_lookup_off; P.lookup_padding = p->d_lookup_padding; P.poseidon_rows = p->d_poseidon_rows;
     // one warp per witness, one warp per block: the witnesses of a batch spread over the SMs
     witgen_kernel<<<count, 32, 0, ctx->st>>>(P, d_in, count, d_ext, d_err);
@@ -333,9 +350,27 @@ extern "C" int32_t p2g_wprog_generate(p2g_ctx* ctx, const p2g_wprog* p, const ui
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return P2G_E_CUDA; }
     for (uint32_t i = 0; i < count; i++)
         if (err[i]) {
-            ctx->err = (err[i] & 4) ? "partition set twice with different values (P2W_E_CONFLICT)"
-                     : (err[i] & 2) ? "lookup input not in table (P2W_E_LOOKUP)" : "non-canonical input value";
-            return (err[i] & 4) ? P2W_E_CONFLICT : (err[i] & 2) ? P2W_E_LOOKUP : P2G_E_BADARG;
+            // a value outside its table usually also derails later generators: report the lookup first
+            ctx->err = (err[i] & 2) ? "lookup input not in table (P2W_E_LOOKUP)"
+                     : (err[i] & 4) ? "partition set twice with different values (P2W_E_CONFLICT)" : "non-canonical input value";
+            return (err[i] & 2) ? P2W_E_LOOKUP : (err[i] & 4) ? P2W_E_CONFLICT : P2G_E_BADARG;
         }
     return P2G_OK;
+}
+
+// Batch form for pipelines that keep the witnesses in HBM: `count` witnesses are generated into caller-owned device
+// memory (ext_dev: [count][ext_slots] words, flags_dev: [count] int32, 0 = ok or a P2W_E-style bit set: 1 non-canonical
+// input, 2 lookup, 4 conflict); nothing is waited for -- the work is ordered on the context's stream, and
+// p2g_prove_slots_dev on the SAME context (or after p2g_ctx_sync) consumes the vectors.
+extern "C" int32_t p2g_wprog_generate_dev(p2g_ctx* ctx, const p2g_wprog* p, const uint64_t* input_vals_host, uint32_t count,
+                                          uint64_t* ext_dev, int32_t* flags_dev) {
+    if (!ctx || !p || !input_vals_host || !ext_dev || !flags_dev || !count) return P2G_E_BADARG;
+    CU(cudaSetDevice(ctx->device));
+    gl_t* d_in; int rc;
+    if ((rc = ctx_alloc(ctx, &d_in, (size_t)count * p->num_inputs))) return rc;
+    cudaError_t e = cudaMemcpyAsync(d_in, input_vals_host, (size_t)count * p->num_inputs * sizeof(gl_t), cudaMemcpyHostToDevice, ctx->st);
+    if (e == cudaSuccess) rc = wprog_launch(ctx, p, d_in, count, ext_dev, flags_dev);
+    ctx_free(ctx, d_in);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return P2G_E_CUDA; }
+    return rc;
 }

@@ -88,6 +88,8 @@ SIGNATURES = {
     "p2g_wprog_ext_slots": (C.c_uint32, [_vp]),
     "p2g_wprog_levels": (C.c_uint32, [_vp]),
     "p2g_wprog_generate": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp]),
+    "p2g_wprog_generate_dev": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "p2g_prove_slots_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2g_prove_inputs": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2g_proof_bytes_len": (C.c_size_t, [_vp]),
     "p2g_proof_to_bytes": (C.c_int32, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -1,129 +1,142 @@
-//! Raw bindings of include/p2gpu.h — one item per C declaration, same order.
-//! The safe wrapper (`GpuProver`) below is what the patched
-//! `plonky2::plonk::prover::prove_with_partition_witness` calls (rust/plonky2-patch/prover.rs).
+//! FFI crate for libp2gpu.so — the B200 backend of plonky2's `prove()` hot path (include/p2gpu.h).
+//!
+//! `ffi` holds one `extern "C"` item per C declaration, GENERATED from the header
+//! (tools/gen_rust_bindings.py; tests/test_abi.py fails when the two drift); `types` the `#[repr(C)]`
+//! structs; below, the safe layer the patched `plonky2::plonk::prover` uses
+//! (rust/plonky2-patch/src/gpu_prover.rs).
+//!
+//! NOT compiled in the build image (no cargo / rustc there).  Link: `P2GPU_LIB_DIR=<repo>/plonky2_aes_b200`.
 #![allow(non_camel_case_types)]
+pub mod ffi;
+pub mod types;
+
 use std::ffi::CStr;
-use std::os::raw::{c_char, c_void};
+use std::ptr;
 
-#[repr(C)] pub struct p2g_ctx { _p: [u8; 0] }
-#[repr(C)] pub struct p2g_batch { _p: [u8; 0] }
-#[repr(C)] pub struct p2g_wmap { _p: [u8; 0] }
-#[repr(C)] pub struct p2g_circuit { _p: [u8; 0] }
-
-pub const P2G_OK: i32 = 0;
-pub const P2G_E_CUDA: i32 = -1;
-pub const P2G_E_BADARG: i32 = -2;
-pub const P2G_E_UNSAT: i32 = -3;
-pub const P2G_E_POW: i32 = -4;
-
-pub const P2G_GATE_NOOP: i32 = 0;
-pub const P2G_GATE_CONSTANT: i32 = 1;
-pub const P2G_GATE_PUBLIC_INPUT: i32 = 2;
-pub const P2G_GATE_ARITHMETIC: i32 = 3;
-pub const P2G_GATE_LOOKUP: i32 = 4;
-pub const P2G_GATE_LOOKUP_TABLE: i32 = 5;
-pub const P2G_GATE_POSEIDON: i32 = 6;
-
-#[repr(C)] #[derive(Clone, Copy, Debug)]
-pub struct p2g_gate {
-    pub kind: i32, pub selector_index: i32, pub group_start: i32, pub group_end: i32,
-    pub num_constraints: i32, pub param0: i32,
-}
-
-#[repr(C)]
-pub struct p2g_circuit_desc {
-    pub degree_bits: i32,
-    pub num_wires: i32, pub num_routed_wires: i32, pub num_constants: i32,
-    pub num_challenges: i32, pub quotient_degree_factor: i32,
-    pub rate_bits: i32, pub cap_height: i32, pub pow_bits: i32, pub num_query_rounds: i32,
-    pub num_reduction_arity_bits: i32, pub reduction_arity_bits: [i32; 16],
-    pub num_selectors: i32, pub num_lookup_selectors: i32,
-    pub num_gates: i32, pub gates: *const p2g_gate,
-    pub num_gate_constraints: i32,
-    pub num_partial_products: i32,
-    pub num_luts: i32,
-    pub lut_lens: *const i32, pub lut_data: *const u16, pub lookup_rows: *const i32,
-    pub num_public_inputs: i32,
-    pub k_is: *const u64, pub constants_sigmas: *const u64,
-    pub circuit_digest: [u64; 4],
-}
-
-#[repr(C)] #[derive(Default, Clone, Copy, Debug)]
-pub struct p2g_timings {
-    pub h2d: f32, pub wires_commit: f32, pub zs_build: f32, pub zs_commit: f32, pub quotient: f32,
-    pub quotient_commit: f32, pub openings: f32, pub fri_combine: f32, pub fri_commit: f32, pub pow: f32,
-    pub queries: f32, pub total: f32,
-}
-
-extern "C" {
-    pub fn p2g_version() -> i32;
-    pub fn p2g_ctx_create(device: i32, out: *mut *mut p2g_ctx) -> i32;
-    pub fn p2g_ctx_destroy(ctx: *mut p2g_ctx);
-    pub fn p2g_last_error(ctx: *mut p2g_ctx) -> *const c_char;
-    pub fn p2g_ctx_sync(ctx: *mut p2g_ctx) -> i32;
-    pub fn p2g_ctx_stream(ctx: *mut p2g_ctx) -> *mut c_void;
-    pub fn p2g_commit_from_values(ctx: *mut p2g_ctx, cols: *const u64, ncols: u32, log_n: u32, rate_bits: u32,
-                                  cap_height: u32, out: *mut *mut p2g_batch, cap_out: *mut u64) -> i32;
-    pub fn p2g_commit_from_coeffs(ctx: *mut p2g_ctx, cols: *const u64, ncols: u32, log_n: u32, rate_bits: u32,
-                                  cap_height: u32, out: *mut *mut p2g_batch, cap_out: *mut u64) -> i32;
-    pub fn p2g_batch_free(ctx: *mut p2g_ctx, b: *mut p2g_batch) -> i32;
-    pub fn p2g_batch_open_leaf(ctx: *mut p2g_ctx, b: *const p2g_batch, leaf: u64, row_out: *mut u64, siblings_out: *mut u64) -> i32;
-    pub fn p2g_circuit_load(ctx: *mut p2g_ctx, desc: *const p2g_circuit_desc, out: *mut *mut p2g_circuit, cap_out: *mut u64) -> i32;
-    pub fn p2g_circuit_free(ctx: *mut p2g_ctx, c: *mut p2g_circuit) -> i32;
-    pub fn p2g_proof_words(c: *const p2g_circuit) -> usize;
-    pub fn p2g_prove(ctx: *mut p2g_ctx, c: *const p2g_circuit, wires: *const u64, public_inputs: *const u64,
-                     proof_out: *mut u64, cap_words: usize, words_out: *mut usize) -> i32;
-    pub fn p2g_prove_dev(ctx: *mut p2g_ctx, c: *const p2g_circuit, wires_dev: *const u64, public_inputs: *const u64,
-                         proof_out: *mut u64, cap_words: usize, words_out: *mut usize) -> i32;
-    // device-side PartitionWitness::full_witness: wire_map = representative_map flattened to [col*n + row]
-    pub fn p2g_wmap_load(ctx: *mut p2g_ctx, c: *const p2g_circuit, wire_map: *const i32, num_slots: u32,
-                         fixed_pos: *const i64, fixed_val: *const u64, num_fixed: u32, out: *mut *mut p2g_wmap) -> i32;
-    pub fn p2g_wmap_free(ctx: *mut p2g_ctx, m: *mut p2g_wmap) -> i32;
-    pub fn p2g_prove_slots(ctx: *mut p2g_ctx, c: *const p2g_circuit, m: *const p2g_wmap, slots: *const u64,
-                           public_inputs: *const u64, proof_out: *mut u64, cap_words: usize, words_out: *mut usize) -> i32;
-    pub fn p2g_set_timing(ctx: *mut p2g_ctx, enabled: i32) -> i32;
-    pub fn p2g_last_timings(ctx: *mut p2g_ctx, out: *mut p2g_timings) -> i32;
-}
-
-/// One GPU context + one loaded circuit.  `!Sync`: a context is used by one host thread at a time
-/// (spawn one `GpuProver` per in-flight proof, exactly like `host/sharding.py::BatchProver`).
-pub struct GpuProver { ctx: *mut p2g_ctx, circuit: *mut p2g_circuit }
-unsafe impl Send for GpuProver {}
+pub use ffi::*;
+pub use types::*;
 
 #[derive(Debug)]
-pub enum GpuError { Unsatisfied, Backend(i32, String) }
+pub enum GpuError {
+    /// witness generation found a preset partition that disagrees with the generated value
+    /// (`prove(..).is_err()` of aes-gcm/src/circuit_aes.rs:403-405)
+    WitnessConflict,
+    Backend(i32, String),
+}
+impl std::fmt::Display for GpuError {
+    fn fmt(&self, f: &mut std::fmt::Formatter<'_>) -> std::fmt::Result {
+        match self {
+            GpuError::WitnessConflict => write!(f, "partition set twice with different values"),
+            GpuError::Backend(c, m) => write!(f, "p2gpu error {c}: {m}"),
+        }
+    }
+}
+impl std::error::Error for GpuError {}
 
-impl GpuProver {
-    /// # Safety: every pointer inside `desc` must be valid for the duration of the call.
-    pub unsafe fn load(device: i32, desc: &p2g_circuit_desc, expected_cap: &[u64]) -> Result<Self, GpuError> {
-        let mut ctx = std::ptr::null_mut();
-        let rc = p2g_ctx_create(device, &mut ctx);
-        if rc != P2G_OK { return Err(GpuError::Backend(rc, "no CUDA device".into())); }
-        let mut circuit = std::ptr::null_mut();
-        let mut cap = vec![0u64; expected_cap.len()];
-        let rc = p2g_circuit_load(ctx, desc, &mut circuit, cap.as_mut_ptr());
-        if rc != P2G_OK { let e = Self::err(ctx, rc); p2g_ctx_destroy(ctx); return Err(e); }
-        // the GPU commitment of (constants, sigmas) must equal VerifierOnlyCircuitData::constants_sigmas_cap
-        assert_eq!(cap, expected_cap, "constants_sigmas cap mismatch between CPU build() and GPU load");
-        Ok(Self { ctx, circuit })
+/// One context = one CUDA stream + memory pool on one device.  `!Sync`: used by one host thread at a time;
+/// keep one per in-flight proof (several proofs in flight hide each other's Fiat-Shamir round trips).
+pub struct GpuContext { raw: *mut p2g_ctx, pub device: i32 }
+unsafe impl Send for GpuContext {}
+impl GpuContext {
+    pub fn new(device: i32) -> Result<Self, GpuError> {
+        let mut raw = ptr::null_mut();
+        let rc = unsafe { p2g_ctx_create(device, &mut raw) };
+        if rc != P2G_OK { return Err(GpuError::Backend(rc, "p2g_ctx_create: no usable CUDA device (there is no CPU fallback)".into())); }
+        Ok(Self { raw, device })
     }
-    unsafe fn err(ctx: *mut p2g_ctx, rc: i32) -> GpuError {
-        if rc == P2G_E_UNSAT { return GpuError::Unsatisfied; }
-        GpuError::Backend(rc, CStr::from_ptr(p2g_last_error(ctx)).to_string_lossy().into_owned())
+    fn err(&self, rc: i32) -> GpuError {
+        if rc == P2W_E_CONFLICT { return GpuError::WitnessConflict; }
+        let msg = unsafe { CStr::from_ptr(p2g_last_error(self.raw)) }.to_string_lossy().into_owned();
+        GpuError::Backend(rc, msg)
     }
-    /// `wires`: num_wires columns of `degree` canonical u64, column-major.  Returns the flat proof words.
-    pub fn prove(&mut self, wires: &[u64], public_inputs: &[u64]) -> Result<Vec<u64>, GpuError> {
+    pub fn raw(&self) -> *mut p2g_ctx { self.raw }
+}
+impl Drop for GpuContext { fn drop(&mut self) { unsafe { p2g_ctx_destroy(self.raw) } } }
+
+/// Owned host copy of everything `p2g_circuit_desc` points to (the descriptor borrows from it).
+#[derive(Clone, Default)]
+pub struct CircuitDescOwned {
+    pub degree_bits: i32, pub num_wires: i32, pub num_routed_wires: i32, pub num_constants: i32,
+    pub num_challenges: i32, pub quotient_degree_factor: i32, pub rate_bits: i32, pub cap_height: i32,
+    pub pow_bits: i32, pub num_query_rounds: i32, pub reduction_arity_bits: Vec<i32>,
+    pub num_selectors: i32, pub num_lookup_selectors: i32, pub gates: Vec<p2g_gate>,
+    pub num_gate_constraints: i32, pub num_partial_products: i32,
+    pub lut_lens: Vec<i32>, pub lut_data: Vec<u16>, pub lookup_rows: Vec<i32>,
+    pub num_public_inputs: i32, pub k_is: Vec<u64>,
+    /// [(selectors + lookup selectors + constants + routed wires)][n] VALUES on the subgroup, column-major
+    pub constants_sigmas: Vec<u64>,
+    pub circuit_digest: [u64; 4],
+}
+impl CircuitDescOwned {
+    pub fn as_desc(&self) -> p2g_circuit_desc {
+        let mut rab = [0i32; 16];
+        rab[..self.reduction_arity_bits.len()].copy_from_slice(&self.reduction_arity_bits);
+        p2g_circuit_desc {
+            degree_bits: self.degree_bits, num_wires: self.num_wires, num_routed_wires: self.num_routed_wires,
+            num_constants: self.num_constants, num_challenges: self.num_challenges,
+            quotient_degree_factor: self.quotient_degree_factor, rate_bits: self.rate_bits, cap_height: self.cap_height,
+            pow_bits: self.pow_bits, num_query_rounds: self.num_query_rounds,
+            num_reduction_arity_bits: self.reduction_arity_bits.len() as i32, reduction_arity_bits: rab,
+            num_selectors: self.num_selectors, num_lookup_selectors: self.num_lookup_selectors,
+            num_gates: self.gates.len() as i32, gates: self.gates.as_ptr(),
+            num_gate_constraints: self.num_gate_constraints, num_partial_products: self.num_partial_products,
+            num_luts: self.lut_lens.len() as i32, lut_lens: self.lut_lens.as_ptr(), lut_data: self.lut_data.as_ptr(),
+            lookup_rows: self.lookup_rows.as_ptr(), num_public_inputs: self.num_public_inputs,
+            k_is: self.k_is.as_ptr(), constants_sigmas: self.constants_sigmas.as_ptr(), circuit_digest: self.circuit_digest,
+        }
+    }
+    /// bytes of `ProofWithPublicInputs::to_bytes` for the flat proof words (host-only code of the library)
+    pub fn proof_words_to_bytes(&self, words: &[u64]) -> Result<Vec<u8>, GpuError> {
+        let d = self.as_desc();
         unsafe {
-            let cap = p2g_proof_words(self.circuit);
-            let mut out = vec![0u64; cap];
-            let mut n = 0usize;
-            let rc = p2g_prove(self.ctx, self.circuit, wires.as_ptr(), public_inputs.as_ptr(), out.as_mut_ptr(), cap, &mut n);
-            if rc != P2G_OK { return Err(Self::err(self.ctx, rc)); }
-            out.truncate(n);
+            let cap = p2g_proof_bytes_len(&d);
+            let mut out = vec![0u8; cap];
+            let mut len = 0usize;
+            let rc = p2g_proof_to_bytes(&d, words.as_ptr(), words.len(), out.as_mut_ptr(), cap, &mut len);
+            if rc != P2G_OK { return Err(GpuError::Backend(rc, "p2g_proof_to_bytes".into())); }
+            out.truncate(len);
             Ok(out)
         }
     }
 }
-impl Drop for GpuProver {
-    fn drop(&mut self) { unsafe { p2g_circuit_free(self.ctx, self.circuit); p2g_ctx_destroy(self.ctx); } }
+
+/// The prover data of one `CircuitData` resident on one device (preprocessed commitment, domain tables).
+pub struct GpuCircuit { raw: *mut p2g_circuit, ctx: *mut p2g_ctx, pub desc: CircuitDescOwned }
+unsafe impl Send for GpuCircuit {}
+impl GpuCircuit {
+    /// `expected_cap`: `VerifierOnlyCircuitData::constants_sigmas_cap` flattened; the GPU commitment must equal it.
+    pub fn load(ctx: &GpuContext, desc: CircuitDescOwned, expected_cap: &[u64]) -> Result<Self, GpuError> {
+        let d = desc.as_desc();
+        let mut raw = ptr::null_mut();
+        let mut cap = vec![0u64; expected_cap.len()];
+        let rc = unsafe { p2g_circuit_load(ctx.raw, &d, &mut raw, cap.as_mut_ptr()) };
+        if rc != P2G_OK { return Err(ctx.err(rc)); }
+        if cap != expected_cap {
+            unsafe { p2g_circuit_free(ctx.raw, raw) };
+            return Err(GpuError::Backend(P2G_E_BADARG, "constants_sigmas cap differs between build() and the device".into()));
+        }
+        Ok(Self { raw, ctx: ctx.raw, desc })
+    }
+    /// `wires`: num_wires columns of n canonical u64, column-major (`MatrixWitness::wire_values`).
+    /// Returns the flat proof words.
+    pub fn prove(&self, ctx: &GpuContext, wires: &[u64], public_inputs: &[u64]) -> Result<Vec<u64>, GpuError> {
+        assert!(ctx.raw == self.ctx, "a circuit is bound to the context it was loaded on");
+        unsafe {
+            let cap = p2g_proof_words(self.raw);
+            let mut out = vec![0u64; cap];
+            let mut n = 0usize;
+            let pi = if public_inputs.is_empty() { ptr::null() } else { public_inputs.as_ptr() };
+            let rc = p2g_prove(ctx.raw, self.raw, wires.as_ptr(), pi, out.as_mut_ptr(), cap, &mut n);
+            if rc != P2G_OK { return Err(ctx.err(rc)); }
+            out.truncate(n);
+            Ok(out)
+        }
+    }
+    /// Proof as upstream bytes: `ProofWithPublicInputs::from_bytes(bytes, common_data)` finishes the job.
+    pub fn prove_bytes(&self, ctx: &GpuContext, wires: &[u64], public_inputs: &[u64]) -> Result<Vec<u8>, GpuError> {
+        let words = self.prove(ctx, wires, public_inputs)?;
+        self.desc.proof_words_to_bytes(&words)
+    }
+    pub fn raw(&self) -> *mut p2g_circuit { self.raw }
 }
+impl Drop for GpuCircuit { fn drop(&mut self) { unsafe { p2g_circuit_free(self.ctx, self.raw); } } }

@@ -359,6 +359,16 @@ def test_device_witness_generation(gpu_ctx, oracle):
     p_host = data.prove_wires(w)
     p_dev = data.prove_inputs(vals[0], wp)
     assert np.array_equal(p_dev, p_host) and oc.verify(p_dev) == 0
+    # batch form with the witnesses kept in HBM (p2g_wprog_generate_dev -> p2g_prove_slots_dev)
+    import torch
+    ext_dev = torch.empty((5, data.ext_slots), dtype=torch.int64, device="cuda")
+    flags = torch.ones(5, dtype=torch.int32, device="cuda")
+    gpu_ctx.check(lib.p2g_wprog_generate_dev(gpu_ctx.handle, wp, np.ascontiguousarray(vals).ctypes.data, 5, ext_dev.data_ptr(), flags.data_ptr()))
+    words, got = np.empty(data.proof_words, dtype=np.uint64), C.c_size_t()
+    gpu_ctx.check(lib.p2g_prove_slots_dev(gpu_ctx.handle, data._gpu_circuit, data._wmap, ext_dev[0].data_ptr(), None, words.ctypes.data,
+                                          words.size, C.byref(got)))
+    assert np.array_equal(words, p_host) and int(flags.cpu().abs().sum()) == 0
+    assert np.array_equal(ext_dev.cpu().numpy().view(np.uint64), host)
     bad = vals[:1].copy(); bad[0, -1] ^= 1                     # wrong tag byte: the computed tag disagrees
     with pytest.raises(ValueError, match="set twice"):
         data.generate_slots_device(gpu_ctx, wp, bad)
