@@ -137,7 +137,17 @@ __device__ __forceinline__ gl_t gl_fold5(uint32_t l0, uint32_t l1, uint32_t h0, 
 }
 __device__ __forceinline__ gl_t gl_fold4(uint32_t l0, uint32_t l1, uint32_t h0, uint32_t h1) { return gl_fold5(l0, l1, h0, h1, 0); }
 // 128-bit product of two u64 as four 32-bit words
+// P2G_PMUL_V 1: the product is left to the compiler -- ptxas fuses mul.lo.u64 + mul.hi.u64 into four IMAD.WIDE whose
+// 64-bit addend and carry (IMAD.WIDE.U32.X) absorb the partial-product additions: 7 instructions instead of 4 + 6.
+#ifndef P2G_PMUL_V
+#define P2G_PMUL_V 1
+#endif
 __device__ __forceinline__ void pmul128(gl_t a, gl_t b, uint32_t& l0, uint32_t& l1, uint32_t& h0, uint32_t& h1) {
+#if P2G_PMUL_V == 1
+    const unsigned __int128 p = (unsigned __int128)a * b;
+    gl_unpack((uint64_t)p, l0, l1); gl_unpack((uint64_t)(p >> 64), h0, h1);
+    return;
+#endif
     uint32_t a0, a1, b0, b1; gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
     uint32_t c0, m1l, m1h, m2l, m2h, p11l, p11h;
     gl_unpack(gl_mulw(a0, b0), l0, c0); gl_unpack(gl_mulw(a0, b1), m1l, m1h);

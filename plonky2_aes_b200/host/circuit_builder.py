@@ -618,7 +618,8 @@ class CircuitData:
         self._wprog = None
 
     def _witness_lib(self):
-        path = os.path.join(os.path.dirname(ffi.lib_path()), "libp2witness.so")
+        # next to the in-tree libp2gpu.so (P2G_LIB_PATH may point at an A/B variant of libp2gpu.so elsewhere)
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libp2witness.so")
         if not os.path.exists(path):
             raise ffi.P2GError(-1, f"{path} not built")
         lib = C.CDLL(path)

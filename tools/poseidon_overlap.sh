@@ -10,11 +10,11 @@ cd "$(dirname "$0")/.."
 SRC=plonky2_aes_b200/csrc
 OUT=$(mktemp -d)
 for v in NO_SBOX NO_MDS; do
-  for f in api ntt merkle prover; do
+  for f in api ntt merkle prover witgen; do
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -DP2G_DIAG_$v -c $SRC/$f.cu -o $OUT/$f.o &
   done
   wait
-  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libp2gpu.so $OUT/api.o $OUT/ntt.o $OUT/merkle.o $OUT/prover.o -lcudart
+  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libp2gpu.so $OUT/api.o $OUT/ntt.o $OUT/merkle.o $OUT/prover.o $OUT/witgen.o -lcudart
   cp plonky2_aes_b200/libp2witness.so $OUT/
   echo -n "$v: "; P2G_LIB_PATH=$OUT/libp2gpu.so python tools/poseidon_peak.py | tail -1
 done
