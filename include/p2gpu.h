@@ -148,6 +148,23 @@ int32_t p2g_prove(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host
 int32_t p2g_prove_dev(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_dev, const uint64_t* public_inputs,
                       uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
 
+/* ---- ONE proof split over `world` GPUs by coset (SURVEY.md section 8(e) split 2; BASELINE north_star: "column-sharded
+ * LDE / Merkle leaves within one large proof, with an NCCL all-gather over NVLink of leaf digests") -------------------
+ * One process per GPU.  Rank r extends, hashes and evaluates only the 2^rate_bits / world cosets it owns (contiguous
+ * Merkle leaf blocks); the quotient at a point reads rows i and i + 8, which lie in the same coset, so the only data
+ * exchanged are: the cap entries of every commitment (wires, Z, quotient, each FRI layer), the per-coset interpolants
+ * of the two quotient columns (16 N / world bytes), the last FRI layer and the query records.  Each exchange is ONE
+ * all-gather the caller provides: `exchange(user, stage, bytes)` must gather `bytes` bytes from every rank's `send_dev`
+ * into every rank's `recv_dev` ([world][bytes], rank order) and return 0 once recv_dev is complete (e.g.
+ * ncclAllGather + stream synchronize; tests on one GPU run the ranks as host threads and copy between their buffers).
+ * send_dev: p2g_shard_buffer_bytes(c, world) bytes, recv_dev: world times that, both DEVICE memory owned by the caller.
+ * Every rank passes the same wires and returns the same proof, bit-identical to p2g_prove's. */
+typedef int32_t (*p2g_exchange_fn)(void* user, int32_t stage, uint64_t bytes_per_rank);
+size_t p2g_shard_buffer_bytes(const p2g_circuit* c, uint32_t world);
+int32_t p2g_prove_sharded(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host, const uint64_t* public_inputs,
+                          uint32_t rank, uint32_t world, uint64_t* send_dev, uint64_t* recv_dev, size_t buf_bytes,
+                          p2g_exchange_fn exchange, void* user, uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
+
 /* stage read-backs for parity tests (valid after a p2g_prove on this ctx) */
 typedef struct {
     uint64_t betas[4], gammas[4], deltas[16], alphas[4];

@@ -387,8 +387,19 @@ struct Scratch {
     }
 };
 
+// Coset shard of ONE proof over `world` GPUs (one process per GPU): this rank extends, hashes and evaluates only the
+// leaf blocks [blk_first, blk_first + blk_count); what the ranks need from each other -- Merkle cap entries, the
+// per-coset quotient interpolants, the last FRI layer, the query records -- goes through `exchange`, an all-gather
+// of `bytes` bytes per rank from `send` into `recv` ([world][bytes], rank order) that the caller implements (NCCL).
+struct ShardHost {
+    uint32_t blk_first, blk_count, world, rank;
+    gl_t* send; gl_t* recv; size_t buf_bytes;
+    p2g_exchange_fn exchange; void* user;
+};
+
 static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wires_in, bool wires_on_host,
-                          const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap, size_t* proof_words_out) {
+                          const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap, size_t* proof_words_out,
+                          const ShardHost* sh = nullptr) {
     if (!ctx || !C || !d_wires_in || !proof_out) return P2G_E_BADARG;
     if (proof_cap < C->proof_words) return P2G_E_BADARG;
     if (C->d.num_public_inputs > 0 && !public_inputs) { ctx->err = "public_inputs is NULL"; return P2G_E_BADARG; }
@@ -405,6 +416,40 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     int rc;
     Scratch S(ctx);     // every temporary of this proof; whatever is still held when the function returns
                         // (an error path, e.g. an unsatisfied witness) is released by its destructor
+    auto S_own = [&](p2g_batch* b) { S.own(b); };
+    // ---- coset shard geometry (one shard = everything when sh is null) ----
+    const uint32_t nblk = 1u << cd.rate_bits;
+    const uint32_t b0 = sh ? sh->blk_first : 0, bc = sh ? sh->blk_count : nblk;
+    uint32_t blk_log = 0; while ((1u << blk_log) < bc) blk_log++;
+    const size_t N_loc = (size_t)bc << logn, j_off = (size_t)b0 << logn;
+    const ShardDev shd = {b0, bc};
+    const int cap_h_loc = sh ? d.cap_height + (int)blk_log - cd.rate_bits : d.cap_height;   // cap entries below a shard's subtree roots
+    if (sh) {
+        if ((1u << blk_log) != bc || b0 % bc || b0 + bc > nblk || sh->world * bc != nblk || sh->rank * bc != b0 || !sh->exchange ||
+            !sh->send || !sh->recv || cap_h_loc < 0) { ctx->err = "bad coset shard"; return P2G_E_BADARG; }
+    }
+    // all-gather of `bytes` device bytes per rank; afterwards sh->recv holds [world][bytes]
+    auto gather = [&](int stage, const void* d_src, size_t bytes) -> int {
+        if (bytes > sh->buf_bytes) { ctx->err = "exchange buffer too small"; return P2G_E_BADARG; }
+        CU(cudaMemcpyAsync(sh->send, d_src, bytes, cudaMemcpyDeviceToDevice, st));
+        CU(ctx_wait(ctx));
+        if (sh->exchange(sh->user, stage, (uint64_t)bytes) != 0) { ctx->err = "exchange callback failed"; return P2G_E_CUDA; }
+        return P2G_OK;
+    };
+    // PolynomialBatch commitment of this shard's blocks; cap_full receives the whole cap (gathered when sharded)
+    auto commit = [&](int stage, const gl_t* cols, uint32_t ncols, bool from_values, p2g_batch** out, std::vector<gl_t>& cap_full) -> int {
+        int r = commit_dev(ctx, cols, ncols, logn, cd.rate_bits, (uint32_t)cap_h_loc, from_values, out, !sh, sh ? b0 : 0, sh ? bc : 0);
+        if (r) return r;
+        S_own(*out);
+        cap_full.resize(capw);
+        if (!sh) { cap_full = (*out)->cap_host; return P2G_OK; }
+        const size_t part = (size_t)4 << cap_h_loc;
+        if ((r = gather(stage, (*out)->cap, part * sizeof(gl_t)))) return r;
+        CU(cudaMemcpyAsync(ctx->pinned, sh->recv, capw * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx_wait(ctx));
+        memcpy(cap_full.data(), ctx->pinned, capw * sizeof(gl_t));
+        return P2G_OK;
+    };
     StageTimer tm(ctx);
     const bool dbg = getenv("P2G_DEBUG") != nullptr;
 #define DBG(msg) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[p2g] %s (%s)\n", msg, cudaGetErrorString(e_)); } } while (0)
@@ -422,15 +467,15 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     }
     tm.mark();
     p2g_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
-    if ((rc = commit_dev(ctx, wires, W, logn, cd.rate_bits, d.cap_height, true, &wb, true))) return rc;
-    S.own(wb);
+    std::vector<gl_t> wcap, zcap, qcap;
+    if ((rc = commit(1, wires, W, true, &wb, wcap))) return rc;
     tm.mark();
 
     DBG("wires committed");
     Challenger ch;
     ch.observe_many(d.circuit_digest, 4);
     ch.observe_many(pi_hash, 4);
-    ch.observe_many(wb->cap_host.data(), capw);
+    ch.observe_many(wcap.data(), capw);
     ProofConsts* pc_host = (ProofConsts*)(ctx->pinned + ctx->pinned_words / 2);   // upper half of the pinned staging buffer (the lower half receives D2H results)
     static_assert(sizeof(ProofConsts) < 16384, "ProofConsts too large");
     memset(pc_host, 0, sizeof(ProofConsts));
@@ -484,11 +529,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         CU(cudaMemcpyAsync(ctx->last_zs.data(), d_zs, ctx->last_zs.size() * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
     }
     tm.mark();
-    if ((rc = commit_dev(ctx, d_zs, zs_cols, logn, cd.rate_bits, d.cap_height, true, &zb, true))) return rc;
-    S.own(zb);
+    if ((rc = commit(2, d_zs, zs_cols, true, &zb, zcap))) return rc;
     S.free(d_zs); S.free(d_rowprod);
     tm.mark();
-    ch.observe_many(zb->cap_host.data(), capw);
+    ch.observe_many(zcap.data(), capw);
     // pc_host (pinned) was consumed by the H2D copy above once commit_dev synchronised
     for (int i = 0; i < nch; i++) {
         pc_host->alphas[i] = ch.get();
@@ -500,23 +544,26 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     DBG("zs committed");
     // ---- quotient ----
     gl_t *d_qv, *d_qa, *d_qc;
-    if ((rc = S.alloc(&d_qv, (size_t)nch * N))) return rc;
-    if ((rc = S.alloc(&d_qa, (size_t)nch * N))) return rc;
+    if ((rc = S.alloc(&d_qv, (size_t)nch * N_loc))) return rc;
+    if ((rc = S.alloc(&d_qa, (size_t)nch * N_loc))) return rc;
     if ((rc = S.alloc(&d_qc, (size_t)nch * N))) return rc;
     {
         bool has_pos = false;
         for (const auto& g : C->gates) has_pos |= g.kind == P2G_GATE_POSEIDON;
         P2G_COUNT_LAUNCH(1);
-        if (has_pos) quotient_kernel<true><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
-        else quotient_kernel<false><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(cd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
+        if (has_pos) quotient_kernel<true><<<(unsigned)((N_loc + 127) / 128), 128, 0, st>>>(cd, shd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
+        else quotient_kernel<false><<<(unsigned)((N_loc + 127) / 128), 128, 0, st>>>(cd, shd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
     }
     CU(cudaGetLastError());
     {
         const NttPlan* inv;
         if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, logn, 0, &inv))) return rc;
-        if (ntt_launch(inv, d_qv, n, d_qa, n, nch * 8, 1, st)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
+        if (ntt_launch(inv, d_qv, n, d_qa, n, nch * (int)bc, 1, st)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
+        // the 8-point cross-coset combination needs every coset's interpolant: all-gather of 16 N / world bytes
+        const gl_t* d_qall = d_qa;
+        if (sh) { if ((rc = gather(3, d_qa, (size_t)nch * N_loc * sizeof(gl_t)))) return rc; d_qall = sh->recv; }
         dim3 grid((unsigned)((n + 255) / 256), nch);
-        P2G_COUNT_LAUNCH(1); quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, d_qa, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
+        P2G_COUNT_LAUNCH(1); quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, bc, d_qall, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
         CU(cudaGetLastError());
     }
     DBG("quotient evaluated");
@@ -525,11 +572,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         CU(cudaMemcpyAsync(ctx->last_quotient_chunks.data(), d_qc, (size_t)nch * N * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
     }
     tm.mark();
-    if ((rc = commit_dev(ctx, d_qc, nch * qdf, logn, cd.rate_bits, d.cap_height, false, &qb, true))) return rc;
-    S.own(qb);
+    if ((rc = commit(4, d_qc, nch * qdf, false, &qb, qcap))) return rc;
     S.free(d_qv); S.free(d_qa); S.free(d_qc);
     tm.mark();
-    ch.observe_many(qb->cap_host.data(), capw);
+    ch.observe_many(qcap.data(), capw);
     const ext_t zeta = ch.get_ext();
     const gl_t g = gl_root_of_unity(logn);
     const ext_t zeta_next = ext_mul_base(zeta, g);
@@ -573,9 +619,9 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
 
     // ---- proof assembly starts: caps + openings ----
     gl_t* w = proof_out;
-    memcpy(w, wb->cap_host.data(), capw * 8); w += capw;
-    memcpy(w, zb->cap_host.data(), capw * 8); w += capw;
-    memcpy(w, qb->cap_host.data(), capw * 8); w += capw;
+    memcpy(w, wcap.data(), capw * 8); w += capw;
+    memcpy(w, zcap.data(), capw * 8); w += capw;
+    memcpy(w, qcap.data(), capw * 8); w += capw;
     {
         const ext_t* o0 = open.data(); const ext_t* o1 = open.data() + tot0;
         auto put = [&](const ext_t* p, int cnt) { memcpy(w, p, (size_t)cnt * sizeof(ext_t)); w += 2 * (size_t)cnt; };
@@ -596,8 +642,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     const ext_t fri_alpha = ch.get_ext();
     gl_t *d_comp, *d_comp_lde, *d_vals;
     if ((rc = S.alloc(&d_comp, 4 * n))) return rc;
-    if ((rc = S.alloc(&d_comp_lde, 4 * N))) return rc;
-    if ((rc = S.alloc(&d_vals, 2 * N))) return rc;
+    if ((rc = S.alloc(&d_comp_lde, 4 * N_loc))) return rc;
+    if ((rc = S.alloc(&d_vals, 2 * N_loc))) return rc;
     gl_t* d_apow;
     {
         // alpha^j for j < max(|batch 0|, |batch 1|)
@@ -615,11 +661,11 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     {
         const NttPlan* lde;
         if ((rc = ctx_get_plan(ctx, NTT_KIND_LDE, logn, cd.rate_bits, &lde))) return rc;
-        if (ntt_launch(lde, d_comp, n, d_comp_lde, N, 4, 0, st)) { ctx->err = "fri lde"; return P2G_E_CUDA; }
+        if (ntt_launch(lde, d_comp, n, d_comp_lde, N_loc, 4, 0, st, sh ? b0 : 0, sh ? bc : 0)) { ctx->err = "fri lde"; return P2G_E_CUDA; }
         ext_t comp0_at = ext_reduce_with_powers(open.data(), tot0, fri_alpha);
         ext_t comp1_at = ext_reduce_with_powers(open.data() + tot0, tot1, fri_alpha);
         ext_t shift0 = ext_pow(fri_alpha, (uint64_t)tot1);
-        P2G_COUNT_LAUNCH(1); fri_final_values_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_comp_lde, N, C->d_domain, zeta, zeta_next, comp0_at, comp1_at, shift0, d_vals);
+        P2G_COUNT_LAUNCH(1); fri_final_values_kernel<<<(unsigned)((N_loc + 255) / 256), 256, 0, st>>>(d_comp_lde, N_loc, C->d_domain + j_off, zeta, zeta_next, comp0_at, comp1_at, shift0, d_vals);
         CU(cudaGetLastError());
     }
     tm.mark();
@@ -637,11 +683,20 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         if (ab > 4) { ctx->err = "arity > 16"; return P2G_E_BADARG; }
         Layer& L = layers[l];
         L.vals = cur_vals; L.log_len = cur_log; L.arity_bits = ab;
-        const uint32_t log_leaves = cur_log - ab;
-        if ((rc = S.alloc(&L.digests, merkle_digest_words(log_leaves, d.cap_height)))) return rc;
-        if ((rc = S.alloc(&L.cap, capw))) return rc;
-        if (merkle_build(cur_vals, 0, 0, 2u << ab, log_leaves, d.cap_height, L.digests, L.cap, st)) { ctx->err = "fri merkle"; return P2G_E_CUDA; }
-        CU(cudaMemcpyAsync(ctx->pinned, L.cap, capw * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+        const uint32_t log_leaves = cur_log - ab;                     // of the whole layer
+        // a coset shard holds the leaves of its blocks: leaf index (bit-reversed order) = block | position, so a leaf of
+        // 2^ab consecutive values, its subtree and its cap entries never straddle two shards
+        if (sh && (log_leaves < (uint32_t)cd.rate_bits || (int)(log_leaves - cd.rate_bits + blk_log) < cap_h_loc)) {
+            ctx->err = "FRI layer too small for this cap height / shard count"; return P2G_E_BADARG;
+        }
+        const uint32_t log_leaves_loc = sh ? log_leaves - cd.rate_bits + blk_log : log_leaves;
+        const size_t part = (size_t)4 << cap_h_loc;
+        if ((rc = S.alloc(&L.digests, merkle_digest_words(log_leaves_loc, (uint32_t)cap_h_loc)))) return rc;
+        if ((rc = S.alloc(&L.cap, part))) return rc;
+        if (merkle_build(cur_vals, 0, 0, 2u << ab, log_leaves_loc, (uint32_t)cap_h_loc, L.digests, L.cap, st)) { ctx->err = "fri merkle"; return P2G_E_CUDA; }
+        const gl_t* d_cap_full = L.cap;
+        if (sh) { if ((rc = gather(5 + l, L.cap, part * sizeof(gl_t)))) return rc; d_cap_full = sh->recv; }
+        CU(cudaMemcpyAsync(ctx->pinned, d_cap_full, capw * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
         CU(ctx_wait(ctx));
         memcpy(w, ctx->pinned, capw * sizeof(gl_t));
         ch.observe_many(w, capw);
@@ -649,10 +704,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         const ext_t beta = ch.get_ext();
         fri_betas[l] = beta;
         gl_t* nxt;
-        if ((rc = S.alloc(&nxt, (size_t)2 << log_leaves))) return rc;
-        const size_t chunks = (size_t)1 << log_leaves;
+        const size_t chunks = (size_t)1 << log_leaves_loc, chunk_first = sh ? ((size_t)b0 << log_leaves) >> cd.rate_bits : 0;
+        if ((rc = S.alloc(&nxt, 2 * chunks))) return rc;
         P2G_COUNT_LAUNCH(1); fri_fold_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, st>>>(cur_vals, cur_log, ab, gl_inv(shift), gl_inv(gl_root_of_unity(cur_log)),
-                                                                           gl_inv(gl_root_of_unity(ab)), gl_inv((gl_t)1 << ab), beta, nxt);
+                                                                           gl_inv(gl_root_of_unity(ab)), gl_inv((gl_t)1 << ab), beta, nxt, chunk_first, chunks);
         CU(cudaGetLastError());
         cur_vals = nxt; cur_log = (int)log_leaves;
         shift = gl_pow(shift, (uint64_t)1 << ab);
@@ -660,7 +715,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     // final polynomial: interpolate the last layer on the host (<= a few hundred points)
     const size_t fl = (size_t)1 << cur_log;
     std::vector<ext_t> fvals(fl), fcoef(fl);
-    CU(cudaMemcpyAsync(ctx->pinned, cur_vals, fl * sizeof(ext_t), cudaMemcpyDeviceToHost, st));
+    if (sh && fl < nblk) { ctx->err = "final FRI layer smaller than the number of cosets"; return P2G_E_BADARG; }
+    const gl_t* d_final = cur_vals;
+    if (sh) { if ((rc = gather(21, cur_vals, (fl >> cd.rate_bits << blk_log) * sizeof(ext_t)))) return rc; d_final = sh->recv; }
+    CU(cudaMemcpyAsync(ctx->pinned, d_final, fl * sizeof(ext_t), cudaMemcpyDeviceToHost, st));
     CU(ctx_wait(ctx));
     memcpy(fvals.data(), ctx->pinned, fl * sizeof(ext_t));
     {
@@ -721,14 +779,21 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     DBG("pow done");
     // ---- query rounds ----
     const int nq = d.num_query_rounds;
-    std::vector<unsigned long long> qidx(nq);
-    for (int q = 0; q < nq; q++) qidx[q] = ch.get() % N;
+    std::vector<unsigned long long> qidx(nq), qown(nq);
+    for (int q = 0; q < nq; q++) {
+        qidx[q] = ch.get() % N;
+        const unsigned long long blk = qidx[q] >> logn;               // the coset block that holds this query's leaves
+        qown[q] = (blk >= b0 && blk < b0 + bc) ? qidx[q] : ~0ull;     // another shard's query: skipped by the gather kernel
+    }
     std::vector<GatherTree> gt;
     unsigned long long rec = 0;
     const int ocols[4] = {NC + R, W, zs_cols, nch * qdf};
     for (int o = 0; o < 4; o++) {
-        GatherTree T; T.data = oracles[o]->lde; T.digests = oracles[o]->digests; T.col_stride = N;
-        T.leaf_len = ocols[o]; T.log_leaves = logN; T.path_len = logN - d.cap_height; T.index_shift = 0; T.out_offset = rec;
+        // the preprocessed batch (o = 0) is whole on every rank; the per-proof batches hold this shard's blocks
+        const bool whole = o == 0 || !sh;
+        GatherTree T; T.data = oracles[o]->lde; T.digests = oracles[o]->digests; T.col_stride = whole ? N : N_loc;
+        T.leaf_len = ocols[o]; T.log_leaves = whole ? logN : logn + (int)blk_log; T.path_len = logN - d.cap_height; T.index_shift = 0; T.out_offset = rec;
+        T.leaf_first = whole ? 0 : j_off;
         rec += T.leaf_len + 1 + 4ull * T.path_len;
         gt.push_back(T);
     }
@@ -736,9 +801,11 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         unsigned shift_bits = 0;
         for (int l = 0; l < nl; l++) {
             shift_bits += layers[l].arity_bits;
+            const unsigned log_leaves = layers[l].log_len - layers[l].arity_bits;
             GatherTree T; T.data = layers[l].vals; T.digests = layers[l].digests; T.col_stride = 0;
-            T.leaf_len = 2u << layers[l].arity_bits; T.log_leaves = layers[l].log_len - layers[l].arity_bits;
-            T.path_len = T.log_leaves - d.cap_height; T.index_shift = shift_bits; T.out_offset = rec;
+            T.leaf_len = 2u << layers[l].arity_bits; T.log_leaves = sh ? log_leaves - cd.rate_bits + blk_log : log_leaves;
+            T.path_len = log_leaves - d.cap_height; T.index_shift = shift_bits; T.out_offset = rec;
+            T.leaf_first = sh ? ((unsigned long long)b0 << log_leaves) >> cd.rate_bits : 0;
             rec += T.leaf_len + 1 + 4ull * T.path_len;
             gt.push_back(T);
         }
@@ -748,11 +815,23 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     CU(S.alloc_bytes((void**)&d_qidx, nq * 8));
     if ((rc = S.alloc(&d_q, rec * nq))) return rc;
     CU(cudaMemcpyAsync(d_gt, gt.data(), gt.size() * sizeof(GatherTree), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_qidx, qidx.data(), nq * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_qidx, qown.data(), nq * 8, cudaMemcpyHostToDevice, st));
+    if (sh) CU(cudaMemsetAsync(d_q, 0, rec * nq * sizeof(gl_t), st));
     P2G_COUNT_LAUNCH(1); query_gather_kernel<<<dim3(nq, (unsigned)gt.size()), 128, 0, st>>>(d_gt, (int)gt.size(), d_qidx, rec, d_q);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(w, d_q, rec * nq * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
-    CU(ctx_wait(ctx));
+    if (!sh) {
+        CU(cudaMemcpyAsync(w, d_q, rec * nq * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx_wait(ctx));
+    } else {
+        // every rank gathered the records of the queries that fall into its blocks; after the all-gather each
+        // record is taken from its owner
+        if ((rc = gather(22, d_q, rec * nq * sizeof(gl_t)))) return rc;
+        for (int q = 0; q < nq; q++) {
+            const size_t owner = (size_t)((qidx[q] >> logn) / bc);
+            CU(cudaMemcpyAsync(w + (size_t)q * rec, sh->recv + (owner * nq + q) * rec, rec * sizeof(gl_t), cudaMemcpyDeviceToHost, st));
+        }
+        CU(ctx_wait(ctx));
+    }
     w += rec * nq;
     memcpy(w, fcoef.data(), final_len * sizeof(ext_t)); w += 2 * final_len;
     *w++ = pow_witness;
@@ -786,6 +865,33 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
 extern "C" int32_t p2g_prove(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host, const uint64_t* public_inputs,
                              uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {
     return prove_impl(ctx, c, wires_host, true, public_inputs, proof_out, proof_cap_words, proof_words_out);
+}
+extern "C" int32_t p2g_prove_sharded(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host, const uint64_t* public_inputs,
+                                     uint32_t rank, uint32_t world, uint64_t* send_dev, uint64_t* recv_dev, size_t buf_bytes,
+                                     p2g_exchange_fn exchange, void* user, uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {
+    if (!c || !world || rank >= world) return P2G_E_BADARG;
+    const uint32_t nblk = 1u << c->cd.rate_bits;
+    if (world > nblk || nblk % world) { if (ctx) ctx->err = "world size must divide the number of cosets"; return P2G_E_BADARG; }
+    ShardHost sh = {rank * (nblk / world), nblk / world, world, rank, send_dev, recv_dev, buf_bytes, exchange, user};
+    return prove_impl(ctx, c, wires_host, true, public_inputs, proof_out, proof_cap_words, proof_words_out, &sh);
+}
+extern "C" size_t p2g_shard_buffer_bytes(const p2g_circuit* c, uint32_t world) {
+    if (!c || !world) return 0;
+    const p2g_circuit_desc& d = c->d;
+    const size_t N = (size_t)1 << (d.degree_bits + d.rate_bits);
+    size_t q = (size_t)d.num_challenges * (N / world) * sizeof(gl_t);                     // quotient interpolants
+    size_t per_q = 0;                                                                     // one query record
+    {
+        const int nlp = num_lookup_polys(d), NC = d.num_selectors + d.num_lookup_selectors + d.num_constants;
+        const int cols[4] = {NC + d.num_routed_wires, d.num_wires, d.num_challenges * (1 + d.num_partial_products + nlp), d.num_challenges * d.quotient_degree_factor};
+        const int logN = d.degree_bits + d.rate_bits;
+        for (int o = 0; o < 4; o++) per_q += cols[o] + 1 + 4 * (size_t)(logN - d.cap_height);
+        int lg = logN;
+        for (int l = 0; l < d.num_reduction_arity_bits; l++) { lg -= d.reduction_arity_bits[l]; per_q += (2u << d.reduction_arity_bits[l]) + 1 + 4 * (size_t)(lg - d.cap_height); }
+    }
+    size_t r = per_q * d.num_query_rounds * sizeof(gl_t);
+    size_t b = q > r ? q : r;
+    return (b + 255) & ~(size_t)255;
 }
 extern "C" int32_t p2g_prove_dev(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_dev, const uint64_t* public_inputs,
                                  uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {

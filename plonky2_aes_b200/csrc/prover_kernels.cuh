@@ -74,6 +74,10 @@ struct CircuitDev {
     int nlp, num_sldc, lut_degree, lu_degree, lu_slots, lut_slots, num_luts, num_gates, num_gate_constraints;
     int zs_cols;
 };
+// Coset shard of one proof (multi-GPU split of a single proof): this rank holds the leaf
+// blocks [blk_first, blk_first + blk_count) of the 2^rate_bits cosets; its per-proof buffers (wires / zs / quotient
+// LDE, FRI layers) cover only those blocks, the per-circuit tables (constants_sigmas LDE, domain) all of them.
+struct ShardDev { unsigned int blk_first, blk_count; };
 
 // ---------------------------------------------------------------------------------------------
 // wires_permutation_partial_products_and_zs (plonk/prover.rs), step 1: per row and challenge
@@ -379,16 +383,20 @@ lut_eval_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const uint16_
 
 template <bool HAS_POSEIDON>
 __global__ void __launch_bounds__(128)
-quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ lut_evals, const p2g_gate* __restrict__ gates,
+quotient_kernel(CircuitDev cd, ShardDev sh, const ProofConsts* __restrict__ pc, const gl_t* __restrict__ lut_evals, const p2g_gate* __restrict__ gates,
                 const gl_t* __restrict__ cs, const gl_t* __restrict__ wl, const gl_t* __restrict__ zl,
                 const gl_t* __restrict__ domain, const gl_t* __restrict__ l0inv, gl_t* __restrict__ out) {
-    const int logn = cd.logn, logN = logn + cd.rate_bits;
-    const size_t n = (size_t)1 << logn, N = (size_t)1 << logN;
+    const int logn = cd.logn;
+    const size_t n = (size_t)1 << logn;
+    // per-proof arrays (wl, zl, out) hold this shard's blocks only: N = leaves held, j = local leaf index; the
+    // per-circuit arrays are addressed through the pointer offsets below
+    const size_t N = (size_t)sh.blk_count << logn, NG = n << cd.rate_bits, j_off = (size_t)sh.blk_first << logn;
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
-    const uint32_t blk = (uint32_t)(j >> logn), within = (uint32_t)(j & (n - 1));
+    cs += j_off; domain += j_off; l0inv += j_off;
+    const uint32_t blk_l = (uint32_t)(j >> logn), blk = blk_l + sh.blk_first, within = (uint32_t)(j & (n - 1));
     const uint32_t k = gl_bitrev(within, logn);
-    const size_t jn = ((size_t)blk << logn) + gl_bitrev((k + 1) & (uint32_t)(n - 1), logn);
+    const size_t jn = ((size_t)blk_l << logn) + gl_bitrev((k + 1) & (uint32_t)(n - 1), logn);
     const uint32_t coset = gl_bitrev(blk, cd.rate_bits);
     const gl_t x = domain[j];
     const gl_t zh = pc->zh[coset];
@@ -409,7 +417,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
         gl_t prev[MAX_CH];
         for (int c = 0; c < nch; c++) prev[c] = zl[(size_t)c * N + j];
         // the wire / sigma values of routed wire w+1 are loaded while wire w is multiplied in
-        gl_t wv_n = wl[j], sv_n = cs[(size_t)cd.NC * N + j];
+        gl_t wv_n = wl[j], sv_n = cs[(size_t)cd.NC * NG + j];
 #pragma unroll 1
         for (int ck = 0; ck <= cd.num_prods; ck++) {
             gl_t np[MAX_CH], dp[MAX_CH];
@@ -419,7 +427,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
 #pragma unroll 1
             for (int w = lo; w < hi; w++) {
                 const gl_t wv = wv_n, sv = sv_n;
-                if (w + 1 < R) { wv_n = wl[(size_t)(w + 1) * N + j]; sv_n = cs[(size_t)(cd.NC + w + 1) * N + j]; }
+                if (w + 1 < R) { wv_n = wl[(size_t)(w + 1) * N + j]; sv_n = cs[(size_t)(cd.NC + w + 1) * NG + j]; }
 #pragma unroll
                 for (int c = 0; c < MAX_CH; c++) if (c < nch) {
                     // lazy residues: they only feed the running products
@@ -441,8 +449,8 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
     // lookup terms (check_lookup_constraints_batch)
     if (cd.num_luts > 0) {
         const int zpp = nch * (1 + cd.num_prods);
-        const gl_t* lsel = cs + (size_t)cd.num_sel * N;       // lookup selector columns
-        const gl_t s_trans_sre = lsel[0 * N + j], s_trans_ldc = lsel[1 * N + j], s_init = lsel[2 * N + j], s_last = lsel[3 * N + j];
+        const gl_t* lsel = cs + (size_t)cd.num_sel * NG;       // lookup selector columns
+        const gl_t s_trans_sre = lsel[0 * NG + j], s_trans_ldc = lsel[1 * NG + j], s_init = lsel[2 * NG + j], s_last = lsel[3 * NG + j];
         const int n_lookup_terms = 4 + cd.num_luts + 2 * cd.num_sldc;
 #pragma unroll 1
         for (int c = 0; c < nch; c++) {
@@ -455,7 +463,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
             ADD_TERM(tb + 2, gl_mul(s_init, z_re));
 #pragma unroll 1
             for (int r = 0; r < cd.num_luts; r++)
-                ADD_TERM(tb + 3 + r, gl_mul(lsel[(size_t)(4 + r) * N + j], gl_sub(z_re, lut_evals[c * 8 + r])));
+                ADD_TERM(tb + 3 + r, gl_mul(lsel[(size_t)(4 + r) * NG + j], gl_sub(z_re, lut_evals[c * 8 + r])));
             gl_t re_cur = next_z_re;
             const int tt = tb + 4 + cd.num_luts;   // index of the first per-poly term (after RE transition at tt-1)
 #pragma unroll 1
@@ -497,7 +505,7 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
     }
     // gate constraints: slot k accumulates filter * constraint_k over all gates
     {
-        const gl_t* gconst = cs + (size_t)(cd.num_sel + cd.num_lsel) * N;
+        const gl_t* gconst = cs + (size_t)(cd.num_sel + cd.num_lsel) * NG;
         const bool many = cd.num_sel > 1;
         gl_t f_arith = 0, f_const = 0, f_pi = 0, f_pos = 0;
         int arith_ops = 0, nconst = 0;
@@ -506,13 +514,13 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
         for (int g = 0; g < cd.num_gates; g++) {
             const p2g_gate G = gates[g];
             if (G.num_constraints == 0) continue;
-            gl_t f = gate_filter(g, G.group_start, G.group_end, cs[(size_t)G.selector_index * N + j], many);
+            gl_t f = gate_filter(g, G.group_start, G.group_end, cs[(size_t)G.selector_index * NG + j], many);
             if (G.kind == P2G_GATE_ARITHMETIC) { f_arith = f; arith_ops = G.param0; }
             else if (G.kind == P2G_GATE_CONSTANT) { f_const = f; nconst = G.param0; }
             else if (G.kind == P2G_GATE_PUBLIC_INPUT) f_pi = f;
             else if (G.kind == P2G_GATE_POSEIDON) { f_pos = f; has_poseidon = true; }
         }
-        const gl_t c0 = cd.num_consts > 0 ? gconst[j] : 0, c1 = cd.num_consts > 1 ? gconst[N + j] : 0;
+        const gl_t c0 = cd.num_consts > 0 ? gconst[j] : 0, c1 = cd.num_consts > 1 ? gconst[NG + j] : 0;
         // contribution of the cheap gates to constraint slot k
         auto small_gates = [&](int k) -> gl_t {
             gl_t v = 0;
@@ -543,14 +551,14 @@ quotient_kernel(CircuitDev cd, const ProofConsts* __restrict__ pc, const gl_t* _
 #undef ADD_TERM
     const gl_t zi = pc->zh_inv[coset];
     for (int c = 0; c < nch; c++)
-        out[(size_t)c * N + ((size_t)blk << logn) + k] = gl_mul(acc_fold(acc[c]), zi);
+        out[(size_t)c * N + ((size_t)blk_l << logn) + k] = gl_mul(acc_fold(acc[c]), zi);
 }
 
 // Recover the quotient chunk coefficients from the 8 per-coset inverse NTTs:
 //   t_c[j] = 7^(-n c)/8 * sum_s w_8^(-s c) * h_s^(-j) * a_s[j],  h_s = 7 w_N^s
 // in: [nch][8 blocks (bit-reversed coset order)][n]; table: [8 (natural coset s)][n] = h_s^(-j)/8
 __global__ void __launch_bounds__(256)
-quotient_combine_kernel(int logn, int nch, const gl_t* __restrict__ in, const gl_t* __restrict__ table,
+quotient_combine_kernel(int logn, int nch, unsigned int blk_count, const gl_t* __restrict__ in, const gl_t* __restrict__ table,
                         const gl_t* __restrict__ w8inv_pows /*[8]*/, const gl_t* __restrict__ shift_n_inv_pows /*[8]*/,
                         gl_t* __restrict__ out /*[nch*8][n]*/) {
     const size_t n = (size_t)1 << logn;
@@ -561,7 +569,9 @@ quotient_combine_kernel(int logn, int nch, const gl_t* __restrict__ in, const gl
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         uint32_t blk = gl_bitrev((uint32_t)s, 3);
-        v[s] = gl_mul(in[((size_t)ch * 8 + blk) * n + j], table[(size_t)s * n + j]);
+        // `in` is the all-gather of the shards' [nch][blk_count][n] arrays (blk_count = 8: one shard, plain layout)
+        const uint32_t rk = blk / blk_count, bl = blk % blk_count;
+        v[s] = gl_mul(in[(((size_t)rk * nch + ch) * blk_count + bl) * n + j], table[(size_t)s * n + j]);
     }
 #pragma unroll
     for (int c = 0; c < 8; c++) {
@@ -629,8 +639,8 @@ fri_compose_kernel(const gl_t* const* __restrict__ polys, int npolys, const gl_t
 // final(x) = alpha^{|b1|} (comp0(x) - comp0(zeta)) / (x - zeta) + (comp1(x) - comp1(g zeta)) / (x - g zeta)
 // lde: [4][N] = comp0.c0, comp0.c1, comp1.c0, comp1.c1 on the LDE domain (bit-reversed); out [N][2]
 __global__ void __launch_bounds__(256)
-fri_final_values_kernel(const gl_t* __restrict__ lde, size_t N, const gl_t* __restrict__ domain, ext_t zeta, ext_t zeta_next,
-                        ext_t comp0_at, ext_t comp1_at, ext_t shift0, gl_t* __restrict__ out) {
+fri_final_values_kernel(const gl_t* __restrict__ lde, size_t N, const gl_t* __restrict__ domain /* at this shard's first point */,
+                        ext_t zeta, ext_t zeta_next, ext_t comp0_at, ext_t comp1_at, ext_t shift0, gl_t* __restrict__ out) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     const gl_t x = domain[j];
@@ -651,9 +661,11 @@ fri_final_values_kernel(const gl_t* __restrict__ lde, size_t N, const gl_t* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 fri_fold_kernel(const gl_t* __restrict__ values, int log_len, int arity_bits, gl_t shift_inv, gl_t w_len_inv,
-                gl_t w_arity_inv, gl_t arity_inv, ext_t beta, gl_t* __restrict__ out) {
+                gl_t w_arity_inv, gl_t arity_inv, ext_t beta, gl_t* __restrict__ out, size_t chunk_first = 0, size_t chunk_count = 0) {
+    // log_len: size of the WHOLE layer; a coset shard holds the chunks [chunk_first, chunk_first + chunk_count)
+    // (values / out point at its first chunk); chunk_count = 0: the whole layer
     const int arity = 1 << arity_bits;
-    const size_t chunks = (size_t)1 << (log_len - arity_bits);
+    const size_t chunks = chunk_count ? chunk_count : (size_t)1 << (log_len - arity_bits);
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= chunks) return;
     ext_t u[16];
@@ -663,7 +675,7 @@ fri_fold_kernel(const gl_t* __restrict__ values, int log_len, int arity_bits, gl
         u[m] = ext_make(values[2 * (k * arity + tpos)], values[2 * (k * arity + tpos) + 1]);
     }
     // x0^-1 = shift^-1 * w_len^-(bitrev_{log_len - arity_bits}(k))
-    uint32_t e = gl_bitrev((uint32_t)k, log_len - arity_bits);
+    uint32_t e = gl_bitrev((uint32_t)(k + chunk_first), log_len - arity_bits);
     gl_t x0_inv = gl_mul(shift_inv, gl_pow(w_len_inv, e));
     ext_t y = ext_mul_base(beta, x0_inv);
     // out = sum_i r_i y^i with r_i = (1/arity) sum_m u[m] w^-(i m): evaluate directly (arity <= 16)
@@ -707,13 +719,15 @@ struct GatherTree {
     unsigned long long col_stride;   // column-major stride (N); 0 = row-major
     unsigned int leaf_len, log_leaves, path_len, index_shift;  // leaf index = query_index >> index_shift
     unsigned long long out_offset;   // offset inside one query's record
+    unsigned long long leaf_first;   // coset shard: first leaf held (data / digests are local); 0 otherwise
 };
 __global__ void __launch_bounds__(128)
 query_gather_kernel(const GatherTree* __restrict__ trees, int ntrees, const unsigned long long* __restrict__ qidx,
                     unsigned long long record_words, gl_t* __restrict__ out) {
     const int q = blockIdx.x, t = blockIdx.y;
     const GatherTree T = trees[t];
-    const size_t leaf = (size_t)(qidx[q] >> T.index_shift);
+    if (qidx[q] == ~0ull) return;                    // a query another shard owns: its record stays zero
+    const size_t leaf = (size_t)(qidx[q] >> T.index_shift) - (size_t)T.leaf_first;
     gl_t* o = out + (size_t)q * record_words + T.out_offset;
     for (unsigned int c = threadIdx.x; c < T.leaf_len; c += blockDim.x)
         o[c] = T.col_stride ? T.data[(size_t)c * T.col_stride + leaf] : T.data[leaf * T.leaf_len + c];

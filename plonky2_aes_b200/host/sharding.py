@@ -124,3 +124,101 @@ def sharded_commit(ctx, dev_cols, ncols, log_n, rank, world, dist=None, rate_bit
     dist.all_gather(parts, mine)
     cap = torch.cat(parts).cpu().numpy().view(np.uint64)
     return cap, h
+
+
+EXCHANGE_FN = None
+
+
+def _exchange_type():
+    import ctypes as C
+    global EXCHANGE_FN
+    if EXCHANGE_FN is None:
+        EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_uint64)
+    return EXCHANGE_FN
+
+
+def sharded_prove(ctx, circuit, proof_words, wires, rank, world, all_gather, public_inputs=None):
+    """One proof split over `world` GPUs by coset (p2g_prove_sharded, SURVEY.md section 8(e) split 2).
+
+    `all_gather(recv, send, nbytes)` gathers the first nbytes of every rank's `send` (a uint8 CUDA tensor) into
+    `recv` ([world * nbytes], rank order) and returns when recv is complete -- torch.distributed.all_gather_into_tensor
+    on NCCL in production (nccl_all_gather below), a copy between host threads in the single-GPU tests.  Every
+    rank passes the same wire matrix and gets the same proof back."""
+    import ctypes as C
+    import torch
+    lib = ctx.lib
+    nbytes = lib.p2g_shard_buffer_bytes(circuit, world)
+    dev = torch.device("cuda", ctx.device)
+    send = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    recv = torch.empty(nbytes * world, dtype=torch.uint8, device=dev)
+    errors = []
+
+    def cb(_user, stage, nb):
+        try:
+            all_gather(recv, send, int(nb))
+            return 0
+        except Exception as e:          # an exception must not cross the C frames
+            errors.append(e)
+            return 1
+    fn = _exchange_type()(cb)
+    out = np.empty(proof_words, dtype=np.uint64)
+    got = C.c_size_t()
+    wires = np.ascontiguousarray(wires, dtype=np.uint64)
+    pi = np.ascontiguousarray(public_inputs, dtype=np.uint64) if public_inputs is not None and len(public_inputs) else None
+    rc = lib.p2g_prove_sharded(ctx.handle, circuit, wires.ctypes.data, pi.ctypes.data if pi is not None else None, rank, world,
+                               send.data_ptr(), recv.data_ptr(), nbytes, C.cast(fn, C.c_void_p), None, out.ctypes.data, proof_words,
+                               C.byref(got))
+    if errors:
+        raise errors[0]
+    ctx.check(rc)
+    return out[:got.value]
+
+
+def nccl_all_gather(dist, device):
+    """the exchange of sharded_prove over torch.distributed (NCCL): one all_gather_into_tensor per stage"""
+    import torch
+
+    def gather(recv, send, nbytes):
+        world = dist.get_world_size()
+        dist.all_gather_into_tensor(recv[:world * nbytes], send[:nbytes])
+        torch.cuda.synchronize(device)
+    return gather
+
+
+class ThreadedShards:
+    """`world` coset shards of one proof as host threads on ONE GPU (tests, and the single-GPU emulation the
+    profiling recipe asks for: no kernel ever waits for another rank, the rendezvous is on the host)."""
+
+    def __init__(self, world):
+        self.world, self.barrier = world, threading.Barrier(world)
+        self.sends = [None] * world
+
+    def gather_fn(self, rank):
+        import torch
+
+        def gather(recv, send, nbytes):
+            self.sends[rank] = send
+            self.barrier.wait()
+            for r in range(self.world):
+                recv[r * nbytes:(r + 1) * nbytes].copy_(self.sends[r][:nbytes])
+            torch.cuda.synchronize()
+            self.barrier.wait()
+        return gather
+
+    def prove(self, ctxs, circuits, proof_words, wires, public_inputs=None):
+        out, errors = [None] * self.world, []
+
+        def run(r):
+            try:
+                out[r] = sharded_prove(ctxs[r], circuits[r], proof_words, wires, r, self.world, self.gather_fn(r), public_inputs)
+            except Exception as e:
+                errors.append(e)
+                self.barrier.abort()
+        ths = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out

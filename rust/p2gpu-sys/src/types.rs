@@ -5,6 +5,10 @@
 macro_rules! opaque { ($($n:ident),*) => { $(#[repr(C)] pub struct $n { _p: [u8; 0] })* } }
 opaque!(p2g_ctx, p2g_batch, p2g_circuit, p2g_wmap, p2g_wprog);
 
+/// all-gather callback of `p2g_prove_sharded`: gather `bytes_per_rank` bytes of every rank's send buffer into every
+/// rank's receive buffer, return 0 when the receive buffer is complete
+pub type p2g_exchange_fn = Option<unsafe extern "C" fn(user: *mut std::os::raw::c_void, stage: i32, bytes_per_rank: u64) -> i32>;
+
 pub const P2G_OK: i32 = 0;
 pub const P2G_E_CUDA: i32 = -1;
 pub const P2G_E_BADARG: i32 = -2;

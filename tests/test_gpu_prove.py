@@ -401,3 +401,28 @@ def test_device_witness_generation(gpu_ctx, oracle):
         lib.p2g_wprog_free(gpu_ctx.handle, h)
     slots = slots[:10]            # without the plaintext the AES rounds read partitions nobody sets
     assert lib.p2g_wprog_load(gpu_ctx.handle, C.byref(data._wdesc), slots.ctypes.data, len(slots), C.byref(h)) == -2
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_coset_sharded_proof_equals_single_gpu_proof(gpu_ctx, oracle, world):
+    """p2g_prove_sharded: one proof split by coset over `world` ranks (here host threads on one GPU, each with its
+    own context and exchange buffers) is bit-identical to the unsharded proof on every rank -- commitments of the
+    owned leaf blocks only, quotient evaluated per coset, all-gathers of cap entries / quotient interpolants /
+    last FRI layer / query records.  AES-GCM (lookups), Feistel (PoseidonGate) and the public-input circuit."""
+    from plonky2_aes_b200.host.polynomial_batch import Context
+    from plonky2_aes_b200.host.sharding import ThreadedShards
+    cases = [circuits.aes_gcm(13, True)[:2] + (None,), circuits.feistel_poseidon()[:2] + (None,)]
+    if world <= 4:
+        cases.append(circuits.aes_block()[:2] + (None,))
+    ctxs = [Context(0) for _ in range(world)]
+    for data, wires, pi in cases:
+        data.load(gpu_ctx)
+        ref = data.prove_wires(wires, pi)
+        handles = [data.load_handle(c) for c in ctxs]
+        proofs = ThreadedShards(world).prove(ctxs, handles, data.proof_words, wires, pi)
+        for r, p in enumerate(proofs):
+            assert np.array_equal(p, ref), (world, r)
+        for c, h in zip(ctxs, handles):
+            c.check(c.lib.p2g_circuit_free(c.handle, h))
+    for c in ctxs:
+        c.close()
