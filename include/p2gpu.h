@@ -144,6 +144,12 @@ int32_t p2g_proof_from_bytes(const p2g_circuit_desc* desc, const uint8_t* bytes,
  * proof_out: flat u64 proof (layout in DESIGN.md, identical to the oracle's). */
 int32_t p2g_prove(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host, const uint64_t* public_inputs,
                   uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
+/* Batch of independent proofs (BASELINE config 5): proof i is proved on context i mod n_ctx, one host thread per
+ * context inside the call; contexts may sit on one GPU (several proofs in flight) or on several.  circuits[t] must
+ * have been loaded on ctxs[t].  status_out[i] receives each proof's return code; returns the first failure. */
+int32_t p2g_prove_batch(p2g_ctx* const* ctxs, const p2g_circuit* const* circuits, uint32_t n_ctx,
+                        const uint64_t* const* wires_host, const uint64_t* const* public_inputs /* may be NULL */, uint32_t n_proofs,
+                        uint64_t* const* proofs_out, size_t proof_cap_words, int32_t* status_out);
 /* same with the witness already in HBM */
 int32_t p2g_prove_dev(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_dev, const uint64_t* public_inputs,
                       uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);

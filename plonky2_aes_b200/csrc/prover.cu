@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <algorithm>
 #include <stdlib.h>
+#include <thread>
 
 // ---------------------------------------------------------------------------------------------
 // host transcript: Challenger<F, PoseidonHash> (iop/challenger.rs)
@@ -892,6 +893,26 @@ extern "C" size_t p2g_shard_buffer_bytes(const p2g_circuit* c, uint32_t world) {
     size_t r = per_q * d.num_query_rounds * sizeof(gl_t);
     size_t b = q > r ? q : r;
     return (b + 255) & ~(size_t)255;
+}
+// p2g_prove for a batch: proof i runs on context i mod n_ctx, one host thread per context, so the latency-bound
+// parts of one proof (Fiat-Shamir round trips, tree tops) overlap the heavy kernels of the others
+extern "C" int32_t p2g_prove_batch(p2g_ctx* const* ctxs, const p2g_circuit* const* circuits, uint32_t n_ctx,
+                                   const uint64_t* const* wires_host, const uint64_t* const* public_inputs, uint32_t n_proofs,
+                                   uint64_t* const* proofs_out, size_t proof_cap_words, int32_t* status_out) {
+    if (!ctxs || !circuits || !n_ctx || !wires_host || !proofs_out || (n_proofs && !status_out)) return P2G_E_BADARG;
+    for (uint32_t t = 0; t < n_ctx; t++) if (!ctxs[t] || !circuits[t]) return P2G_E_BADARG;
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_ctx && t < n_proofs; t++)
+        th.emplace_back([=]() {
+            for (uint32_t i = t; i < n_proofs; i += n_ctx) {
+                size_t got = 0;
+                status_out[i] = prove_impl(ctxs[t], circuits[t], wires_host[i], true, public_inputs ? public_inputs[i] : nullptr,
+                                           proofs_out[i], proof_cap_words, &got);
+            }
+        });
+    for (auto& x : th) x.join();
+    for (uint32_t i = 0; i < n_proofs; i++) if (status_out[i] != P2G_OK) return status_out[i];
+    return P2G_OK;
 }
 extern "C" int32_t p2g_prove_dev(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_dev, const uint64_t* public_inputs,
                                  uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out) {

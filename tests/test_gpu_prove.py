@@ -426,3 +426,26 @@ def test_coset_sharded_proof_equals_single_gpu_proof(gpu_ctx, oracle, world):
             c.check(c.lib.p2g_circuit_free(c.handle, h))
     for c in ctxs:
         c.close()
+
+
+def test_prove_batch_entry_point(gpu_ctx, oracle):
+    """p2g_prove_batch: the C-level batch (host threads inside the library, proof i on context i mod n_ctx) returns the
+    proofs p2g_prove returns one at a time"""
+    from plonky2_aes_b200.host.polynomial_batch import Context
+    data, _, tg = circuits.aes_gcm(13, True)
+    data.load(gpu_ctx)
+    wires = data.generate_witnesses(tg.input_targets(), circuits.gcm_inputs(tg, 21, 5))
+    ctxs = [gpu_ctx, Context(0), Context(0)]
+    handles = [data._gpu_circuit] + [data.load_handle(c) for c in ctxs[1:]]
+    words = data.proof_words
+    out = np.zeros((5, words), dtype=np.uint64)
+    status = np.full(5, 99, dtype=np.int32)
+    vp = C.c_void_p
+    rc = gpu_ctx.lib.p2g_prove_batch((vp * 3)(*[c.handle for c in ctxs]), (vp * 3)(*handles), 3,
+                                     (vp * 5)(*[w.ctypes.data for w in wires]), None, 5,
+                                     (vp * 5)(*[o.ctypes.data for o in out]), words, status.ctypes.data)
+    assert rc == 0 and not status.any()
+    for i in range(5):
+        assert np.array_equal(out[i], data.prove_wires(wires[i]))
+    for c, h in zip(ctxs[1:], handles[1:]):
+        c.check(c.lib.p2g_circuit_free(c.handle, h)); c.close()
