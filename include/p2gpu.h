@@ -232,6 +232,10 @@ int32_t p2g_last_timings(p2g_ctx* ctx, p2g_timings* out);
 int32_t p2g_set_timing(p2g_ctx* ctx, int32_t enabled);
 /* device ms of the last commit's three kernels groups: inverse NTT, coset LDE, Merkle tree */
 int32_t p2g_last_commit_timings(p2g_ctx* ctx, float out[3]);
+/* Debug aid (contexts created with P2G_CANARY=1 in the environment): every device block the library allocates gets a
+ * guard band that is verified when the block is released; returns the number of blocks checked and of overwritten
+ * bands.  P2G_E_BADARG when the context was not created in canary mode. */
+int32_t p2g_debug_canary(p2g_ctx* ctx, uint64_t* blocks_checked, uint64_t* failures);
 /* kernels launched by the library since it was loaded (all contexts) */
 uint64_t p2g_launch_count(void);
 

@@ -28,6 +28,8 @@ extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
     p2g_ctx* ctx = new p2g_ctx();
     ctx->device = device; ctx->timing = false; ctx->keep_debug = false;
     ctx->st = nullptr; ctx->pool = nullptr; ctx->pinned = nullptr; ctx->wait_ev = nullptr;
+    { const char* e = getenv("P2G_CANARY"); ctx->canary = e && atoi(e) != 0; }
+    ctx->canary_failures = ctx->canary_checked = 0;
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     memset(&ctx->transcript, 0, sizeof(ctx->transcript));
     bool ok = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) == cudaSuccess;
@@ -101,10 +103,43 @@ int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan
     return P2G_OK;
 }
 int ctx_alloc(p2g_ctx* ctx, gl_t** p, size_t words) {
-    CU(cudaMallocFromPoolAsync((void**)p, (words ? words : 1) * sizeof(gl_t), ctx->pool, ctx->st));
+    if (!words) words = 1;
+    if (!ctx->canary) {
+        CU(cudaMallocFromPoolAsync((void**)p, words * sizeof(gl_t), ctx->pool, ctx->st));
+        return P2G_OK;
+    }
+    CU(cudaMallocFromPoolAsync((void**)p, (words + P2G_CANARY_WORDS) * sizeof(gl_t), ctx->pool, ctx->st));
+    CU(cudaMemsetAsync(*p + words, 0xA5, P2G_CANARY_WORDS * sizeof(gl_t), ctx->st));
+    ctx->canary_words[*p] = words;
     return P2G_OK;
 }
-void ctx_free(p2g_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->st); }
+void ctx_free(p2g_ctx* ctx, void* p) {
+    if (!p) return;
+    if (ctx->canary) {
+        auto it = ctx->canary_words.find(p);
+        if (it != ctx->canary_words.end()) {            // everything queued before this free has run once the copy is back
+            gl_t* band = ctx->pinned + ctx->pinned_words - P2G_CANARY_WORDS;
+            if (cudaMemcpyAsync(band, (gl_t*)p + it->second, P2G_CANARY_WORDS * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st) == cudaSuccess &&
+                cudaStreamSynchronize(ctx->st) == cudaSuccess) {
+                ctx->canary_checked++;
+                for (int i = 0; i < P2G_CANARY_WORDS; i++)
+                    if (band[i] != 0xA5A5A5A5A5A5A5A5ULL) {
+                        ctx->canary_failures++;
+                        fprintf(stderr, "[p2g] guard band behind a %zu-word block overwritten at word +%d\n", it->second, i);
+                        break;
+                    }
+            }
+            ctx->canary_words.erase(it);
+        }
+    }
+    cudaFreeAsync(p, ctx->st);
+}
+extern "C" int32_t p2g_debug_canary(p2g_ctx* ctx, uint64_t* blocks_checked, uint64_t* failures) {
+    if (!ctx || !ctx->canary) return P2G_E_BADARG;
+    if (blocks_checked) *blocks_checked = ctx->canary_checked;
+    if (failures) *failures = ctx->canary_failures;
+    return P2G_OK;
+}
 
 int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
                uint32_t cap_height, bool from_values, p2g_batch** out, bool sync_cap, uint32_t blk_first, uint32_t blk_count) {

@@ -40,7 +40,13 @@ struct p2g_ctx {
     float commit_ms[3];     // last commit: inverse NTT, coset LDE, Merkle (when timing is on)
     cudaEvent_t wait_ev;    // blocking-sync event: host threads sleep while they wait for the stream
     int wait_mode;          // 0 spin (cudaStreamSynchronize), 1 blocking-sync event, 2 poll + sched_yield
+    // P2G_CANARY=1 (debug): every ctx_alloc block gets a guard band behind it that ctx_free checks -- the
+    // out-of-bounds-write detector used where compute-sanitizer is not available (tests/test_gpu_prove.py)
+    bool canary;
+    std::map<void*, size_t> canary_words;
+    unsigned long long canary_failures, canary_checked;
 };
+#define P2G_CANARY_WORDS 64
 
 // Host wait for everything queued on the context's stream.  A proof has ~10 such waits (Fiat-Shamir
 // round trips) and a process keeps several proofs in flight on separate host threads, times one

@@ -449,3 +449,44 @@ def test_prove_batch_entry_point(gpu_ctx, oracle):
         assert np.array_equal(out[i], data.prove_wires(wires[i]))
     for c, h in zip(ctxs[1:], handles[1:]):
         c.check(c.lib.p2g_circuit_free(c.handle, h)); c.close()
+
+
+def test_guard_bands_see_no_out_of_bounds_write(oracle):
+    """compute-sanitizer is closed on the GPU pool, so the library carries its own out-of-bounds-WRITE detector:
+    with P2G_CANARY=1 every device block gets a guard band that is checked on release.  Run over the shapes with
+    the most irregular indexing: tiny / odd commitments, a lookup circuit, the PoseidonGate circuit, public inputs,
+    the device witness generator and a coset-sharded proof."""
+    import os
+    from plonky2_aes_b200.host.polynomial_batch import Context, PolynomialBatch
+    from plonky2_aes_b200.host.sharding import ThreadedShards
+    os.environ["P2G_CANARY"] = "1"
+    try:
+        ctxs = [Context(0) for _ in range(3)]
+    finally:
+        del os.environ["P2G_CANARY"]
+    ctx = ctxs[0]
+    rng = np.random.default_rng(1)
+    for ncols, log_n, cap in ((1, 1, 0), (5, 1, 3), (3, 2, 1), (9, 6, 4), (135, 10, 4), (3, 14, 4)):
+        PolynomialBatch.from_values(ctx, rng.integers(0, P, size=(ncols, 1 << log_n), dtype=np.uint64), 3, cap).free()
+    for data, wires, pi in (circuits.tiny_arith() + (None,), circuits.aes_gcm(13, True)[:2] + (None,),
+                            circuits.feistel_poseidon()[:2] + (None,), circuits.public_input_circuit()):
+        data.load(ctx)
+        data.prove_wires(wires, pi)
+    data, wires, tg = circuits.aes_gcm(13, True)
+    data.load(ctx)
+    wp = data.load_witness_program(ctx, tg.input_targets())
+    data._wmap = None
+    data.prove_inputs(circuits.gcm_inputs(tg, 3, 1)[0], wp)
+    handles = [data._gpu_circuit] + [data.load_handle(c) for c in ctxs[1:]]
+    ThreadedShards(2).prove(ctxs[:2], handles[:2], data.proof_words, wires)
+    checked = 0
+    for c in ctxs:
+        n, bad = C.c_uint64(), C.c_uint64()
+        c.check(c.lib.p2g_debug_canary(c.handle, C.byref(n), C.byref(bad)))
+        assert bad.value == 0
+        checked += n.value
+    assert checked > 200
+    for d in (circuits.tiny_arith()[0], circuits.aes_gcm(13, True)[0], circuits.feistel_poseidon()[0], circuits.public_input_circuit()[0]):
+        d._gpu_circuit = None; d.ctx = None; d._wmap = None      # handles of the contexts closed below
+    for c in ctxs:
+        c.close()
