@@ -144,6 +144,16 @@ int32_t p2g_proof_from_bytes(const p2g_circuit_desc* desc, const uint8_t* bytes,
  * proof_out: flat u64 proof (layout in DESIGN.md, identical to the oracle's). */
 int32_t p2g_prove(p2g_ctx* ctx, const p2g_circuit* c, const uint64_t* wires_host, const uint64_t* public_inputs,
                   uint64_t* proof_out, size_t proof_cap_words, size_t* proof_words_out);
+/* ---- stages of the hot path on their own --------------------------------------------
+ * p2g_quotient = compute_quotient_polys + the commitment of the quotient chunks (plonk/prover.rs): wires / zs are whole
+ * batches of this circuit (p2g_commit_from_values*: 135 wire columns; Z, partial products and lookup polynomials in the
+ * prover's column order), challenges as plonky2's get_n_challenges returned them: betas / gammas / alphas
+ * [num_challenges], deltas [num_challenges][4] = (a, b, alpha, delta) per challenge (NULL without lookups).
+ * p2g_open = OpeningSet::new: f(zeta) of every polynomial of the given batches, in batch and column order, as (c0, c1). */
+int32_t p2g_quotient(p2g_ctx* ctx, const p2g_circuit* c, const p2g_batch* wires, const p2g_batch* zs, const uint64_t* public_inputs,
+                     const uint64_t* betas, const uint64_t* gammas, const uint64_t* deltas, const uint64_t* alphas,
+                     p2g_batch** quotient_out, uint64_t* cap_out);
+int32_t p2g_open(p2g_ctx* ctx, const p2g_batch* const* batches, uint32_t n_batches, const uint64_t zeta[2], uint64_t* openings_out);
 /* Batch of independent proofs (BASELINE config 5): proof i is proved on context i mod n_ctx, one host thread per
  * context inside the call; contexts may sit on one GPU (several proofs in flight) or on several.  circuits[t] must
  * have been loaded on ctxs[t].  status_out[i] receives each proof's return code; returns the first failure. */

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <stdlib.h>
 #include <thread>
+#include <functional>
 
 // ---------------------------------------------------------------------------------------------
 // host transcript: Challenger<F, PoseidonHash> (iop/challenger.rs)
@@ -388,6 +389,61 @@ struct Scratch {
     }
 };
 
+// Challenge-dependent constants of one proof.  deltas_flat: [nch][4] = (a, b, alpha, delta) per challenge (only with
+// lookups), alphas may be NULL (filled later by set_alphas).
+static void fill_consts(ProofConsts* pc, const p2g_circuit* C, const gl_t* betas, const gl_t* gammas, const gl_t* deltas_flat,
+                        const gl_t pi_hash[4]) {
+    const CircuitDev& cd = C->cd;
+    const size_t n = (size_t)1 << cd.logn;
+    memset(pc, 0, sizeof(ProofConsts));
+    for (int i = 0; i < cd.nch; i++) { pc->betas[i] = betas[i]; pc->gammas[i] = gammas[i]; }
+    if (cd.num_luts > 0)
+        for (int i = 0; i < cd.nch; i++) for (int j = 0; j < 4; j++) pc->deltas[i][j] = deltas_flat[4 * i + j];
+    for (int j = 0; j < cd.R; j++) {
+        pc->k_is[j] = C->k_is[j];
+        for (int i = 0; i < cd.nch; i++) pc->beta_kis[i][j] = gl_mul(pc->betas[i], C->k_is[j]);
+    }
+    memcpy(pc->pi_hash, pi_hash, 4 * sizeof(gl_t));
+    gl_t sn = gl_pow(7, n), w8 = gl_root_of_unity(cd.rate_bits), t = 1;
+    for (int s = 0; s < (1 << cd.rate_bits); s++) { pc->zh[s] = gl_sub(gl_mul(sn, t), 1); pc->zh_inv[s] = gl_inv(pc->zh[s]); t = gl_mul(t, w8); }
+    if (cd.num_luts > 0) for (int i = 0; i < cd.nch; i++) pc->delta_pow_slots[i] = gl_pow(pc->deltas[i][3], cd.lut_slots);
+}
+static void set_alphas(ProofConsts* pc, int nch, const gl_t* alphas) {
+    for (int i = 0; i < nch; i++) {
+        pc->alphas[i] = alphas[i];
+        gl_t p = 1;
+        for (int k = 0; k < 256; k++) { pc->alpha_pows[i][k] = p; p = gl_mul(p, alphas[i]); }
+    }
+}
+// compute_quotient_polys on (a shard of) the LDE domain: quotient kernel, per-coset inverse NTTs, optional
+// all-gather of the interpolants, cross-coset combination -> the nch * 8 chunk coefficient columns d_qc [nch*8][n]
+struct ShardHost;
+static int quotient_chunks(p2g_ctx* ctx, const p2g_circuit* C, ShardDev shd, const ProofConsts* d_pc, const gl_t* d_lut_evals,
+                           const p2g_batch* wb, const p2g_batch* zb, gl_t* d_qv, gl_t* d_qa, gl_t* d_qc,
+                           const std::function<int(const gl_t*, const gl_t**)>& gather_interpolants) {
+    const CircuitDev& cd = C->cd;
+    const int logn = cd.logn, nch = cd.nch;
+    const size_t n = (size_t)1 << logn, N_loc = (size_t)shd.blk_count << logn;
+    cudaStream_t st = ctx->st;
+    int rc;
+    bool has_pos = false;
+    for (const auto& g : C->gates) has_pos |= g.kind == P2G_GATE_POSEIDON;
+    P2G_COUNT_LAUNCH(1);
+    if (has_pos) quotient_kernel<true><<<(unsigned)((N_loc + 127) / 128), 128, 0, st>>>(cd, shd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
+    else quotient_kernel<false><<<(unsigned)((N_loc + 127) / 128), 128, 0, st>>>(cd, shd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
+    CU(cudaGetLastError());
+    const NttPlan* inv;
+    if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, logn, 0, &inv))) return rc;
+    if (ntt_launch(inv, d_qv, n, d_qa, n, nch * (int)shd.blk_count, 1, st)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
+    // the 8-point cross-coset combination needs every coset's interpolant: all-gather of 16 N / world bytes when sharded
+    const gl_t* d_qall = d_qa;
+    if (gather_interpolants && (rc = gather_interpolants(d_qa, &d_qall))) return rc;
+    dim3 grid((unsigned)((n + 255) / 256), nch);
+    P2G_COUNT_LAUNCH(1); quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, shd.blk_count, d_qall, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
+    CU(cudaGetLastError());
+    return P2G_OK;
+}
+
 // Coset shard of ONE proof over `world` GPUs (one process per GPU): this rank extends, hashes and evaluates only the
 // leaf blocks [blk_first, blk_first + blk_count); what the ranks need from each other -- Merkle cap entries, the
 // per-coset quotient interpolants, the last FRI layer, the query records -- goes through `exchange`, an all-gather
@@ -479,27 +535,19 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     ch.observe_many(wcap.data(), capw);
     ProofConsts* pc_host = (ProofConsts*)(ctx->pinned + ctx->pinned_words / 2);   // upper half of the pinned staging buffer (the lower half receives D2H results)
     static_assert(sizeof(ProofConsts) < 16384, "ProofConsts too large");
-    memset(pc_host, 0, sizeof(ProofConsts));
     gl_t deltas_flat[16] = {0};
-    for (int i = 0; i < nch; i++) pc_host->betas[i] = ch.get();
-    for (int i = 0; i < nch; i++) pc_host->gammas[i] = ch.get();
-    if (has_lookup) {
-        int k = 0;
-        for (int i = 0; i < nch; i++) deltas_flat[k++] = pc_host->betas[i];
-        for (int i = 0; i < nch; i++) deltas_flat[k++] = pc_host->gammas[i];
-        for (int i = 0; i < 2 * nch; i++) deltas_flat[k++] = ch.get();
-        for (int i = 0; i < nch; i++) for (int j = 0; j < 4; j++) pc_host->deltas[i][j] = deltas_flat[4 * i + j];
-    }
-    for (int j = 0; j < R; j++) {
-        pc_host->k_is[j] = C->k_is[j];
-        for (int i = 0; i < nch; i++) pc_host->beta_kis[i][j] = gl_mul(pc_host->betas[i], C->k_is[j]);
-    }
-    memcpy(pc_host->pi_hash, pi_hash, sizeof(pi_hash));
     {
-        gl_t sn = gl_pow(7, n), w8 = gl_root_of_unity(cd.rate_bits), t = 1;
-        for (int s = 0; s < (1 << cd.rate_bits); s++) { pc_host->zh[s] = gl_sub(gl_mul(sn, t), 1); pc_host->zh_inv[s] = gl_inv(pc_host->zh[s]); t = gl_mul(t, w8); }
+        gl_t betas[MAX_CH], gammas[MAX_CH];
+        for (int i = 0; i < nch; i++) betas[i] = ch.get();
+        for (int i = 0; i < nch; i++) gammas[i] = ch.get();
+        if (has_lookup) {      // get_n_challenges(4 * nch) with the first 2 * nch taken from (betas, gammas)
+            int k = 0;
+            for (int i = 0; i < nch; i++) deltas_flat[k++] = betas[i];
+            for (int i = 0; i < nch; i++) deltas_flat[k++] = gammas[i];
+            for (int i = 0; i < 2 * nch; i++) deltas_flat[k++] = ch.get();
+        }
+        fill_consts(pc_host, C, betas, gammas, deltas_flat, pi_hash);
     }
-    if (has_lookup) for (int i = 0; i < nch; i++) pc_host->delta_pow_slots[i] = gl_pow(pc_host->deltas[i][3], cd.lut_slots);
     ProofConsts* d_pc;
     CU(S.alloc_bytes((void**)&d_pc, sizeof(ProofConsts)));
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
@@ -535,10 +583,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     tm.mark();
     ch.observe_many(zcap.data(), capw);
     // pc_host (pinned) was consumed by the H2D copy above once commit_dev synchronised
-    for (int i = 0; i < nch; i++) {
-        pc_host->alphas[i] = ch.get();
-        gl_t p = 1;
-        for (int k = 0; k < 256; k++) { pc_host->alpha_pows[i][k] = p; p = gl_mul(p, pc_host->alphas[i]); }
+    {
+        gl_t alphas[MAX_CH];
+        for (int i = 0; i < nch; i++) alphas[i] = ch.get();
+        set_alphas(pc_host, nch, alphas);
     }
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
 
@@ -549,23 +597,13 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     if ((rc = S.alloc(&d_qa, (size_t)nch * N_loc))) return rc;
     if ((rc = S.alloc(&d_qc, (size_t)nch * N))) return rc;
     {
-        bool has_pos = false;
-        for (const auto& g : C->gates) has_pos |= g.kind == P2G_GATE_POSEIDON;
-        P2G_COUNT_LAUNCH(1);
-        if (has_pos) quotient_kernel<true><<<(unsigned)((N_loc + 127) / 128), 128, 0, st>>>(cd, shd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
-        else quotient_kernel<false><<<(unsigned)((N_loc + 127) / 128), 128, 0, st>>>(cd, shd, d_pc, d_lut_evals, C->d_gates, C->cs->lde, wb->lde, zb->lde, C->d_domain, C->d_l0inv, d_qv);
-    }
-    CU(cudaGetLastError());
-    {
-        const NttPlan* inv;
-        if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, logn, 0, &inv))) return rc;
-        if (ntt_launch(inv, d_qv, n, d_qa, n, nch * (int)bc, 1, st)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
-        // the 8-point cross-coset combination needs every coset's interpolant: all-gather of 16 N / world bytes
-        const gl_t* d_qall = d_qa;
-        if (sh) { if ((rc = gather(3, d_qa, (size_t)nch * N_loc * sizeof(gl_t)))) return rc; d_qall = sh->recv; }
-        dim3 grid((unsigned)((n + 255) / 256), nch);
-        P2G_COUNT_LAUNCH(1); quotient_combine_kernel<<<grid, 256, 0, st>>>(logn, nch, bc, d_qall, C->d_qtable, C->d_small, C->d_small + 8, d_qc);
-        CU(cudaGetLastError());
+        std::function<int(const gl_t*, const gl_t**)> gq;
+        if (sh) gq = [&](const gl_t* own, const gl_t** all) -> int {
+            int r = gather(3, own, (size_t)nch * N_loc * sizeof(gl_t));
+            *all = sh->recv;
+            return r;
+        };
+        if ((rc = quotient_chunks(ctx, C, shd, d_pc, d_lut_evals, wb, zb, d_qv, d_qa, d_qc, gq))) return rc;
     }
     DBG("quotient evaluated");
     if (ctx->keep_debug) {
@@ -894,6 +932,70 @@ extern "C" size_t p2g_shard_buffer_bytes(const p2g_circuit* c, uint32_t world) {
     size_t b = q > r ? q : r;
     return (b + 255) & ~(size_t)255;
 }
+// ---- staged entry points: the quotient stage and the openings on their own ------------
+extern "C" int32_t p2g_quotient(p2g_ctx* ctx, const p2g_circuit* C, const p2g_batch* wires, const p2g_batch* zs,
+                                const uint64_t* public_inputs, const uint64_t* betas, const uint64_t* gammas, const uint64_t* deltas,
+                                const uint64_t* alphas, p2g_batch** quotient_out, uint64_t* cap_out) {
+    if (!ctx || !C || !wires || !zs || !betas || !gammas || !alphas || !quotient_out) return P2G_E_BADARG;
+    const CircuitDev& cd = C->cd;
+    const p2g_circuit_desc& d = C->d;
+    if ((cd.num_luts > 0 && !deltas) || (d.num_public_inputs > 0 && !public_inputs)) return P2G_E_BADARG;
+    if (wires->ncols != (uint32_t)cd.W || zs->ncols != (uint32_t)cd.zs_cols || wires->log_n != (uint32_t)cd.logn || zs->log_n != (uint32_t)cd.logn ||
+        wires->blk_log != (uint32_t)cd.rate_bits || zs->blk_log != (uint32_t)cd.rate_bits || wires->rate_bits != (uint32_t)cd.rate_bits) {
+        ctx->err = "batches do not match the circuit (columns, degree, whole LDE domain)"; return P2G_E_BADARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)1 << (cd.logn + cd.rate_bits);
+    Scratch S(ctx);
+    int rc;
+    gl_t pi_hash[4];
+    host_hash_no_pad(public_inputs, (size_t)d.num_public_inputs, pi_hash);
+    ProofConsts* pc_host = (ProofConsts*)(ctx->pinned + ctx->pinned_words / 2);
+    fill_consts(pc_host, C, betas, gammas, deltas, pi_hash);
+    set_alphas(pc_host, cd.nch, alphas);
+    ProofConsts* d_pc; gl_t *d_lut_evals, *d_qv, *d_qa, *d_qc;
+    CU(S.alloc_bytes((void**)&d_pc, sizeof(ProofConsts)));
+    CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = S.alloc(&d_lut_evals, MAX_CH * 8))) return rc;
+    if (cd.num_luts > 0) {
+        P2G_COUNT_LAUNCH(1); lut_eval_kernel<<<dim3(cd.num_luts, cd.nch), 1024, 0, ctx->st>>>(cd, d_pc, C->d_lut_data, C->d_lut_off, C->d_lut_len, d_lut_evals);
+    }
+    if ((rc = S.alloc(&d_qv, (size_t)cd.nch * N))) return rc;
+    if ((rc = S.alloc(&d_qa, (size_t)cd.nch * N))) return rc;
+    if ((rc = S.alloc(&d_qc, (size_t)cd.nch * N))) return rc;
+    const ShardDev whole = {0u, 1u << cd.rate_bits};
+    if ((rc = quotient_chunks(ctx, C, whole, d_pc, d_lut_evals, wires, zs, d_qv, d_qa, d_qc, nullptr))) return rc;
+    if ((rc = commit_dev(ctx, d_qc, cd.nch * cd.qdf, cd.logn, cd.rate_bits, d.cap_height, false, quotient_out, true))) return rc;
+    if (cap_out) memcpy(cap_out, (*quotient_out)->cap_host.data(), (*quotient_out)->cap_host.size() * sizeof(gl_t));
+    return P2G_OK;
+}
+// OpeningSet::new for any set of batches of one degree: f(zeta) for every committed polynomial, batch by batch
+extern "C" int32_t p2g_open(p2g_ctx* ctx, const p2g_batch* const* batches, uint32_t n_batches, const uint64_t zeta[2], uint64_t* openings_out) {
+    if (!ctx || !batches || !n_batches || !zeta || !openings_out || zeta[0] >= GL_P || zeta[1] >= GL_P) return P2G_E_BADARG;
+    std::vector<const gl_t*> plist;
+    for (uint32_t b = 0; b < n_batches; b++) {
+        if (!batches[b] || batches[b]->log_n != batches[0]->log_n) { ctx->err = "batches of different degree"; return P2G_E_BADARG; }
+        for (uint32_t c = 0; c < batches[b]->ncols; c++) plist.push_back(batches[b]->coeffs + (size_t)c * batches[b]->n());
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = batches[0]->n(), tot = plist.size();
+    Scratch S(ctx);
+    const gl_t** d_plist; gl_t *d_zp, *d_open; int rc;
+    CU(S.alloc_bytes((void**)&d_plist, tot * sizeof(gl_t*)));
+    CU(cudaMemcpyAsync(d_plist, plist.data(), tot * sizeof(gl_t*), cudaMemcpyHostToDevice, ctx->st));
+    if ((rc = S.alloc(&d_zp, 2 * n))) return rc;
+    if ((rc = S.alloc(&d_open, 2 * tot))) return rc;
+    Pow2Table t0;
+    t0.p[0] = ext_make(zeta[0], zeta[1]);
+    for (int b = 1; b < 32; b++) t0.p[b] = ext_mul(t0.p[b - 1], t0.p[b - 1]);
+    P2G_COUNT_LAUNCH(1); ext_powers_kernel2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(t0, n, d_zp);
+    P2G_COUNT_LAUNCH(1); eval_polys_kernel<<<(unsigned)tot, 256, 0, ctx->st>>>(d_plist, d_zp, n, d_open);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(openings_out, d_open, 2 * tot * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(ctx_wait(ctx));               // the host vector of pointers dies with this frame
+    return P2G_OK;
+}
+
 // p2g_prove for a batch: proof i runs on context i mod n_ctx, one host thread per context, so the latency-bound
 // parts of one proof (Fiat-Shamir round trips, tree tops) overlap the heavy kernels of the others
 extern "C" int32_t p2g_prove_batch(p2g_ctx* const* ctxs, const p2g_circuit* const* circuits, uint32_t n_ctx,

@@ -490,3 +490,47 @@ def test_guard_bands_see_no_out_of_bounds_write(oracle):
         d._gpu_circuit = None; d.ctx = None; d._wmap = None      # handles of the contexts closed below
     for c in ctxs:
         c.close()
+
+
+def test_staged_quotient_and_openings(gpu_ctx, oracle):
+    """p2g_quotient / p2g_open on their own: fed with the commitments and challenges of a real proof they return
+    that proof's quotient chunks, quotient cap and openings"""
+    from plonky2_aes_b200.host.polynomial_batch import PolynomialBatch
+    from plonky2_aes_b200.host.proof import Proof
+    lib = gpu_ctx.lib
+    for data, wires, pi in (circuits.aes_gcm(13, True)[:2] + (None,), circuits.public_input_circuit()):
+        data.load(gpu_ctx)
+        gpu_ctx.check(lib.p2g_set_timing(gpu_ctx.handle, 2))
+        proof = data.prove_wires(wires, pi)
+        tr = ffi.Transcript()
+        gpu_ctx.check(lib.p2g_last_transcript(gpu_ctx.handle, C.byref(tr)))
+        d = data.descriptor()
+        nch = d.num_challenges
+        nlp = 0 if d.num_luts == 0 else -(-(d.num_routed_wires // 2) // (d.quotient_degree_factor - 1)) + 1
+        zs = np.empty((nch * (1 + d.num_partial_products + nlp), data.n), dtype=np.uint64)
+        qc = np.empty((nch * d.quotient_degree_factor, data.n), dtype=np.uint64)
+        gpu_ctx.check(lib.p2g_last_zs_values(gpu_ctx.handle, zs.ctypes.data))
+        gpu_ctx.check(lib.p2g_last_quotient_chunks(gpu_ctx.handle, qc.ctypes.data))
+        gpu_ctx.check(lib.p2g_set_timing(gpu_ctx.handle, 0))
+        wb = PolynomialBatch.from_values(gpu_ctx, wires)
+        zb = PolynomialBatch.from_values(gpu_ctx, zs)
+        pr = Proof(proof, d)
+        assert np.array_equal(wb.cap.ravel(), pr["wires_cap"]) and np.array_equal(zb.cap.ravel(), pr["plonk_zs_partial_products_cap"])
+        u64 = lambda xs, k: np.array(list(xs)[:k], dtype=np.uint64)
+        betas, gammas, alphas, deltas = u64(tr.betas, nch), u64(tr.gammas, nch), u64(tr.alphas, nch), u64(tr.deltas, 4 * nch)
+        h = C.c_void_p()
+        cap = np.empty((16, 4), dtype=np.uint64)
+        pin = np.ascontiguousarray(pi, dtype=np.uint64) if pi is not None else None
+        gpu_ctx.check(lib.p2g_quotient(gpu_ctx.handle, data._gpu_circuit, wb.handle, zb.handle, pin.ctypes.data if pin is not None else None,
+                                       betas.ctypes.data, gammas.ctypes.data, deltas.ctypes.data if d.num_luts else None, alphas.ctypes.data,
+                                       C.byref(h), cap.ctypes.data))
+        assert np.array_equal(cap.ravel(), pr["quotient_polys_cap"])
+        qb = PolynomialBatch(gpu_ctx, h, qc.shape[0], data.degree_bits, 3, 4, cap)
+        assert np.array_equal(qb.coeffs(), qc)
+        # openings at zeta of the wires and quotient batches
+        zeta = np.array(list(tr.zeta), dtype=np.uint64)
+        out = np.empty((wb.ncols + qb.ncols, 2), dtype=np.uint64)
+        gpu_ctx.check(lib.p2g_open(gpu_ctx.handle, (C.c_void_p * 2)(wb.handle, qb.handle), 2, zeta.ctypes.data, out.ctypes.data))
+        assert np.array_equal(out[:wb.ncols].ravel(), pr["openings.wires"])
+        assert np.array_equal(out[wb.ncols:].ravel(), pr["openings.quotient_polys"])
+        wb.free(); zb.free(); qb.free()
