@@ -113,27 +113,7 @@ merkle_leaves_kernel(const gl_t* __restrict__ data, size_t col_stride, uint32_t 
     }
 }
 
-// finishes levels (from_level, L] with one block; level `from_level` is complete in global memory
-__global__ void __launch_bounds__(1024)
-merkle_top_kernel(gl_t* digests, gl_t* cap, uint32_t log_leaves, uint32_t L, uint32_t from_level) {
-    for (uint32_t lv = from_level + 1; lv <= L; lv++) {
-        const gl_t* src = level_ptr(digests, cap, log_leaves, L, lv - 1);
-        gl_t* dst = level_ptr(digests, cap, log_leaves, L, lv);
-        size_t cnt = (size_t)1 << (log_leaves - lv);
-        for (size_t t = threadIdx.x; t < cnt; t += blockDim.x) {
-            gl_t l[4], r[4], o[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) { l[i] = src[8 * t + i]; r[i] = src[8 * t + 4 + i]; }
-            poseidon_two_to_one(l, r, o);
-#pragma unroll
-            for (int i = 0; i < 4; i++) dst[4 * t + i] = o[i];
-        }
-        __threadfence_block();
-        __syncthreads();
-    }
-}
-
-// one grid-wide level (used when the level is too wide for the single-block finisher)
+// one grid-wide level, thread per node
 __global__ void __launch_bounds__(POS_BLOCK, POS_MINB)
 merkle_level_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, size_t cnt) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
