@@ -298,11 +298,11 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
     const double A[144] = POSEIDON_PAIR_A_INIT;
     double al[12], ah[12];
-#pragma unroll
     // pos_lane_zero(): the table index is made to look per-thread so the biases arrive by LDC straight in
     // vector registers; a uniform index is loaded to uniform registers and then costs two moves per
     // double (52 of the 753 instructions of this loop body)
     const int pz = 12 * pair + zero;
+#pragma unroll
     for (int r = 0; r < 12; r++) { al[r] = POSEIDON_PAIRK_LO[pz + r]; ah[r] = POSEIDON_PAIRK_HI[pz + r]; }
     const int row_a = 5 + 2 * pair;                       // constants between the two rounds
     double tl = POSEIDON_RCD_LO[12 * row_a + zero], th = POSEIDON_RCD_HI[12 * row_a + zero];

@@ -32,7 +32,7 @@ def _compare(gb, ob, check_levels=True):
     assert np.array_equal(gb.cap, ob.tree.cap)
 
 
-@pytest.mark.parametrize("ncols,log_n", [(1, 1), (3, 2), (4, 4), (5, 5), (9, 6), (16, 7), (34, 9), (2, 10), (7, 12), (3, 13), (3, 14), (2, 16)])
+@pytest.mark.parametrize("ncols,log_n", [(1, 1), (3, 2), (4, 4), (5, 5), (9, 6), (16, 7), (34, 9), (2, 10), (7, 12), (3, 13), (3, 14), (2, 16), (5, 17)])
 def test_from_values_small(gpu_ctx, oracle, ncols, log_n):
     cols = _cols(10 + log_n, ncols, log_n, edge=True)
     gb = PolynomialBatch.from_values(gpu_ctx, cols, 3, min(4, log_n + 3))
