@@ -130,23 +130,6 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 #ifndef P2G_MDS_SPLIT
 #define P2G_MDS_SPLIT 1
 #endif
-// P2G_PARK > 0: state words that are not needed for a while are parked in shared memory (one 64-bit slot per
-// word and thread, [word][thread] so a warp's accesses are conflict-free) instead of being held in registers
-// across the stretch where the 24 FP64 accumulators are live: S-box outputs 6..11 of a full round until their
-// column is accumulated, words 12 - P2G_PARK..11 of a partial pair until they enter the dense product.  This is
-// what lets the kernels run at 72 registers (7 blocks of 128 threads per SM instead of 24 warps).
-#ifndef P2G_PARK
-#define P2G_PARK 0
-#endif
-#ifndef P2G_PARK_THREADS
-#define P2G_PARK_THREADS 256
-#endif
-#if P2G_PARK > 0
-__device__ __forceinline__ volatile gl_t* pos_park_slot(int k) {
-    __shared__ gl_t pos_park[6][P2G_PARK_THREADS];
-    return &pos_park[k][threadIdx.x];
-}
-#endif
 
 #if P2G_MDS_SPLIT
 // Split-circulant form of the same layer.  The MDS matrix is circ(C) (+ 8 on entry [0][0]), i.e.
@@ -165,21 +148,11 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
         apl[r] = POSEIDON_RCS_LO[12 * next_row + r]; aml[r] = POSEIDON_RCS_LO[12 * next_row + 6 + r];
         aph[r] = POSEIDON_RCS_HI[12 * next_row + r]; amh[r] = POSEIDON_RCS_HI[12 * next_row + 6 + r];
     }
-#if P2G_PARK > 0
-    if (SBOX_ALL) {
-#pragma unroll
-        for (int j = 0; j < 6; j++) *pos_park_slot(j) = poseidon_sbox(s[j + 6]);
-    }
-#endif
 #pragma unroll
     for (int jj = 0; jj < 6; jj++) {
         const int j = SBOX_ALL ? jj : (jj + 1) % 6;             // pair (0, 6) last in partial rounds
         const gl_t v0 = (SBOX_ALL || j == 0) ? poseidon_sbox(s[j]) : s[j];
-#if P2G_PARK > 0
-        const gl_t v1 = SBOX_ALL ? *pos_park_slot(j) : s[j + 6];
-#else
         const gl_t v1 = SBOX_ALL ? poseidon_sbox(s[j + 6]) : s[j + 6];
-#endif
         const double x0l = (double)(uint32_t)v0, x0h = (double)(uint32_t)(v0 >> 32);
         const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
         const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
@@ -306,19 +279,11 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
     for (int r = 0; r < 12; r++) { al[r] = POSEIDON_PAIRK_LO[pz + r]; ah[r] = POSEIDON_PAIRK_HI[pz + r]; }
     const int row_a = 5 + 2 * pair;                       // constants between the two rounds
     double tl = POSEIDON_RCD_LO[12 * row_a + zero], th = POSEIDON_RCD_HI[12 * row_a + zero];
-#if P2G_PARK > 0
-#pragma unroll
-    for (int k = 0; k < P2G_PARK; k++) *pos_park_slot(k) = s[12 - P2G_PARK + k];
-#endif
     const gl_t y0 = poseidon_sbox(s[0]);
 #pragma unroll
     for (int jj = 0; jj < 12; jj++) {
         const int j = (jj + 1) % 12;                      // word 0 last: its S-box chain hides behind the others
-#if P2G_PARK > 0
-        const gl_t v = j == 0 ? y0 : j >= 12 - P2G_PARK ? *pos_park_slot(j - (12 - P2G_PARK)) : s[j];
-#else
         const gl_t v = j == 0 ? y0 : s[j];
-#endif
         const double xl = (double)(uint32_t)v, xh = (double)(uint32_t)(v >> 32);
 #ifdef P2G_DIAG_NO_MDS
         al[j] = __dadd_rn(al[j], xl); ah[j] = __dadd_rn(ah[j], xh);
