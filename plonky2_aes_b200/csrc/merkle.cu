@@ -165,7 +165,8 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
     if (cap_height > log_leaves) return -2;
     const uint32_t L = log_leaves - cap_height;
     const size_t num_leaves = (size_t)1 << log_leaves;
-    const uint32_t COOP_MAX = 4096;     // levels (or leaf sets) this narrow use the 12-lane permutation
+    // levels (or leaf sets) this narrow use the 12-lane permutation; P2G_COOP_MAX: A/B knob
+    static const uint32_t COOP_MAX = [] { const char* e = getenv("P2G_COOP_MAX"); return e ? (uint32_t)atoi(e) : 4096u; }();
     uint32_t lv;
     if (!col_major && leaf_len > 4 && num_leaves <= COOP_MAX) {
         gl_t* d0 = L == 0 ? cap : digests;
