@@ -35,7 +35,7 @@ extern "C" int32_t p2g_ctx_create(int32_t device, p2g_ctx** out) {
     bool ok = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) == cudaSuccess;
     if (ok) {
         const char* mode = getenv("P2G_SYNC");
-        ctx->wait_mode = !mode ? 2 : strcmp(mode, "block") == 0 ? 1 : strcmp(mode, "spin") == 0 ? 0 : 2;
+        ctx->wait_mode = !mode ? 2 : strcmp(mode, "block") == 0 ? 1 : strcmp(mode, "spin") == 0 ? 0 : strcmp(mode, "sleep") == 0 ? 3 : 2;
         ok = cudaEventCreateWithFlags(&ctx->wait_ev, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
     }
     if (ok) {

@@ -1,6 +1,8 @@
 // Internal context/batch structures of libp2gpu.so.
 #pragma once
 #include <sched.h>
+#include <time.h>
+#include <sys/prctl.h>
 #include "common.h"
 #include "../../include/p2gpu.h"
 #include <map>
@@ -39,7 +41,7 @@ struct p2g_ctx {
     bool keep_debug;
     float commit_ms[3];     // last commit: inverse NTT, coset LDE, Merkle (when timing is on)
     cudaEvent_t wait_ev;    // blocking-sync event: host threads sleep while they wait for the stream
-    int wait_mode;          // 0 spin (cudaStreamSynchronize), 1 blocking-sync event, 2 poll + sched_yield
+    int wait_mode;          // 0 spin (cudaStreamSynchronize), 1 blocking-sync event, 2 poll + sched_yield, 3 poll + 15 us sleeps
     // P2G_CANARY=1 (debug): every ctx_alloc block gets a guard band behind it that ctx_free checks -- the
     // out-of-bounds-write detector used where compute-sanitizer is not available (tests/test_gpu_prove.py)
     bool canary;
@@ -60,6 +62,13 @@ static inline cudaError_t ctx_wait(p2g_ctx* ctx) {
     if (ctx->wait_mode == 2) {          // P2G_SYNC=yield: poll, giving the core away between polls
         cudaError_t e;
         while ((e = cudaStreamQuery(ctx->st)) == cudaErrorNotReady) sched_yield();
+        return e;
+    }
+    if (ctx->wait_mode == 3) {          // P2G_SYNC=sleep: poll with short sleeps -- the core is free between polls
+        static thread_local bool slack_set = false;
+        if (!slack_set) { prctl(PR_SET_TIMERSLACK, 2000UL, 0, 0, 0); slack_set = true; }   // 2 us instead of the default 50 us
+        cudaError_t e;
+        while ((e = cudaStreamQuery(ctx->st)) == cudaErrorNotReady) { struct timespec ts = {0, 15000}; nanosleep(&ts, nullptr); }
         return e;
     }
     cudaError_t e = cudaEventRecord(ctx->wait_ev, ctx->st);
