@@ -106,8 +106,14 @@ witgen_kernel(WgProg P, const gl_t* __restrict__ in_vals, uint32_t count, gl_t* 
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= count) return;
-    // volatile: values written by other lanes are read after a __syncwarp(), never from a stale register
+    // plain (L1-cached) accesses: a value written by another lane is read only after the __syncwarp() that ends its
+    // level, which orders memory among the lanes of the warp (and is a compiler barrier); volatile accesses would go to
+    // L2 every time and triple the latency of the level chain
+#ifdef P2G_WITGEN_VOLATILE
     volatile gl_t* ext = ext_all + (size_t)w * P.ext_total;
+#else
+    gl_t* ext = ext_all + (size_t)w * P.ext_total;
+#endif
     int bad = 0;
     for (uint32_t i = lane; i < P.num_inputs; i += 32) {
         const gl_t v = in_vals[(size_t)w * P.num_inputs + i];
@@ -156,10 +162,10 @@ witgen_kernel(WgProg P, const gl_t* __restrict__ in_vals, uint32_t count, gl_t* 
                 for (int i = 0; i < 12; i++) in[i] = ext[pr[1 + i]];
                 wg_poseidon_gate(in, trace);
                 for (int i = 0; i < 12; i++) {             // outputs (checked against values already set)
-                    volatile gl_t* o = ext + pr[13 + i];
+                    auto* o = ext + pr[13 + i];
                     if (kf & WG_CHECK0) { if (*o != trace[i]) bad |= 4; } else *o = trace[i];
                 }
-                volatile gl_t* tr = ext + P.ext_pos + (size_t)111 * s0;
+                auto* tr = ext + P.ext_pos + (size_t)111 * s0;
                 for (int i = 0; i < 111; i++) tr[i] = trace[12 + i];
                 continue;
             }
