@@ -130,6 +130,19 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 #ifndef P2G_MDS_SPLIT
 #define P2G_MDS_SPLIT 1
 #endif
+// u32 -> double.  I2F.F64.U32 occupies the FP64 pipe for 6.4 cycles per warp (tools/microbench/pos_parts.cu), a
+// DADD for 2.07: the "magic" form builds 2^52 + w from the raw words (high word 0x43300000) and subtracts 2^52.
+// P2G_CVT_MAGIC bit 0: partial-round pairs (FP64-bound), bit 1: full rounds (integer-bound).
+#ifndef P2G_CVT_MAGIC
+#define P2G_CVT_MAGIC 0
+#endif
+#ifndef P2G_SBOX_LAG
+#define P2G_SBOX_LAG 0
+#endif
+__device__ __forceinline__ double pos_u2d_magic(uint32_t w) {
+    return __dsub_rn(__hiloint2double(0x43300000, (int)w), 4503599627370496.0);
+}
+template <bool MAGIC> __device__ __forceinline__ double pos_u2d(uint32_t w) { return MAGIC ? pos_u2d_magic(w) : (double)w; }
 
 #if P2G_MDS_SPLIT
 // Split-circulant form of the same layer.  The MDS matrix is circ(C) (+ 8 on entry [0][0]), i.e.
@@ -153,10 +166,21 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
         const int j = SBOX_ALL ? jj : (jj + 1) % 6;             // pair (0, 6) last in partial rounds
         const gl_t v0 = (SBOX_ALL || j == 0) ? poseidon_sbox(s[j]) : s[j];
         const gl_t v1 = SBOX_ALL ? poseidon_sbox(s[j + 6]) : s[j + 6];
-        const double x0l = (double)(uint32_t)v0, x0h = (double)(uint32_t)(v0 >> 32);
-        const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
+#if (P2G_CVT_MAGIC & 4)
+        // m = (2^52 + a) - (2^52 + b) needs no conversion at all; p = m + 2 b
+        const double BIAS0 = 4503599627370496.0;
+        const double M0l = __hiloint2double(0x43300000, (int)(uint32_t)v0), M0h = __hiloint2double(0x43300000, (int)(uint32_t)(v0 >> 32));
+        const double M1l = __hiloint2double(0x43300000, (int)(uint32_t)v1), M1h = __hiloint2double(0x43300000, (int)(uint32_t)(v1 >> 32));
+        const double ml = __dsub_rn(M0l, M1l), mh = __dsub_rn(M0h, M1h);
+        const double x1l = __dsub_rn(M1l, BIAS0), x1h = __dsub_rn(M1h, BIAS0);
+        const double pl = __fma_rn(x1l, 2., ml), ph = __fma_rn(x1h, 2., mh);
+        const double x0l = (j == 0) ? __dsub_rn(M0l, BIAS0) : 0., x0h = (j == 0) ? __dsub_rn(M0h, BIAS0) : 0.;
+#else
+        const double x0l = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)v0), x0h = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)(v0 >> 32));
+        const double x1l = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)v1), x1h = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)(v1 >> 32));
         const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
         const double ph = __dadd_rn(x0h, x1h), mh = __dsub_rn(x0h, x1h);
+#endif
 #ifdef P2G_DIAG_NO_MDS
         apl[j] = __dadd_rn(apl[j], pl); aph[j] = __dadd_rn(aph[j], ph); aml[j] = __dadd_rn(aml[j], ml); amh[j] = __dadd_rn(amh[j], mh);
 #else
@@ -172,6 +196,15 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
             apl[0] = __fma_rn(x0l, 4., apl[0]); aml[0] = __fma_rn(x0l, 4., aml[0]);
             aph[0] = __fma_rn(x0h, 4., aph[0]); amh[0] = __fma_rn(x0h, 4., amh[0]);
         }
+#if P2G_SBOX_LAG
+        // Scheduling aid, no arithmetic effect: the S-box inputs of step jj + LAG are made to depend on an accumulator
+        // of this step (OR with the sign bit of a positive double, i.e. with 0), so ptxas cannot hoist all twelve
+        // S-boxes in front of the FP64 block and the DFMAs of one step issue between the integer instructions of the next.
+        if (SBOX_ALL && jj + P2G_SBOX_LAG < 6) {
+            const uint32_t z0 = (uint32_t)__double2hiint(apl[5]) & 0x80000000u, z1 = (uint32_t)__double2hiint(amh[5]) & 0x80000000u;
+            s[jj + P2G_SBOX_LAG] |= z0; s[jj + P2G_SBOX_LAG + 6] |= z1;
+        }
+#endif
     }
     const double BIAS = 4503599627370496.0;                      // 2^52
 #pragma unroll
@@ -284,7 +317,7 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
     for (int jj = 0; jj < 12; jj++) {
         const int j = (jj + 1) % 12;                      // word 0 last: its S-box chain hides behind the others
         const gl_t v = j == 0 ? y0 : s[j];
-        const double xl = (double)(uint32_t)v, xh = (double)(uint32_t)(v >> 32);
+        const double xl = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)v), xh = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)(v >> 32));
 #ifdef P2G_DIAG_NO_MDS
         al[j] = __dadd_rn(al[j], xl); ah[j] = __dadd_rn(ah[j], xh);
 #else
@@ -298,7 +331,7 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
         tl = __fma_rn(xl, m0j, tl); th = __fma_rn(xh, m0j, th);
     }
     const gl_t z0 = poseidon_sbox(pos_readout(tl, th));
-    const double zl = (double)(uint32_t)z0, zh = (double)(uint32_t)(z0 >> 32);
+    const double zl = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)z0), zh = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)(z0 >> 32));
 #pragma unroll
     for (int r = 0; r < 12; r++) {
         const double mr0 = C[(12 - r) % 12] + (r == 0 ? 8. : 0.);
