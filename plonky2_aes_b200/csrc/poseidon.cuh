@@ -300,6 +300,81 @@ __device__ __forceinline__ int pos_lane_zero() {
 // the products with 32-bit halves are still exact on the FP64 pipe (row sums < 2^49), and the 11
 // words that skip the S-box are read out of the accumulators and converted back once per TWO rounds:
 // 336 FP64 instructions and 13 readouts per pair instead of 408 and 24.
+#ifndef P2G_PAIR_SPLIT
+#define P2G_PAIR_SPLIT 1
+#endif
+#if P2G_PAIR_SPLIT
+// Split form of the pair.  From  u = M t' + cB,  t' = t + (z - t0) e0,  t = M s' + cA:
+//     u = M^2 s' + (z - t0) col0(M) + (M cA + cB),
+// and with M = circ(C) + 8 E00:  M^2 = circ(C2) + 8 col0(circ) e0^T + 8 e0 row0(circ) + 64 E00  (C2 = C cyclically
+// convolved with itself), so
+//     u = circ(C2) s' + 8 cc y0 + cm (z - t0) + 8 (t0 - cA_0) e0 + K'
+//       = circ(C2) s' + cc (8 y0 + z - t0) + 8 (z - cA_0) e0 + K',          cc = col0(circ), cm = col0(M), y0 = s'_0.
+// circ(C2) is circulant and splits like the full-round layer (72 products per 32-bit half instead of 144); the
+// rank-one term costs 24 products and word 0 two more: 260 FP64 instructions per pair instead of 336.  The
+// constants, the read-out offset and an offset = 0 (mod p) that keeps the accumulators positive although
+// 8 y0 + z - t0 can be negative are in POSEIDON_PAIRS_* (tools/gen_poseidon_f64.py, which emulates this function
+// exactly).  z needs no I2F: (2^52 + z_half) is built from the raw words and (2^52 + z_half) - (biased t
+// accumulator) is exact.
+__device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int zero) {
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    const double C2[12] = POSEIDON_C2_INIT;
+    const double BIAS = 4503599627370496.0;               // 2^52
+    double apl[6], aml[6], aph[6], amh[6];
+    const int pz = 12 * pair + zero;                      // per-thread looking index: LDC instead of LDCU + moves
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        apl[r] = POSEIDON_PAIRS_LO[pz + r]; aml[r] = POSEIDON_PAIRS_LO[pz + 6 + r];
+        aph[r] = POSEIDON_PAIRS_HI[pz + r]; amh[r] = POSEIDON_PAIRS_HI[pz + 6 + r];
+    }
+    const int row_a = 5 + 2 * pair;                       // constants between the two rounds
+    double tl = POSEIDON_RCD_LO[12 * row_a + zero], th = POSEIDON_RCD_HI[12 * row_a + zero];
+    const gl_t y0 = poseidon_sbox(s[0]);
+    double y0l8 = 0., y0h8 = 0.;
+#pragma unroll
+    for (int jj = 0; jj < 6; jj++) {
+        const int j = (jj + 1) % 6;                       // words (0, 6) last: the S-box chain of word 0 hides behind the others
+        const gl_t v0 = j == 0 ? y0 : s[j], v1 = s[j + 6];
+        const double x0l = (double)(uint32_t)v0, x0h = (double)(uint32_t)(v0 >> 32);
+        const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
+        const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
+        const double ph = __dadd_rn(x0h, x1h), mh = __dsub_rn(x0h, x1h);
+#ifdef P2G_DIAG_NO_MDS
+        apl[j] = __dadd_rn(apl[j], pl); aph[j] = __dadd_rn(aph[j], ph); aml[j] = __dadd_rn(aml[j], ml); amh[j] = __dadd_rn(amh[j], mh);
+#else
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const double a = C2[(j - r + 12) % 12], b = C2[(j + 6 - r + 12) % 12];
+            const double Pc = 0.5 * (a + b), Nc = 0.5 * (a - b);
+            apl[r] = __fma_rn(pl, Pc, apl[r]); aml[r] = __fma_rn(ml, Nc, aml[r]);
+            aph[r] = __fma_rn(ph, Pc, aph[r]); amh[r] = __fma_rn(mh, Nc, amh[r]);
+        }
+#endif
+        const double m0 = C[j] + (j == 0 ? 8. : 0.), m1 = C[j + 6];          // row 0 of M
+        tl = __fma_rn(x0l, m0, tl); th = __fma_rn(x0h, m0, th);
+        tl = __fma_rn(x1l, m1, tl); th = __fma_rn(x1h, m1, th);
+        if (j == 0) { y0l8 = x0l; y0h8 = x0h; }
+    }
+    const gl_t z0 = poseidon_sbox(pos_readout(tl, th));
+    // while that S-box runs: recombine the split accumulators
+    double yl[12], yh[12];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        yl[r] = __dadd_rn(apl[r], aml[r]); yl[r + 6] = __dadd_rn(__dsub_rn(apl[r], aml[r]), BIAS);
+        yh[r] = __dadd_rn(aph[r], amh[r]); yh[r + 6] = __dadd_rn(__dsub_rn(aph[r], amh[r]), BIAS);
+    }
+    const double mzl = __hiloint2double(0x43300000, (int)(uint32_t)z0), mzh = __hiloint2double(0x43300000, (int)(uint32_t)(z0 >> 32));
+    const double gl = __fma_rn(y0l8, 8., __dsub_rn(mzl, tl)), gh = __fma_rn(y0h8, 8., __dsub_rn(mzh, th));   // 8 y0 + z - t0 (+ E)
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        const double cr = C[(12 - r) % 12];                                   // cc[r]
+        yl[r] = __fma_rn(gl, cr, yl[r]); yh[r] = __fma_rn(gh, cr, yh[r]);
+    }
+    yl[0] = __fma_rn(__dsub_rn(mzl, BIAS), 8., yl[0]); yh[0] = __fma_rn(__dsub_rn(mzh, BIAS), 8., yh[0]);
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = pos_readout(yl[r], yh[r]);
+}
+#else
 __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int zero) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
     const double A[144] = POSEIDON_PAIR_A_INIT;
@@ -340,6 +415,7 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
 #pragma unroll
     for (int r = 0; r < 12; r++) s[r] = pos_readout(al[r], ah[r]);
 }
+#endif  // P2G_PAIR_SPLIT
 __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonical
     gl_t s = a + c;
     return s < a ? s + GL_EPS : s;
