@@ -130,28 +130,17 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 #ifndef P2G_MDS_SPLIT
 #define P2G_MDS_SPLIT 1
 #endif
-// u32 -> double.  I2F.F64.U32 occupies the FP64 pipe for 6.4 cycles per warp (tools/microbench/pos_parts.cu), a
-// DADD for 2.07: the "magic" form builds 2^52 + w from the raw words (high word 0x43300000) and subtracts 2^52.
-// P2G_CVT_MAGIC bit 0: partial-round pairs (FP64-bound), bit 1: full rounds (integer-bound).
-#ifndef P2G_CVT_MAGIC
-#define P2G_CVT_MAGIC 0
-#endif
-#ifndef P2G_SBOX_LAG
-#define P2G_SBOX_LAG 0
-#endif
-__device__ __forceinline__ double pos_u2d_magic(uint32_t w) {
-    return __dsub_rn(__hiloint2double(0x43300000, (int)w), 4503599627370496.0);
-}
-template <bool MAGIC> __device__ __forceinline__ double pos_u2d(uint32_t w) { return MAGIC ? pos_u2d_magic(w) : (double)w; }
 
 #if P2G_MDS_SPLIT
 // Split-circulant form of the same layer.  The MDS matrix is circ(C) (+ 8 on entry [0][0]), i.e.
 // [[A, B], [B, A]] in 6x6 blocks, so with X+ = x_lo + x_hi and X- = x_lo - x_hi (word halves j, j+6)
 //     y_lo = ((A+B)/2) X+  +  ((A-B)/2) X-,      y_hi = ((A+B)/2) X+  -  ((A-B)/2) X-
 // which is 72 products per 32-bit half instead of 144 (204 FP64-pipe instructions per round
-// instead of 290).  (A+-B)/2 are multiples of 1/2, so the two accumulators are biased by 2^51
-// (ulp 1/2, POSEIDON_RCS_*): every partial sum stays exact, acc+ + acc- lands in [2^52, 2^53)
-// as 2^52 + integer, and acc+ - acc- is a plain non-negative integer that gets its 2^52 added.
+// instead of 290).  For this matrix (A+-B)/2 are integers, so acc+ is biased by 2^52 and acc- is a plain signed
+// integer (POSEIDON_RCS_*): acc+ + acc- and acc+ - acc- both land in [2^52, 2^53) as 2^52 + word, two FP64
+// instructions per pair of words (a third one re-biased the difference before: -12 per round).  I2F.F64.U32
+// stays: building 2^52 + w from the raw words and subtracting 2^52 trades one I2F for a DADD plus 1.5 moves and
+// measured slower (profiles/r2_poseidon_magic_lag_experiments.jsonl).
 template <bool SBOX_ALL>
 __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
@@ -166,21 +155,10 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
         const int j = SBOX_ALL ? jj : (jj + 1) % 6;             // pair (0, 6) last in partial rounds
         const gl_t v0 = (SBOX_ALL || j == 0) ? poseidon_sbox(s[j]) : s[j];
         const gl_t v1 = SBOX_ALL ? poseidon_sbox(s[j + 6]) : s[j + 6];
-#if (P2G_CVT_MAGIC & 4)
-        // m = (2^52 + a) - (2^52 + b) needs no conversion at all; p = m + 2 b
-        const double BIAS0 = 4503599627370496.0;
-        const double M0l = __hiloint2double(0x43300000, (int)(uint32_t)v0), M0h = __hiloint2double(0x43300000, (int)(uint32_t)(v0 >> 32));
-        const double M1l = __hiloint2double(0x43300000, (int)(uint32_t)v1), M1h = __hiloint2double(0x43300000, (int)(uint32_t)(v1 >> 32));
-        const double ml = __dsub_rn(M0l, M1l), mh = __dsub_rn(M0h, M1h);
-        const double x1l = __dsub_rn(M1l, BIAS0), x1h = __dsub_rn(M1h, BIAS0);
-        const double pl = __fma_rn(x1l, 2., ml), ph = __fma_rn(x1h, 2., mh);
-        const double x0l = (j == 0) ? __dsub_rn(M0l, BIAS0) : 0., x0h = (j == 0) ? __dsub_rn(M0h, BIAS0) : 0.;
-#else
-        const double x0l = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)v0), x0h = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)(v0 >> 32));
-        const double x1l = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)v1), x1h = pos_u2d<(P2G_CVT_MAGIC & 2) != 0>((uint32_t)(v1 >> 32));
+        const double x0l = (double)(uint32_t)v0, x0h = (double)(uint32_t)(v0 >> 32);
+        const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
         const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
         const double ph = __dadd_rn(x0h, x1h), mh = __dsub_rn(x0h, x1h);
-#endif
 #ifdef P2G_DIAG_NO_MDS
         apl[j] = __dadd_rn(apl[j], pl); aph[j] = __dadd_rn(aph[j], ph); aml[j] = __dadd_rn(aml[j], ml); amh[j] = __dadd_rn(amh[j], mh);
 #else
@@ -196,21 +174,13 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
             apl[0] = __fma_rn(x0l, 4., apl[0]); aml[0] = __fma_rn(x0l, 4., aml[0]);
             aph[0] = __fma_rn(x0h, 4., aph[0]); amh[0] = __fma_rn(x0h, 4., amh[0]);
         }
-#if P2G_SBOX_LAG
-        // Scheduling aid, no arithmetic effect: the S-box inputs of step jj + LAG are made to depend on an accumulator
-        // of this step (OR with the sign bit of a positive double, i.e. with 0), so ptxas cannot hoist all twelve
-        // S-boxes in front of the FP64 block and the DFMAs of one step issue between the integer instructions of the next.
-        if (SBOX_ALL && jj + P2G_SBOX_LAG < 6) {
-            const uint32_t z0 = (uint32_t)__double2hiint(apl[5]) & 0x80000000u, z1 = (uint32_t)__double2hiint(amh[5]) & 0x80000000u;
-            s[jj + P2G_SBOX_LAG] |= z0; s[jj + P2G_SBOX_LAG + 6] |= z1;
-        }
-#endif
     }
-    const double BIAS = 4503599627370496.0;                      // 2^52
+    // (C_j +- C_{j+6}) / 2 are integers, so acc+ (biased by 2^52) and acc- (unbiased, signed) hold integers and both
+    // acc+ + acc- and acc+ - acc- are 2^52 + word (POSEIDON_RCS_*, tools/gen_poseidon_f64.py)
 #pragma unroll
     for (int r = 0; r < 6; r++) {
-        const double yl[2] = {__dadd_rn(apl[r], aml[r]), __dadd_rn(__dsub_rn(apl[r], aml[r]), BIAS)};
-        const double yh[2] = {__dadd_rn(aph[r], amh[r]), __dadd_rn(__dsub_rn(aph[r], amh[r]), BIAS)};
+        double yl[2] = {__dadd_rn(apl[r], aml[r]), __dsub_rn(apl[r], aml[r])};
+        double yh[2] = {__dadd_rn(aph[r], amh[r]), __dsub_rn(aph[r], amh[r])};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             uint32_t al0, al1, ah0, ah1;
@@ -360,8 +330,8 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
     double yl[12], yh[12];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
-        yl[r] = __dadd_rn(apl[r], aml[r]); yl[r + 6] = __dadd_rn(__dsub_rn(apl[r], aml[r]), BIAS);
-        yh[r] = __dadd_rn(aph[r], amh[r]); yh[r + 6] = __dadd_rn(__dsub_rn(aph[r], amh[r]), BIAS);
+        yl[r] = __dadd_rn(apl[r], aml[r]); yl[r + 6] = __dsub_rn(apl[r], aml[r]);
+        yh[r] = __dadd_rn(aph[r], amh[r]); yh[r + 6] = __dsub_rn(aph[r], amh[r]);
     }
     const double mzl = __hiloint2double(0x43300000, (int)(uint32_t)z0), mzh = __hiloint2double(0x43300000, (int)(uint32_t)(z0 >> 32));
     const double gl = __fma_rn(y0l8, 8., __dsub_rn(mzl, tl)), gh = __fma_rn(y0h8, 8., __dsub_rn(mzh, th));   // 8 y0 + z - t0 (+ E)
@@ -392,7 +362,7 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
     for (int jj = 0; jj < 12; jj++) {
         const int j = (jj + 1) % 12;                      // word 0 last: its S-box chain hides behind the others
         const gl_t v = j == 0 ? y0 : s[j];
-        const double xl = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)v), xh = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)(v >> 32));
+        const double xl = (double)(uint32_t)v, xh = (double)(uint32_t)(v >> 32);
 #ifdef P2G_DIAG_NO_MDS
         al[j] = __dadd_rn(al[j], xl); ah[j] = __dadd_rn(ah[j], xh);
 #else
@@ -406,7 +376,7 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
         tl = __fma_rn(xl, m0j, tl); th = __fma_rn(xh, m0j, th);
     }
     const gl_t z0 = poseidon_sbox(pos_readout(tl, th));
-    const double zl = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)z0), zh = pos_u2d<(P2G_CVT_MAGIC & 1) != 0>((uint32_t)(z0 >> 32));
+    const double zl = (double)(uint32_t)z0, zh = (double)(uint32_t)(z0 >> 32);
 #pragma unroll
     for (int r = 0; r < 12; r++) {
         const double mr0 = C[(12 - r) % 12] + (r == 0 ? 8. : 0.);
