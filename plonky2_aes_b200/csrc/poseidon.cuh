@@ -94,7 +94,7 @@ __device__ __forceinline__ gl_t pmul_v1(gl_t a, gl_t b) {
     return gl_fold4(l0, l1, h0, h1);
 }
 #ifndef P2G_SBOX_V
-#define P2G_SBOX_V 1
+#define P2G_SBOX_V 3
 #endif
 __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 #ifdef P2G_DIAG_NO_SBOX
@@ -104,6 +104,9 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
     return pmul_v2(x3, x4);
 #elif P2G_SBOX_V == 1
     gl_t x2 = pmul_v1(x, x), x4 = pmul_v1(x2, x2), x3 = pmul_v1(x, x2);
+    return pmul_v1(x3, x4);
+#elif P2G_SBOX_V == 3
+    gl_t x2 = psqr(x), x4 = psqr(x2), x3 = pmul_v1(x, x2);   // three-product squarings, compiler product elsewhere
     return pmul_v1(x3, x4);
 #else
     gl_t x2 = psqr(x), x4 = psqr(x2), x3 = pmul(x, x2);
