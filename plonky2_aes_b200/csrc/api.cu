@@ -88,7 +88,7 @@ int ctx_get_plan(p2g_ctx* ctx, int kind, int log_n, int rate_bits, const NttPlan
     auto lkey = std::make_tuple(kind, log_n, kind == NTT_KIND_LDE ? rate_bits : 0);
     auto lit = ctx->plans.find(lkey);                      // per-context cache of pointers: no lock on the hot path
     if (lit != ctx->plans.end()) { *out = lit->second; return P2G_OK; }
-    if (log_n > P2G_MAX_LOG_N) { ctx->err = "transform larger than 2^17 points is not supported"; return P2G_E_BADARG; }
+    if (log_n > P2G_MAX_LOG_N) { ctx->err = "transform larger than 2^20 points is not supported"; return P2G_E_BADARG; }
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto key = std::make_tuple(ctx->device, kind, log_n, kind == NTT_KIND_LDE ? rate_bits : 0);
     auto it = g_plans.find(key);
@@ -147,7 +147,7 @@ int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_
     uint32_t blk_log = 0; while ((1u << blk_log) < blk_count) blk_log++;
     if ((1u << blk_log) != blk_count || blk_first % blk_count || blk_first + blk_count > (1u << rate_bits)) return P2G_E_BADARG;
     if (!ncols || log_n > P2G_MAX_LOG_N || log_n + rate_bits > 26 || cap_height > log_n + blk_log) {
-        ctx->err = "unsupported commitment shape (log_n <= 17, cap_height <= log of the leaves held)"; return P2G_E_BADARG;
+        ctx->err = "unsupported commitment shape (log_n <= 20, cap_height <= log of the leaves held)"; return P2G_E_BADARG;
     }
     struct BatchGuard {                 // an early return releases the half-built batch
         p2g_ctx* ctx; p2g_batch* b;
@@ -170,7 +170,13 @@ int commit_dev(p2g_ctx* ctx, const gl_t* cols_dev, uint32_t ncols, uint32_t log_
     if (tim) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->st); }
     if (from_values) {
         if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, log_n, 0, &inv))) return rc;
-        if (ntt_launch(inv, cols_dev, n, b->coeffs, n, ncols, 1, ctx->st)) { ctx->err = "intt launch"; return P2G_E_CUDA; }
+        // large transforms stage their outer stages in scratch (the caller's values must stay intact)
+        gl_t* scratch = nullptr;
+        const size_t sw = ntt_scratch_words(inv, (int)ncols, 1);
+        if (sw && (rc = ctx_alloc(ctx, &scratch, sw))) return rc;
+        const int lrc = ntt_launch(inv, cols_dev, n, b->coeffs, n, ncols, 1, ctx->st, 0, 0, scratch);
+        if (scratch) ctx_free(ctx, scratch);
+        if (lrc) { ctx->err = "intt launch"; return P2G_E_CUDA; }
     } else {
         CU(cudaMemcpyAsync(b->coeffs, cols_dev, (size_t)ncols * n * sizeof(gl_t), cudaMemcpyDeviceToDevice, ctx->st));
     }

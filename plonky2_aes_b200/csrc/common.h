@@ -20,16 +20,22 @@ extern std::atomic<unsigned long long> g_p2g_launches;
 //     y_q[t] = sum_k x[t + k*M] * T[variant][q][k][t]
 // and then runs a size-M decimation-in-frequency transform entirely in shared memory.
 enum { NTT_KIND_LDE = 0, NTT_KIND_INV = 1 };
+// Two shapes.  Direct (R <= 4): the table holds base^(t + kM) for every k, T = [variants][R][R][M], and a block
+// does R multiplications per point on load.  Pre-folded (R >= 8, prefold = 1): a first kernel (ntt_outer_kernel)
+// multiplies x[t + kM] by shift^(kM) (C, [variants][R]) and runs the R-point transform over k for every t, leaving
+// Z[q][t] where block q will read it; the table is base_q^t only, T = [variants][R][M] -- linear in n -- and the
+// size-M kernel does one multiplication per point on load.
 struct NttPlan {
-    int kind, log_n, log_m, log_r, log_variants;
-    gl_t* T;    // [variants][R][R][M]
+    int kind, log_n, log_m, log_r, log_variants, prefold;
+    gl_t* T;    // direct: [variants][R][R][M]; pre-folded: [variants][R][M]
     gl_t* tw;   // per-pass compact twiddle tables (forward or inverse roots), tw_words entries
+    gl_t* C;    // pre-folded only: [variants][R] input scale factors, then R/2 twiddles of the R-point transform
     int tw_words;
 };
-// largest fold factor R = n / 2^log_m a plan may have: the table T grows as variants * R * n words
-// (rate 3: 8 MB at n = 2^15, 67 MB at 2^17, 268 MB at 2^18), so larger transforms are refused
-#define P2G_MAX_LOG_R 3
-#define P2G_MAX_LOG_N (P2G_MAX_LOG_M + P2G_MAX_LOG_R)
+// largest transform: 2^21 points (R = 2^7 chunks of 2^14); the provers accept degree_bits <= 20
+#define P2G_MAX_LOG_R 7
+#define P2G_MAX_LOG_N 20
+#define P2G_PREFOLD_MIN_LOG_R 3
 // per-device kernel attributes (dynamic shared memory opt-in); called by p2g_ctx_create after cudaSetDevice
 int ntt_init_device();
 int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream_t st);
@@ -39,8 +45,11 @@ void ntt_plan_free(NttPlan* plan);
 // out_mode 1: natural order, out[col*out_stride + f] (variants must be 1)
 // blk_first / blk_count: only the output blocks (cosets in leaf order) [blk_first, blk_first + blk_count) are
 // produced, into out[col*out_stride + (b - blk_first)*n ...]; blk_count = 0 means all
+// scratch: pre-folded plans with out_mode 1 need ncols * n words of scratch (out_mode 0 stages Z in `out` itself);
+// ntt_scratch_words tells how much
+size_t ntt_scratch_words(const NttPlan* plan, int ncols, int out_mode);
 int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out, size_t out_stride,
-               int ncols, int out_mode, cudaStream_t st, uint32_t blk_first = 0, uint32_t blk_count = 0);
+               int ncols, int out_mode, cudaStream_t st, uint32_t blk_first = 0, uint32_t blk_count = 0, gl_t* scratch = nullptr);
 
 // ---- Merkle (merkle.cu) -------------------------------------------------------------------
 // Leaves are read either column-major (element c of leaf j at data[c*col_stride + j]) or

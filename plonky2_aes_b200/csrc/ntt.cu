@@ -95,10 +95,51 @@ __device__ __forceinline__ void dif_pass_last16(gl_t* sm, int log_m, uint32_t ti
     }
 }
 
+// Pre-folded plans, first kernel: for one column, one coset variant and 32 consecutive t it loads the R values
+// x[t + kM] (32 consecutive words per k: coalesced), scales them by shift^(kM) and runs the R-point decimation in
+// frequency over k in shared memory; entry q of the result, Z[q][t], is what block q of the size-M kernel folds in,
+// and it is written where that block will read it (z + blk_local * n + q * M + t).  in == z is allowed for a
+// single variant (every (col, t) reads its R words before it writes them).
+__global__ void __launch_bounds__(256)
+ntt_outer_kernel(const gl_t* in, size_t in_stride, gl_t* z, size_t z_stride, const gl_t* __restrict__ C,
+                 int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first, int scale) {
+    extern __shared__ gl_t sm[];
+    const int log_r = log_n - log_m;
+    const uint32_t R = 1u << log_r;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x * 32 + lane;
+    const uint32_t blk_local = blockIdx.y;
+    const uint32_t variant = out_mode == 0 ? gl_bitrev(blk_first + blk_local, log_variants) : blk_local;
+    const gl_t* x = in + (size_t)blockIdx.z * in_stride;
+    const gl_t* Cv = C + (size_t)variant * R;
+    const gl_t* twr = C + ((size_t)R << log_variants);
+    for (uint32_t k = w; k < R; k += 8) {
+        gl_t v = x[t + ((size_t)k << log_m)];
+        if (scale && k) v = gl_mul(v, __ldg(Cv + k));
+        sm[k * 33 + lane] = v;
+    }
+    __syncthreads();
+    for (int s = 0; s < log_r; s++) {
+        const int log_half = log_r - 1 - s;
+        const uint32_t half = 1u << log_half;
+        for (uint32_t b = w; b < (R >> 1); b += 8) {
+            const uint32_t lowp = b & (half - 1);
+            const uint32_t i = ((b >> log_half) << (log_half + 1)) | lowp, j = i + half;
+            const gl_t a = sm[i * 33 + lane], c = sm[j * 33 + lane];
+            sm[i * 33 + lane] = gl_add(a, c);
+            const gl_t d = gl_sub(a, c);
+            sm[j * 33 + lane] = lowp ? gl_mul(d, __ldg(twr + ((size_t)lowp << s))) : d;
+        }
+        __syncthreads();
+    }
+    gl_t* o = z + (size_t)blockIdx.z * z_stride + ((size_t)blk_local << log_n) + t;
+    for (uint32_t q = w; q < R; q += 8) o[(size_t)q << log_m] = sm[q * 33 + lane];
+}
+
 __global__ void __launch_bounds__(512, 1)
 ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__ out, size_t out_stride,
                const gl_t* __restrict__ T, const gl_t* __restrict__ tw,
-               int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first, int inverse, uint32_t tw_skip) {
+               int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first, int inverse, uint32_t tw_skip, int prefold) {
     extern __shared__ gl_t sm[];
     const int log_r = log_n - log_m;
     const uint32_t M = 1u << log_m, R = 1u << log_r;
@@ -108,8 +149,10 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
     const uint32_t variant = out_mode == 0 ? gl_bitrev(blk_first + blk_local, log_variants) : blk_local;
     const uint32_t col = blockIdx.y;
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
-    const gl_t* x = in + (size_t)col * in_stride;
-    const gl_t* Tq = T + ((size_t)(variant * R + q) << log_n);   // [k][t]
+    // pre-folded plans: `in` holds Z[q][t] at blk_local * n + q * M + t (possibly the output buffer itself: the block
+    // has read its M words before anyone writes) and the table is base_q^t only
+    const gl_t* x = in + (size_t)col * in_stride + (prefold ? ((size_t)blk_local << log_n) + ((size_t)q << log_m) : 0);
+    const gl_t* Tq = T + ((size_t)(variant * R + q) << (prefold ? log_m : log_n));   // [k][t], or [t]
     // per-pass twiddle tables live behind the data in shared memory (global/L2 twiddle loads were
     // the dominant stall of this kernel: long_scoreboard 3.0 per issue, profiles/)
     // tw_skip: leading table words left in global memory (the block-size-2^13 table of the two-blocks-
@@ -126,7 +169,19 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
     // load + fold: y[t] = sum_k x[t + kM] * T[k][t].  All loads of a batch of 8 points are issued
     // before any arithmetic so that one block per SM still keeps ~32 loads per thread in flight
     // (the kernel was stalled on these loads: long_scoreboard 3.0 per issue).
-    if (R <= 2 && (M % (8 * nth)) == 0) {
+    if (prefold) {
+        if ((M % (8 * nth)) == 0) {
+            for (uint32_t t0 = tid; t0 < M; t0 += 8 * nth) {
+                gl_t xv[8], tv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { xv[u] = x[t0 + u * nth]; tv[u] = __ldg(Tq + t0 + u * nth); }
+#pragma unroll
+                for (int u = 0; u < 8; u++) sm[smpad(t0 + u * nth)] = gl_mul(xv[u], tv[u]);
+            }
+        } else {
+            for (uint32_t t = tid; t < M; t += nth) sm[smpad(t)] = gl_mul(x[t], __ldg(Tq + t));
+        }
+    } else if (R <= 2 && (M % (8 * nth)) == 0) {
         for (uint32_t t0 = tid; t0 < M; t0 += 8 * nth) {
             gl_t xv[8][2], tv[8][2];
 #pragma unroll
@@ -205,7 +260,7 @@ int ntt_init_device() {
 
 // returns 0, -1 (CUDA error) or -2 (out of device memory)
 int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream_t st) {
-    plan->kind = kind; plan->log_n = log_n; plan->T = plan->tw = nullptr;
+    plan->kind = kind; plan->log_n = log_n; plan->T = plan->tw = plan->C = nullptr; plan->prefold = 0;
     if (log_n > P2G_MAX_LOG_N) return -1;
     plan->log_m = log_n < P2G_MAX_LOG_M ? log_n : P2G_MAX_LOG_M;
     if (log_n == 13) plan->log_m = 13;
@@ -215,13 +270,21 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
     if (log_n == 14 || log_n == 15) plan->log_m = 13;
     {
         const char* e = getenv("P2G_NTT_LOG_M");
-        if (e && atoi(e) >= 10 && atoi(e) <= P2G_MAX_LOG_M && log_n > atoi(e) && log_n - atoi(e) <= 2) plan->log_m = atoi(e);
+        if (e && atoi(e) >= 5 && atoi(e) <= P2G_MAX_LOG_M && log_n > atoi(e) && log_n - atoi(e) <= P2G_MAX_LOG_R) plan->log_m = atoi(e);
     }
     plan->log_r = log_n - plan->log_m;
+    // R >= 8: pre-folded shape (table linear in n, one multiplication per point on load); P2G_NTT_PREFOLD=1 forces it
+    // for every R >= 2 (tests), =0 forbids it below the table-size limit
+    plan->prefold = plan->log_r >= P2G_PREFOLD_MIN_LOG_R;
+    {
+        const char* e = getenv("P2G_NTT_PREFOLD");
+        if (e && atoi(e) == 1 && plan->log_r >= 1) plan->prefold = 1;
+    }
+    if (!plan->prefold && plan->log_r > 2) return -1;
     plan->log_variants = kind == NTT_KIND_LDE ? rate_bits : 0;
     const size_t n = (size_t)1 << log_n, M = (size_t)1 << plan->log_m, R = (size_t)1 << plan->log_r;
     const size_t V = (size_t)1 << plan->log_variants;
-    std::vector<gl_t> T(V * R * n), tw(M / 2 ? M / 2 : 1);
+    std::vector<gl_t> T(plan->prefold ? V * R * M : V * R * n), tw(M / 2 ? M / 2 : 1), Cs;
     gl_t wn = gl_root_of_unity(log_n);
     gl_t wN = gl_root_of_unity(log_n + plan->log_variants);
     gl_t wm = gl_root_of_unity(plan->log_m);
@@ -232,9 +295,21 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
         for (size_t q = 0; q < R; q++) {
             gl_t base = gl_mul(shift, gl_pow(wn, gl_bitrev((uint32_t)q, plan->log_r)));
             gl_t x = kind == NTT_KIND_INV ? ninv : 1;
-            gl_t* dst = T.data() + (v * R + q) * n;   // index j = t + k*M  == [k][t]
-            for (size_t j = 0; j < n; j++) { dst[j] = x; x = gl_mul(x, base); }
+            const size_t len = plan->prefold ? M : n;
+            gl_t* dst = T.data() + (v * R + q) * len;   // index j = t + k*M  == [k][t]; pre-folded: k = 0 only
+            for (size_t j = 0; j < len; j++) { dst[j] = x; x = gl_mul(x, base); }
         }
+    }
+    if (plan->prefold) {
+        // C[v][k] = shift_v^(kM) (inverse plans: 1, the 1/n sits in T), then w_R^p for p < R/2 with w_R = w_n^M
+        Cs.resize(V * R + R / 2 + 1);
+        for (size_t v = 0; v < V; v++) {
+            gl_t shift = kind == NTT_KIND_LDE ? gl_mul(7, gl_pow(wN, v)) : 1;
+            gl_t step = gl_pow(shift, M), x = 1;
+            for (size_t k = 0; k < R; k++) { Cs[v * R + k] = x; x = gl_mul(x, step); }
+        }
+        gl_t wr = gl_pow(wn, M), x = 1;
+        for (size_t p2 = 0; p2 < R / 2; p2++) { Cs[V * R + p2] = x; x = gl_mul(x, wr); }
     }
     {   // per-pass compact twiddle tables, in pass order: w_B^p, p < B/2
         tw.clear();
@@ -253,6 +328,10 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
     }
     if (cudaMalloc(&plan->T, T.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); return -2; }
     if (cudaMalloc(&plan->tw, tw.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); ntt_plan_free(plan); return -2; }
+    if (plan->prefold) {
+        if (cudaMalloc(&plan->C, Cs.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); ntt_plan_free(plan); return -2; }
+        if (cudaMemcpyAsync(plan->C, Cs.data(), Cs.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess) { ntt_plan_free(plan); return -1; }
+    }
     if (cudaMemcpyAsync(plan->T, T.data(), T.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(plan->tw, tw.data(), tw.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {             // host vectors die here
@@ -260,11 +339,20 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
     }
     return 0;
 }
-void ntt_plan_free(NttPlan* plan) { if (plan->T) cudaFree(plan->T); if (plan->tw) cudaFree(plan->tw); plan->T = plan->tw = nullptr; }
+void ntt_plan_free(NttPlan* plan) {
+    if (plan->T) cudaFree(plan->T);
+    if (plan->tw) cudaFree(plan->tw);
+    if (plan->C) cudaFree(plan->C);
+    plan->T = plan->tw = plan->C = nullptr;
+}
+size_t ntt_scratch_words(const NttPlan* plan, int ncols, int out_mode) {
+    return plan->prefold && out_mode == 1 ? (size_t)ncols << plan->log_n : 0;
+}
 
 int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out, size_t out_stride,
-               int ncols, int out_mode, cudaStream_t st, uint32_t blk_first, uint32_t blk_count) {
+               int ncols, int out_mode, cudaStream_t st, uint32_t blk_first, uint32_t blk_count, gl_t* scratch) {
     const size_t M = (size_t)1 << plan->log_m;
+    if (plan->prefold && out_mode == 1 && !scratch) return -1;
     // a 2^13-point chunk with a non-trivial fold (n > 2^13) runs two blocks per SM: 256 threads each and
     // the first pass's table (4096 words) stays in global memory
     const bool two_per_sm = plan->log_m == 13 && plan->log_r > 0;
@@ -279,9 +367,23 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
         int nc = ncols - c0 < 65535 ? ncols - c0 : 65535;
         if (blk_count == 0) blk_count = 1u << plan->log_variants;
         dim3 grid(blk_count << plan->log_r, nc);
-        ntt_dif_kernel<<<grid, threads, smem, st>>>(in + (size_t)c0 * in_stride, in_stride, out + (size_t)c0 * out_stride,
+        const gl_t* src = in + (size_t)c0 * in_stride;
+        size_t src_stride = in_stride;
+        if (plan->prefold) {
+            // Z goes where the size-M blocks will read it: the output buffer itself (out_mode 0, same block layout)
+            // or the scratch buffer (out_mode 1, whose output is scattered over the column)
+            gl_t* z = out_mode == 0 ? out + (size_t)c0 * out_stride : scratch + ((size_t)c0 << plan->log_n);
+            const size_t z_stride = out_mode == 0 ? out_stride : (size_t)1 << plan->log_n;
+            dim3 og((unsigned)(M / 32), blk_count, nc);
+            const size_t osm = ((size_t)33 << plan->log_r) * sizeof(gl_t);
+            ntt_outer_kernel<<<og, 256, osm, st>>>(src, src_stride, z, z_stride, plan->C, plan->log_n, plan->log_m,
+                                                  plan->log_variants, out_mode, blk_first, plan->kind == NTT_KIND_LDE ? 1 : 0);
+            P2G_COUNT_LAUNCH(1);
+            src = z; src_stride = z_stride;
+        }
+        ntt_dif_kernel<<<grid, threads, smem, st>>>(src, src_stride, out + (size_t)c0 * out_stride,
                                                     out_stride, plan->T, plan->tw, plan->log_n, plan->log_m,
-                                                    plan->log_variants, out_mode, blk_first, plan->kind == NTT_KIND_INV ? 1 : 0, tw_skip);
+                                                    plan->log_variants, out_mode, blk_first, plan->kind == NTT_KIND_INV ? 1 : 0, tw_skip, plan->prefold);
         P2G_COUNT_LAUNCH(1);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

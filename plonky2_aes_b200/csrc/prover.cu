@@ -434,7 +434,8 @@ static int quotient_chunks(p2g_ctx* ctx, const p2g_circuit* C, ShardDev shd, con
     CU(cudaGetLastError());
     const NttPlan* inv;
     if ((rc = ctx_get_plan(ctx, NTT_KIND_INV, logn, 0, &inv))) return rc;
-    if (ntt_launch(inv, d_qv, n, d_qa, n, nch * (int)shd.blk_count, 1, st)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
+    // (large n: the outer stages run in place over d_qv, which is not read again)
+    if (ntt_launch(inv, d_qv, n, d_qa, n, nch * (int)shd.blk_count, 1, st, 0, 0, d_qv)) { ctx->err = "quotient intt"; return P2G_E_CUDA; }
     // the 8-point cross-coset combination needs every coset's interpolant: all-gather of 16 N / world bytes when sharded
     const gl_t* d_qall = d_qa;
     if (gather_interpolants && (rc = gather_interpolants(d_qa, &d_qall))) return rc;

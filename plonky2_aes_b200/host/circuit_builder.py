@@ -324,9 +324,10 @@ class CircuitBuilder:
             lookup_rows.append((last_lu_gate, last_lut_gate, first_lut_gate, padding, mult_pos))
         return lookup_rows, fixed
 
-    def build(self, ctx=None):
+    def build(self, ctx=None, min_degree_bits=0):
         """CircuitBuilder::build::<PoseidonGoldilocksConfig>() -> CircuitData.  `ctx` is the GPU
-        context that will hold the preprocessed (constants, sigmas) commitment."""
+        context that will hold the preprocessed (constants, sigmas) commitment.  `min_degree_bits` pads with
+        NoopGate rows up to 2^min_degree_bits (tests of large degrees without large circuits)."""
         cfg = self.config
         # PublicInputGate row: wires 0..4 are tied to hash_n_to_hash_no_pad(public inputs), computed in
         # circuit by PoseidonGate rows (upstream build() does the same); no inputs -> the zero hash
@@ -345,7 +346,7 @@ class CircuitBuilder:
                 self.connect(t, wire(row, i))
                 const_ops.append((OP_CONST, wire(row, i), 0, 0, 0, 0, c, 0))
         self.ops = const_ops + self.ops
-        while len(self.rows) < 4 or (len(self.rows) & (len(self.rows) - 1)):
+        while len(self.rows) < max(4, 1 << min_degree_bits) or (len(self.rows) & (len(self.rows) - 1)):
             self.add_gate(GATE_NOOP)
         n = len(self.rows)
         degree_bits = n.bit_length() - 1

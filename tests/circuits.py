@@ -28,6 +28,22 @@ def tiny_arith():
     return data, data.generate_witness(pw)
 
 
+def tiny_arith_padded(degree_bits):
+    """the same arithmetic circuit padded with NoopGate rows to n = 2^degree_bits (large-degree prover paths)"""
+    b = CircuitBuilder()
+    x, y = b.add_virtual_target(), b.add_virtual_target()
+    z = b.mul(x, y)
+    w = b.add(z, x)
+    e = b.is_equal(w, y)
+    s = b.select(e, x, y)
+    b.connect(s, b.add_virtual_target())
+    data = b.build(min_degree_bits=degree_bits)
+    pw = PartialWitness()
+    pw.set_target(x, 3)
+    pw.set_target(y, 5)
+    return data, data.generate_witness(pw)
+
+
 @functools.lru_cache(maxsize=None)
 def aes_block(nk=4, nr=10):
     """single AES block encryption circuit, FIPS-197 App. B vector (circuit_aes.rs:619-726)"""

@@ -149,12 +149,61 @@ def test_merkle_fewer_leaves_than_a_warp(gpu_ctx, oracle, log_leaves):
 
 
 def test_unsupported_sizes_are_refused(gpu_ctx):
-    """transforms above 2^17 points would need NTT tables that grow as n^2: refused, not attempted"""
+    """transforms above 2^20 points are refused, not attempted"""
     import ctypes as C
     h = C.c_void_p()
     dummy = np.zeros(8, dtype=np.uint64)
-    rc = gpu_ctx.lib.p2g_commit_from_values(gpu_ctx.handle, dummy.ctypes.data, 1, 18, 3, 4, C.byref(h), None)
+    rc = gpu_ctx.lib.p2g_commit_from_values(gpu_ctx.handle, dummy.ctypes.data, 1, 21, 3, 4, C.byref(h), None)
     assert rc == -2
+
+
+@pytest.mark.parametrize("ncols,log_n", [(3, 18), (1, 20)])
+def test_from_values_large_degrees(gpu_ctx, oracle, ncols, log_n):
+    """n >= 2^17 runs the pre-folded NTT (outer R-point stages in a kernel of their own, R = n / 2^14 up to 64)"""
+    cols = _cols(300 + log_n, ncols, log_n, edge=ncols > 1)
+    gb = PolynomialBatch.from_values(gpu_ctx, cols)
+    ob = oracle.batch(cols, True)
+    _compare(gb, ob, check_levels=False)
+    for j in (0, 54321, gb.lde_size - 1):
+        row, sib = gb.get_and_prove(j)
+        assert np.array_equal(row, ob.leaves()[j])
+        assert np.array_equal(sib, ob.tree.prove(j))
+    gb.free(); ob.free()
+
+
+_PREFOLD_SCRIPT = """
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+from tests import oracle_lib
+from tests.test_gpu_commit import _cols, _compare
+from plonky2_aes_b200.host.polynomial_batch import Context, PolynomialBatch
+oracle = oracle_lib.load()
+ctx = Context(0)
+for ncols, log_n, rate, from_values in %r:
+    cols = _cols(500 + log_n, ncols, log_n, edge=True)
+    gb = (PolynomialBatch.from_values if from_values else PolynomialBatch.from_coeffs)(ctx, cols, rate, min(4, log_n))
+    ob = oracle.batch(cols, from_values, rate, min(4, log_n))
+    _compare(gb, ob)
+    gb.free(); ob.free()
+ctx.close()
+print("prefold ok")
+"""
+
+
+@pytest.mark.parametrize("log_m,cases", [(5, [(3, 6, 3, True), (2, 8, 3, True), (4, 12, 1, False)]),
+                                         (9, [(3, 10, 3, True), (5, 13, 3, True), (2, 16, 2, True)])])
+def test_prefolded_ntt_forced_at_small_sizes(log_m, cases):
+    """The pre-folded shape (R-point outer kernel + size-M kernel with a one-word-per-point table) forced through
+    P2G_NTT_PREFOLD / P2G_NTT_LOG_M at sizes the oracle checks in full: R = 2 ... 128, inverse and coset forms.
+    Runs in a subprocess because NTT plans are cached per device for the life of the process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, P2G_NTT_PREFOLD="1", P2G_NTT_LOG_M=str(log_m))
+    r = subprocess.run([sys.executable, "-c", _PREFOLD_SCRIPT % (root, cases)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "prefold ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_contexts_on_two_devices_in_one_process(oracle):

@@ -57,6 +57,15 @@ def test_tiny_circuit(gpu_ctx, oracle):
     oc.free()
 
 
+def test_degree_2_18(gpu_ctx, oracle):
+    """n = 2^18 (LDE of 2^21 leaves): the pre-folded NTT inside the whole prover, every stage against the oracle"""
+    data, wires = circuits.tiny_arith_padded(18)
+    assert data.degree_bits == 18
+    oc = _check(gpu_ctx, oracle, data, wires)
+    oc.free()
+    gpu_ctx.check(gpu_ctx.lib.p2g_circuit_free(gpu_ctx.handle, data._gpu_circuit))
+
+
 def test_aes_block_c1(gpu_ctx, oracle):
     data, wires, _ = circuits.aes_block()
     _check(gpu_ctx, oracle, data, wires).free()
