@@ -268,6 +268,8 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
     // overlap the other's butterflies (LDE of the 135 x 2^15 wires 0.68 -> 0.65 ms); larger n keep
     // 2^14-point chunks.  P2G_NTT_LOG_M overrides (A/B knob).
     if (log_n == 14 || log_n == 15) plan->log_m = 13;
+    // n >= 2^17 (pre-folded shape): 2^13-point chunks as well (64 x 2^17: LDE 1.72 -> 1.46 ms)
+    if (log_n >= P2G_MAX_LOG_M + P2G_PREFOLD_MIN_LOG_R) plan->log_m = 13;
     {
         const char* e = getenv("P2G_NTT_LOG_M");
         if (e && atoi(e) >= 5 && atoi(e) <= P2G_MAX_LOG_M && log_n > atoi(e) && log_n - atoi(e) <= P2G_MAX_LOG_R) plan->log_m = atoi(e);
