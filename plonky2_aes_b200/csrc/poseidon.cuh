@@ -144,55 +144,77 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 // instructions per pair of words (a third one re-biased the difference before: -12 per round).  I2F.F64.U32
 // stays: building 2^52 + w from the raw words and subtracting 2^52 trades one I2F for a DADD plus 1.5 moves and
 // measured slower (profiles/r2_poseidon_magic_lag_experiments.jsonl).
+// Second level: acc+ is a 6 x 6 cyclic product of X+ and splits once more, acc+_r = pp_r + pm_r, acc+_{r+3} = pp_r - pm_r
+// with U+- = X+_j +- X+_{j+3} (18 + 6 + 6 instead of 36 products and sums per half); acc- is negacyclic and stays.
+// One accumulator set per 32-bit half: pp biased by 2^52, pm and am plain signed integers.
+__device__ __forceinline__ gl_t pos_readout(double l, double h);
+struct PosSplitAcc { double pp[3], pm[3], am[6]; };
+__device__ __forceinline__ void pos_split_load(PosSplitAcc& A, const double* __restrict__ tab) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) { A.pp[r] = tab[r]; A.pm[r] = tab[3 + r]; }
+#pragma unroll
+    for (int r = 0; r < 6; r++) A.am[r] = tab[6 + r];
+}
+// words j, j + 6, j + 3, j + 9 (one half each) of the vector that circ(CX) multiplies; j < 3
+#define POS_SPLIT_GROUP(A, CX, j, xa, xb, xc, xd) do {                                                         \
+        const double xp0 = __dadd_rn(xa, xb), xm0 = __dsub_rn(xa, xb), xp1 = __dadd_rn(xc, xd), xm1 = __dsub_rn(xc, xd); \
+        _Pragma("unroll")                                                                                         \
+        for (int r = 0; r < 6; r++) {                                                                             \
+            (A).am[r] = __fma_rn(xm0, 0.5 * (CX[((j) - r + 12) % 12] - CX[((j) + 6 - r + 12) % 12]), (A).am[r]);   \
+            (A).am[r] = __fma_rn(xm1, 0.5 * (CX[((j) + 3 - r + 12) % 12] - CX[((j) + 9 - r + 12) % 12]), (A).am[r]); \
+        }                                                                                                         \
+        const double up = __dadd_rn(xp0, xp1), um = __dsub_rn(xp0, xp1);                                          \
+        _Pragma("unroll")                                                                                         \
+        for (int r = 0; r < 3; r++) {                                                                             \
+            const double pa = 0.5 * (CX[((j) - r + 12) % 12] + CX[((j) + 6 - r + 12) % 12]);                      \
+            const double pb = 0.5 * (CX[((j) + 3 - r + 12) % 12] + CX[((j) + 9 - r + 12) % 12]);                  \
+            (A).pp[r] = __fma_rn(up, 0.5 * (pa + pb), (A).pp[r]); (A).pm[r] = __fma_rn(um, 0.5 * (pa - pb), (A).pm[r]); \
+        }                                                                                                         \
+    } while (0)
+// y[r], y[r + 6] = acc+ +- acc-, each 2^52 + word
+__device__ __forceinline__ void pos_split_recombine(const PosSplitAcc& A, double y[12]) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const double a0 = __dadd_rn(A.pp[r], A.pm[r]), a1 = __dsub_rn(A.pp[r], A.pm[r]);
+        y[r] = __dadd_rn(a0, A.am[r]); y[r + 6] = __dsub_rn(a0, A.am[r]);
+        y[r + 3] = __dadd_rn(a1, A.am[r + 3]); y[r + 9] = __dsub_rn(a1, A.am[r + 3]);
+    }
+}
 template <bool SBOX_ALL>
 __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
-    double apl[6], aml[6], aph[6], amh[6];
+    PosSplitAcc L, H;
+    pos_split_load(L, POSEIDON_RCS_LO + 12 * next_row); pos_split_load(H, POSEIDON_RCS_HI + 12 * next_row);
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-        apl[r] = POSEIDON_RCS_LO[12 * next_row + r]; aml[r] = POSEIDON_RCS_LO[12 * next_row + 6 + r];
-        aph[r] = POSEIDON_RCS_HI[12 * next_row + r]; amh[r] = POSEIDON_RCS_HI[12 * next_row + 6 + r];
-    }
+    for (int jj = 0; jj < 3; jj++) {
+        const int j = SBOX_ALL ? jj : (jj + 1) % 3;             // words (0, 6, 3, 9) last in partial rounds
+        gl_t v[4];
 #pragma unroll
-    for (int jj = 0; jj < 6; jj++) {
-        const int j = SBOX_ALL ? jj : (jj + 1) % 6;             // pair (0, 6) last in partial rounds
-        const gl_t v0 = (SBOX_ALL || j == 0) ? poseidon_sbox(s[j]) : s[j];
-        const gl_t v1 = SBOX_ALL ? poseidon_sbox(s[j + 6]) : s[j + 6];
-        const double x0l = (double)(uint32_t)v0, x0h = (double)(uint32_t)(v0 >> 32);
-        const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
-        const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
-        const double ph = __dadd_rn(x0h, x1h), mh = __dsub_rn(x0h, x1h);
+        for (int u = 0; u < 4; u++) {
+            const int w = j + 6 * (u & 1) + 3 * (u >> 1);        // j, j + 6, j + 3, j + 9
+            v[u] = (SBOX_ALL || w == 0) ? poseidon_sbox(s[w]) : s[w];
+        }
+        double xl[4], xh[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { xl[u] = (double)(uint32_t)v[u]; xh[u] = (double)(uint32_t)(v[u] >> 32); }
 #ifdef P2G_DIAG_NO_MDS
-        apl[j] = __dadd_rn(apl[j], pl); aph[j] = __dadd_rn(aph[j], ph); aml[j] = __dadd_rn(aml[j], ml); amh[j] = __dadd_rn(amh[j], mh);
+        L.am[j] = __dadd_rn(L.am[j], __dadd_rn(__dadd_rn(xl[0], xl[1]), __dadd_rn(xl[2], xl[3])));
+        H.am[j] = __dadd_rn(H.am[j], __dadd_rn(__dadd_rn(xh[0], xh[1]), __dadd_rn(xh[2], xh[3])));
 #else
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-            const double a = C[(j - r + 12) % 12], b = C[(j + 6 - r + 12) % 12];
-            const double P = 0.5 * (a + b), N = 0.5 * (a - b);
-            apl[r] = __fma_rn(pl, P, apl[r]); aml[r] = __fma_rn(ml, N, aml[r]);
-            aph[r] = __fma_rn(ph, P, aph[r]); amh[r] = __fma_rn(mh, N, amh[r]);
-        }
+        POS_SPLIT_GROUP(L, C, j, xl[0], xl[1], xl[2], xl[3]);
+        POS_SPLIT_GROUP(H, C, j, xh[0], xh[1], xh[2], xh[3]);
 #endif
-        if (j == 0) {                                            // + 8 x_0 on row 0 only
-            apl[0] = __fma_rn(x0l, 4., apl[0]); aml[0] = __fma_rn(x0l, 4., aml[0]);
-            aph[0] = __fma_rn(x0h, 4., aph[0]); amh[0] = __fma_rn(x0h, 4., amh[0]);
+        if (j == 0) {                                            // + 8 x_0 on row 0 only: 4 x_0 to acc+_0 (2 + 2) and to acc-_0
+            L.pp[0] = __fma_rn(xl[0], 2., L.pp[0]); L.pm[0] = __fma_rn(xl[0], 2., L.pm[0]); L.am[0] = __fma_rn(xl[0], 4., L.am[0]);
+            H.pp[0] = __fma_rn(xh[0], 2., H.pp[0]); H.pm[0] = __fma_rn(xh[0], 2., H.pm[0]); H.am[0] = __fma_rn(xh[0], 4., H.am[0]);
         }
     }
-    // (C_j +- C_{j+6}) / 2 are integers, so acc+ (biased by 2^52) and acc- (unbiased, signed) hold integers and both
-    // acc+ + acc- and acc+ - acc- are 2^52 + word (POSEIDON_RCS_*, tools/gen_poseidon_f64.py)
+    // all coefficients are integers for this matrix, so pp (biased by 2^52), pm and acc- (signed) hold integers and
+    // acc+ + acc-, acc+ - acc- are both 2^52 + word (POSEIDON_RCS_*, tools/gen_poseidon_f64.py)
+    double yl[12], yh[12];
+    pos_split_recombine(L, yl); pos_split_recombine(H, yh);
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-        double yl[2] = {__dadd_rn(apl[r], aml[r]), __dsub_rn(apl[r], aml[r])};
-        double yh[2] = {__dadd_rn(aph[r], amh[r]), __dsub_rn(aph[r], amh[r])};
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint32_t al0, al1, ah0, ah1;
-            POS_READ(yl[h], al0, al1); POS_READ(yh[h], ah0, ah1);
-            uint32_t m, t;
-            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=&r"(m), "=&r"(t) : "r"(al1), "r"(ah0), "r"(ah1));
-            s[r + 6 * h] = gl_fold3(al0, m, t);
-        }
-    }
+    for (int r = 0; r < 12; r++) s[r] = pos_readout(yl[r], yh[r]);
 }
 #else
 template <bool SBOX_ALL>
@@ -293,49 +315,38 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
     const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
     const double C2[12] = POSEIDON_C2_INIT;
     const double BIAS = 4503599627370496.0;               // 2^52
-    double apl[6], aml[6], aph[6], amh[6];
+    PosSplitAcc L, H;
     const int pz = 12 * pair + zero;                      // per-thread looking index: LDC instead of LDCU + moves
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        apl[r] = POSEIDON_PAIRS_LO[pz + r]; aml[r] = POSEIDON_PAIRS_LO[pz + 6 + r];
-        aph[r] = POSEIDON_PAIRS_HI[pz + r]; amh[r] = POSEIDON_PAIRS_HI[pz + 6 + r];
-    }
+    pos_split_load(L, POSEIDON_PAIRS_LO + pz); pos_split_load(H, POSEIDON_PAIRS_HI + pz);
     const int row_a = 5 + 2 * pair;                       // constants between the two rounds
     double tl = POSEIDON_RCD_LO[12 * row_a + zero], th = POSEIDON_RCD_HI[12 * row_a + zero];
     const gl_t y0 = poseidon_sbox(s[0]);
     double y0l8 = 0., y0h8 = 0.;
 #pragma unroll
-    for (int jj = 0; jj < 6; jj++) {
-        const int j = (jj + 1) % 6;                       // words (0, 6) last: the S-box chain of word 0 hides behind the others
-        const gl_t v0 = j == 0 ? y0 : s[j], v1 = s[j + 6];
-        const double x0l = (double)(uint32_t)v0, x0h = (double)(uint32_t)(v0 >> 32);
-        const double x1l = (double)(uint32_t)v1, x1h = (double)(uint32_t)(v1 >> 32);
-        const double pl = __dadd_rn(x0l, x1l), ml = __dsub_rn(x0l, x1l);
-        const double ph = __dadd_rn(x0h, x1h), mh = __dsub_rn(x0h, x1h);
-#ifdef P2G_DIAG_NO_MDS
-        apl[j] = __dadd_rn(apl[j], pl); aph[j] = __dadd_rn(aph[j], ph); aml[j] = __dadd_rn(aml[j], ml); amh[j] = __dadd_rn(amh[j], mh);
-#else
+    for (int jj = 0; jj < 3; jj++) {
+        const int j = (jj + 1) % 3;                       // words (0, 6, 3, 9) last: the S-box chain of word 0 hides behind the others
+        double xl[4], xh[4];
 #pragma unroll
-        for (int r = 0; r < 6; r++) {
-            const double a = C2[(j - r + 12) % 12], b = C2[(j + 6 - r + 12) % 12];
-            const double Pc = 0.5 * (a + b), Nc = 0.5 * (a - b);
-            apl[r] = __fma_rn(pl, Pc, apl[r]); aml[r] = __fma_rn(ml, Nc, aml[r]);
-            aph[r] = __fma_rn(ph, Pc, aph[r]); amh[r] = __fma_rn(mh, Nc, amh[r]);
+        for (int u = 0; u < 4; u++) {
+            const int w = j + 6 * (u & 1) + 3 * (u >> 1);  // j, j + 6, j + 3, j + 9
+            const gl_t v = w == 0 ? y0 : s[w];
+            xl[u] = (double)(uint32_t)v; xh[u] = (double)(uint32_t)(v >> 32);
+            const double m0 = C[w] + (w == 0 ? 8. : 0.);  // row 0 of M
+            tl = __fma_rn(xl[u], m0, tl); th = __fma_rn(xh[u], m0, th);
         }
+#ifdef P2G_DIAG_NO_MDS
+        L.am[j] = __dadd_rn(L.am[j], __dadd_rn(__dadd_rn(xl[0], xl[1]), __dadd_rn(xl[2], xl[3])));
+        H.am[j] = __dadd_rn(H.am[j], __dadd_rn(__dadd_rn(xh[0], xh[1]), __dadd_rn(xh[2], xh[3])));
+#else
+        POS_SPLIT_GROUP(L, C2, j, xl[0], xl[1], xl[2], xl[3]);
+        POS_SPLIT_GROUP(H, C2, j, xh[0], xh[1], xh[2], xh[3]);
 #endif
-        const double m0 = C[j] + (j == 0 ? 8. : 0.), m1 = C[j + 6];          // row 0 of M
-        tl = __fma_rn(x0l, m0, tl); th = __fma_rn(x0h, m0, th);
-        tl = __fma_rn(x1l, m1, tl); th = __fma_rn(x1h, m1, th);
-        if (j == 0) { y0l8 = x0l; y0h8 = x0h; }
+        if (j == 0) { y0l8 = xl[0]; y0h8 = xh[0]; }
     }
     const gl_t z0 = poseidon_sbox(pos_readout(tl, th));
     // while that S-box runs: recombine the split accumulators
     double yl[12], yh[12];
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        yl[r] = __dadd_rn(apl[r], aml[r]); yl[r + 6] = __dsub_rn(apl[r], aml[r]);
-        yh[r] = __dadd_rn(aph[r], amh[r]); yh[r + 6] = __dsub_rn(aph[r], amh[r]);
-    }
+    pos_split_recombine(L, yl); pos_split_recombine(H, yh);
     const double mzl = __hiloint2double(0x43300000, (int)(uint32_t)z0), mzh = __hiloint2double(0x43300000, (int)(uint32_t)(z0 >> 32));
     const double gl = __fma_rn(y0l8, 8., __dsub_rn(mzl, tl)), gh = __fma_rn(y0h8, 8., __dsub_rn(mzh, th));   // 8 y0 + z - t0 (+ E)
 #pragma unroll

@@ -344,7 +344,7 @@ def test_circuit_load_error_paths_do_not_leak(gpu_ctx):
     assert free1 >= free0 - (1 << 20), (free0, free1)
     d2 = data.descriptor(); d2.pow_bits = 0
     assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d2), C.byref(h), None) == -2
-    d3 = data.descriptor(); d3.degree_bits = 18
+    d3 = data.descriptor(); d3.degree_bits = 21
     assert lib.p2g_circuit_load(gpu_ctx.handle, C.byref(d3), C.byref(h), None) == -2
 
 

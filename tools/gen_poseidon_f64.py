@@ -3,10 +3,11 @@
 
 Two families of exact-double tables for the FP64-pipe MDS layer of csrc/poseidon.cuh:
   POSEIDON_RCD_LO/HI[31*12]  2^52 + low/high 32 bits of the round constants (plain 12x12 form);
-  POSEIDON_RCS_LO/HI[31*12]  biases of the split-circulant form: for row r and j < 6
-        [12r + j]     = 2^52 + (c_j + c_{j+6}) / 2      (accumulator of Y+ / 2)
-        [12r + 6 + j] =        (c_j - c_{j+6}) / 2      (accumulator of Y- / 2, signed)
-     so that acc+ + acc- = 2^52 + c_j + y_j  and  acc+ - acc- = 2^52 + c_{j+6} + y_{j+6}  (see split2).
+  POSEIDON_RCS_LO/HI[31*12]  biases of the two-level split-circulant form (see split2): per row
+        [0..2]  pp_r = 2^52 + (beta_r + beta_{r+3}) / 2,   [3..5]  pm_r = (beta_r - beta_{r+3}) / 2,
+        [6..11] acc-_j = (c_j - c_{j+6}) / 2,              beta_j = (c_j + c_{j+6}) / 2,
+     so that acc+_r = pp_r + pm_r, acc+_{r+3} = pp_r - pm_r, acc+ + acc- = 2^52 + c_j + y_j and
+     acc+ - acc- = 2^52 + c_{j+6} + y_{j+6}.
 Row r holds the constants added BEFORE round r (rows 0..29); row 30 is zero.
 """
 import os, re, sys
@@ -72,10 +73,45 @@ def split2(lo_rows, hi_rows):
         for j in range(6):
             a, b = PARITY_FIX[((lo_r[j] + lo_r[j + 6]) & 1, (hi_r[j] + hi_r[j + 6]) & 1)]
             lo_r[j + 6] += a; hi_r[j + 6] += b
+        # second level: acc+ itself is a 6 x 6 cyclic product and splits again ((P_k +- P_{k+3}) / 2 are integers too):
+        # acc+_r = pp_r + pm_r, acc+_{r+3} = pp_r - pm_r, so beta_r + beta_{r+3} (beta_r = (k_r + k_{r+6}) / 2) must be
+        # even: fixed on k_{r+9} with twice the pairs above (even, so the first-level parity stays)
+        for r in range(3):
+            need = tuple(((row[r] + row[r + 6] + row[r + 3] + row[r + 9]) // 2) & 1 for row in (lo_r, hi_r))
+            a, b = PARITY_FIX[need]
+            lo_r[r + 9] += 2 * a; hi_r[r + 9] += 2 * b
         for row, out in ((lo_r, out_lo), (hi_r, out_hi)):
-            out += [2**52 + (row[j] + row[j + 6]) // 2 for j in range(6)]
+            beta = [(row[j] + row[j + 6]) // 2 for j in range(6)]
+            assert all((row[j] + row[j + 6]) % 2 == 0 for j in range(6)) and all((beta[r] + beta[r + 3]) % 2 == 0 for r in range(3))
+            out += [2**52 + (beta[r] + beta[r + 3]) // 2 for r in range(3)]
+            out += [(beta[r] - beta[r + 3]) // 2 for r in range(3)]
             out += [(row[j] - row[j + 6]) // 2 for j in range(6)]
     return out_lo, out_hi
+
+
+def split_product(xs, Cx, pp, pm, am):
+    """the device's accumulation order for one 32-bit half: groups (j, j+3), j = 1, 2, 0"""
+    for j in (1, 2, 0):
+        xp = [None] * 2
+        for u, jj in enumerate((j, j + 3)):
+            xp[u] = dbl(xs[jj] + xs[jj + 6])
+            xm = dbl(xs[jj] - xs[jj + 6])
+            for r in range(6):
+                a, b = Cx[(jj - r) % 12], Cx[(jj + 6 - r) % 12]
+                assert (a - b) % 2 == 0
+                am[r] = dbl(am[r] + xm * ((a - b) // 2))
+        up, um = dbl(xp[0] + xp[1]), dbl(xp[0] - xp[1])
+        for r in range(3):
+            a = (Cx[(j - r) % 12] + Cx[(j + 6 - r) % 12]) // 2
+            b = (Cx[(j + 3 - r) % 12] + Cx[(j + 9 - r) % 12]) // 2
+            assert (a + b) % 2 == 0
+            pp[r] = dbl(pp[r] + up * ((a + b) // 2))
+            pm[r] = dbl(pm[r] + um * ((a - b) // 2))
+
+
+def split_recombine(pp, pm, am):
+    ap = [dbl(pp[r] + pm[r]) for r in range(3)] + [dbl(pp[r] - pm[r]) for r in range(3)]
+    return [dbl(ap[r] + am[r]) for r in range(6)] + [dbl(ap[r] - am[r]) for r in range(6)]
 
 
 text = """/* generated by tools/gen_poseidon_f64.py from poseidon_rc.inc (constants: tools/gen_poseidon_constants.py).
@@ -204,18 +240,14 @@ def pair_split_emulated(s, p):
     accs = []
     tb = []
     for half, (xs, tab, t_init) in enumerate(((xl, KS_LO, 2**52 + (cA0e & 0xFFFFFFFF)), (xh, KS_HI, 2**52 + (cA0e >> 32)))):
-        ap = [tab[12 * p + r] for r in range(6)]
-        am = [tab[12 * p + 6 + r] for r in range(6)]
+        pp = [Fraction(tab[12 * p + r]) for r in range(3)]
+        pm = [Fraction(tab[12 * p + 3 + r]) for r in range(3)]
+        am = [Fraction(tab[12 * p + 6 + r]) for r in range(6)]
         t = Fraction(t_init)
-        for j in [1, 2, 3, 4, 5, 0]:
-            pl, ml = dbl(xs[j] + xs[j + 6]), dbl(xs[j] - xs[j + 6])
-            for r in range(6):
-                a, b = C2[(j - r) % 12], C2[(j + 6 - r) % 12]
-                ap[r] = dbl(ap[r] + pl * Fraction(a + b, 2))
-                am[r] = dbl(am[r] + ml * Fraction(a - b, 2))
-            t = dbl(t + xs[j] * M[0][j]); t = dbl(t + xs[j + 6] * M[0][j + 6])
-        y = [dbl(ap[r] + am[r]) for r in range(6)] + [dbl(ap[r] - am[r]) for r in range(6)]
-        accs.append(y); tb.append(t)
+        split_product(xs, C2, pp, pm, am)
+        for j in range(12):
+            t = dbl(t + xs[j] * M[0][j])
+        accs.append(split_recombine(pp, pm, am)); tb.append(t)
     t0 = readout(tb[0], tb[1])
     assert t0 == (sum(M[0][j] * x[j] for j in range(12)) + rc_true[12 * (kA + 1)]) % P
     z = sbox(t0)
@@ -263,17 +295,12 @@ def full_round_emulated(s, next_row):
     x = [sbox(v) for v in s]
     halves = []
     for xs, tab in (([Fraction(v & 0xFFFFFFFF) for v in x], RCS_LO), ([Fraction(v >> 32) for v in x], RCS_HI)):
-        ap = [Fraction(tab[12 * next_row + r]) for r in range(6)]
+        pp = [Fraction(tab[12 * next_row + r]) for r in range(3)]
+        pm = [Fraction(tab[12 * next_row + 3 + r]) for r in range(3)]
         am = [Fraction(tab[12 * next_row + 6 + r]) for r in range(6)]
-        for j in range(6):
-            pl, ml = dbl(xs[j] + xs[j + 6]), dbl(xs[j] - xs[j + 6])
-            for r in range(6):
-                a, b = CIRC[(j - r) % 12], CIRC[(j + 6 - r) % 12]
-                ap[r] = dbl(ap[r] + pl * ((a + b) // 2)); am[r] = dbl(am[r] + ml * ((a - b) // 2))
-            if j == 0:
-                ap[0] = dbl(ap[0] + 4 * xs[0]); am[0] = dbl(am[0] + 4 * xs[0])
-        y = [dbl(ap[r] + am[r]) for r in range(6)] + [dbl(ap[r] - am[r]) for r in range(6)]
-        halves.append(y)
+        split_product(xs, CIRC, pp, pm, am)
+        pp[0] = dbl(pp[0] + 2 * xs[0]); pm[0] = dbl(pm[0] + 2 * xs[0]); am[0] = dbl(am[0] + 4 * xs[0])
+        halves.append(split_recombine(pp, pm, am))
     return [readout(halves[0][r], halves[1][r]) for r in range(12)]
 
 
@@ -282,5 +309,5 @@ for pat in ([random.randrange(P) for _ in range(12)], [P - 1] * 12, [0] * 12, [0
         ref = [(a + b) % P for a, b in zip(mds([sbox(v) for v in pat]), rc_true[12 * row:12 * row + 12])]
         assert full_round_emulated(pat, row) == ref, row
 # extreme S-box outputs (lazy residues up to 2^64 - 1) cannot be produced through sbox(); bound the accumulators directly
-assert 2**52 + 2 * DL + 2**33 + 264 * 2**33 < 2**53
+assert 2**52 + 4 * DL + 2**34 + 264 * 2**33 < 2**53
 print("split full round ok")
