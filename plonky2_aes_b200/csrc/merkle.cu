@@ -141,6 +141,40 @@ merkle_level_coop_kernel(const gl_t* __restrict__ src, gl_t* __restrict__ dst, u
     (void)node; (void)l; (void)g; (void)src; (void)dst;
 #endif
 }
+// Up to 7 consecutive narrow levels in one launch: a block of 1024 threads (64 groups of 16 lanes) owns 128 nodes of
+// level lv_in and hashes its subtree upwards, one 12-lane permutation deep per level, children passed through
+// shared memory; every level is also written to `digests` / `cap` (Merkle paths need them).  Replaces one launch
+// per level for the levels of at most 4096 nodes: 9 launches -> 2 for the tree tops of a 2^18-leaf commitment.
+#define TOP_NODES 128
+__global__ void __launch_bounds__(1024)
+merkle_top_coop_kernel(gl_t* __restrict__ digests, gl_t* __restrict__ cap, uint32_t log_leaves, uint32_t L,
+                       uint32_t lv_in, uint32_t levels, uint32_t nodes_per_block) {
+    __shared__ gl_t sh[2][TOP_NODES][4];
+#if defined(__CUDA_ARCH__)
+    const uint32_t lane = threadIdx.x & 31, l = lane & 15, g = threadIdx.x >> 4;      // group g of 16 lanes
+    const gl_t* src = level_ptr(digests, cap, log_leaves, L, lv_in) + (size_t)blockIdx.x * nodes_per_block * 4;
+    for (uint32_t i = threadIdx.x; i < nodes_per_block * 4; i += blockDim.x) sh[0][i >> 2][i & 3] = src[i];
+    __syncthreads();
+    uint32_t cnt = nodes_per_block >> 1;                    // parents of this block at the current level
+    for (uint32_t p = 0; p < levels; p++, cnt >>= 1) {
+        const uint32_t in = p & 1;
+        if ((g & ~1u) < ((cnt + 1) & ~1u)) {                // whole warps stay together for the shuffles
+            gl_t x = 0;
+            if (g < cnt && l < 8) x = sh[in][2 * g + (l >> 2)][l & 3];
+            x = poseidon_coop(x, l, (lane & 16), POSEIDON_RC_GLOBAL);
+            if (g < cnt && l < 4) {
+                const gl_t v = gl_canon(x);
+                sh[in ^ 1][g][l] = v;
+                gl_t* d = level_ptr(digests, cap, log_leaves, L, lv_in + p + 1);
+                d[((size_t)blockIdx.x * cnt + g) * 4 + l] = v;
+            }
+        }
+        __syncthreads();
+    }
+#else
+    (void)digests; (void)cap; (void)log_leaves; (void)L; (void)lv_in; (void)levels; (void)nodes_per_block; (void)sh;
+#endif
+}
 // row-major leaves hashed cooperatively (FRI layers with few leaves): two leaves per warp
 __global__ void __launch_bounds__(256)
 merkle_leaves_coop_kernel(const gl_t* __restrict__ data, uint32_t leaf_len, uint32_t cnt, gl_t* __restrict__ dst) {
@@ -167,6 +201,7 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
     const size_t num_leaves = (size_t)1 << log_leaves;
     // levels (or leaf sets) this narrow use the 12-lane permutation; P2G_COOP_MAX: A/B knob
     static const uint32_t COOP_MAX = [] { const char* e = getenv("P2G_COOP_MAX"); return e ? (uint32_t)atoi(e) : 4096u; }();
+    static const bool FUSE_TOP = [] { const char* e = getenv("P2G_FUSE_TOP"); return e ? atoi(e) != 0 : true; }();    // A/B knob
     uint32_t lv;
     if (!col_major && leaf_len > 4 && num_leaves <= COOP_MAX) {
         gl_t* d0 = L == 0 ? cap : digests;
@@ -201,12 +236,23 @@ int merkle_build(const gl_t* data, int col_major, size_t col_stride, uint32_t le
         gl_t* dst = (lv + 1 >= L) ? cap : digests + merkle_level_offset(log_leaves, lv + 1);
         if (cnt > COOP_MAX) {
             merkle_level_kernel<<<(uint32_t)((cnt + POS_BLOCK - 1) / POS_BLOCK), POS_BLOCK, 0, st>>>(src, dst, cnt);
+            P2G_COUNT_LAUNCH(1);
+            lv++;
+        } else if (FUSE_TOP) {
+            // up to 7 levels per launch: blocks of 128 nodes (fewer when the level is narrower)
+            const uint32_t nodes = (uint32_t)(2 * cnt);
+            const uint32_t per_block = nodes < TOP_NODES ? nodes : TOP_NODES;
+            uint32_t k = 0; while ((per_block >> (k + 1)) >= 1 && k < L - lv) k++;       // levels below the block's root, capped at the tree's cap
+            const uint32_t threads = per_block * 8 < 32 ? 32 : per_block * 8;              // 16 lanes per parent of the first level
+            merkle_top_coop_kernel<<<nodes / per_block, threads, 0, st>>>(digests, cap, log_leaves, L, lv, k, per_block);
+            P2G_COUNT_LAUNCH(1);
+            lv += k;
         } else {
             uint32_t warps = (uint32_t)((cnt + 1) / 2);
             merkle_level_coop_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(src, dst, (uint32_t)cnt);
+            P2G_COUNT_LAUNCH(1);
+            lv++;
         }
-        P2G_COUNT_LAUNCH(1);
-        lv++;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
