@@ -30,7 +30,7 @@ for r in rows[hdr + 1:]:
 tot = sum(sum(v) for v in d.values())
 nl = sum(len(v) for v in d.values())
 L = [f"# Round {tag[1:]}, end state: ncu launch list summary", "",
-     f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c {nl} --csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --streams 1 --config5-proofs 0`",
+     f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c {nl} --csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --streams 1 --config5-proofs 0`",
      f"({nl} consecutive launches ~ 3 proofs of BASELINE config 2; cold-cache serialised times: compare shares; raw list: {tag}_launches_final.csv)", "",
      "| kernel | launches | total ms | share | avg us |", "|---|---|---|---|---|"]
 pos = 0.0
