@@ -101,6 +101,32 @@ def test_hash_and_merkle_helpers(gpu_ctx, oracle):
     assert [hex(int(v)) for v in z[0]] == ['0x3c18a9786cb0b359', '0xc4055e3364a246c3', '0x7953db0ab48808f4', '0xc71603f33a1144ca']
 
 
+def test_poseidon_extreme_words(gpu_ctx, oracle):
+    """The FP64 linear layers are exact only while their accumulators stay inside [2^52, 2^53): states made of the words
+    that maximise / minimise the 32-bit halves (0, p - 1, 2^32 - 1, 2^64 - 2^32, 2^32, 1) in the patterns that
+    drive X+ / X- and the rank-one term of the merged partial rounds to their extremes, plus 2000 random 8-word rows,
+    through the thread-per-permutation kernel and the 12-lane kernel (merkle_cap of a narrow tree)."""
+    ext = [0, P - 1, 0xFFFFFFFF, 0xFFFFFFFF00000000, 1 << 32, 1, 0xFFFFFFFEFFFFFFFF, 0x7FFFFFFF80000000]
+    rows = []
+    for a in ext:
+        for b in ext:
+            rows.append([a] * 4 + [b] * 4)                  # word j against word j + 4
+            rows.append([a, b] * 4)                         # alternating
+            rows.append([a] + [b] * 7)                      # word 0 (the partial-round S-box) against the rest
+    rows = np.array(rows, dtype=np.uint64)
+    rng = np.random.default_rng(77)
+    rows = np.concatenate([rows, rng.integers(0, P, size=(2000, 8), dtype=np.uint64)])
+    got = gpu_ctx.hash_no_pad_many(rows)
+    for i in range(len(rows)):
+        assert list(got[i]) == list(oracle.hash_no_pad(rows[i])), i
+    # the same words as 16-word leaves of a 64-leaf tree: leaf sponge (2 permutations) + 12-lane levels
+    leaves = np.concatenate([rows[:64], rows[64:128]], axis=1)
+    cap, dig = gpu_ctx.merkle_cap(leaves, 2)
+    t = oracle.merkle(leaves, 2)
+    assert np.array_equal(cap, t.cap) and np.array_equal(dig, t.level(0))
+    t.free()
+
+
 @pytest.mark.parametrize("ncols,log_n", [(20, 10), (3, 14)])
 def test_coset_sharded_commit_matches_full(gpu_ctx, oracle, ncols, log_n):
     """multi-GPU coset split of one commitment, emulated on one GPU: every shard's LDE block and cap
