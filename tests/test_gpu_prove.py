@@ -475,7 +475,8 @@ def test_guard_bands_see_no_out_of_bounds_write(oracle):
         del os.environ["P2G_CANARY"]
     ctx = ctxs[0]
     rng = np.random.default_rng(1)
-    for ncols, log_n, cap in ((1, 1, 0), (5, 1, 3), (3, 2, 1), (9, 6, 4), (135, 10, 4), (3, 14, 4)):
+    # (2, 17): the pre-folded NTT (outer kernel, scratch for the natural-order inverse); (1, 8, 0): a tree folded to one root
+    for ncols, log_n, cap in ((1, 1, 0), (5, 1, 3), (3, 2, 1), (9, 6, 4), (135, 10, 4), (3, 14, 4), (2, 17, 4), (1, 8, 0)):
         PolynomialBatch.from_values(ctx, rng.integers(0, P, size=(ncols, 1 << log_n), dtype=np.uint64), 3, cap).free()
     for data, wires, pi in (circuits.tiny_arith() + (None,), circuits.aes_gcm(13, True)[:2] + (None,),
                             circuits.feistel_poseidon()[:2] + (None,), circuits.public_input_circuit()):
