@@ -154,6 +154,17 @@ int32_t p2g_quotient(p2g_ctx* ctx, const p2g_circuit* c, const p2g_batch* wires,
                      const uint64_t* betas, const uint64_t* gammas, const uint64_t* deltas, const uint64_t* alphas,
                      p2g_batch** quotient_out, uint64_t* cap_out);
 int32_t p2g_open(p2g_ctx* ctx, const p2g_batch* const* batches, uint32_t n_batches, const uint64_t zeta[2], uint64_t* openings_out);
+/* p2g_fri_prove = PolynomialBatch::prove_openings (fri/oracle.rs) + fri_proof (fri/prover.rs) on their own: batch
+ * combination of all committed polynomials at zeta and g * zeta, LDE, commit phase (caps, folding challenges), final
+ * polynomial, proof of work (lowest nonce) and the query rounds.  wires / zs / quotient are whole batches of this circuit
+ * (the preprocessed batch is the circuit's own), zeta the point the caller drew after the quotient cap, challenger_io the
+ * state of the caller's Challenger AFTER it observed the openings, 30 words: [0..12) sponge state, [12..20) input buffer,
+ * [20..28) output buffer, [28] input length, [29] output length; on return it holds the state after the proof-of-work
+ * response and the query indices were drawn.  fri_out receives the FriProof part of the flat proof layout (DESIGN.md
+ * section 5: commit-phase caps, query rounds, final polynomial, pow witness), p2g_fri_proof_words(c) words. */
+size_t p2g_fri_proof_words(const p2g_circuit* c);
+int32_t p2g_fri_prove(p2g_ctx* ctx, const p2g_circuit* c, const p2g_batch* wires, const p2g_batch* zs, const p2g_batch* quotient,
+                      const uint64_t zeta[2], uint64_t* challenger_io, uint64_t* fri_out, size_t fri_cap_words, size_t* fri_words_out);
 /* Batch of independent proofs (BASELINE config 5): proof i is proved on context i mod n_ctx, one host thread per
  * context inside the call; contexts may sit on one GPU (several proofs in flight) or on several.  circuits[t] must
  * have been loaded on ctxs[t].  status_out[i] receives each proof's return code; returns the first failure. */

@@ -455,12 +455,27 @@ struct ShardHost {
     p2g_exchange_fn exchange; void* user;
 };
 
+// p2g_fri_prove: prove_impl entered at prove_openings with the caller's batches, evaluation point and transcript
+struct FriResume {
+    const p2g_batch *wires, *zs, *quotient;
+    ext_t zeta;
+    uint64_t* challenger_io;      // [12 state][8 input buffer][8 output buffer][input length][output length]
+};
+static size_t fri_part_words(const p2g_circuit* C) {
+    // the flat proof minus the three caps, the openings and the public inputs
+    const p2g_circuit_desc& d = C->d;
+    const int nlp = num_lookup_polys(d), nch = d.num_challenges;
+    const int NC = d.num_selectors + d.num_lookup_selectors + d.num_constants;
+    const size_t open = 2 * ((size_t)NC + d.num_routed_wires + d.num_wires + 2 * nch + (size_t)nch * d.num_partial_products +
+                             (size_t)nch * d.quotient_degree_factor + 2 * (size_t)nch * nlp);
+    return C->proof_words - 3 * ((size_t)4 << d.cap_height) - open - (size_t)d.num_public_inputs;
+}
 static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wires_in, bool wires_on_host,
                           const uint64_t* public_inputs, uint64_t* proof_out, size_t proof_cap, size_t* proof_words_out,
-                          const ShardHost* sh = nullptr) {
-    if (!ctx || !C || !d_wires_in || !proof_out) return P2G_E_BADARG;
-    if (proof_cap < C->proof_words) return P2G_E_BADARG;
-    if (C->d.num_public_inputs > 0 && !public_inputs) { ctx->err = "public_inputs is NULL"; return P2G_E_BADARG; }
+                          const ShardHost* sh = nullptr, const FriResume* fr = nullptr) {
+    if (!ctx || !C || (!fr && !d_wires_in) || !proof_out) return P2G_E_BADARG;
+    if (proof_cap < (fr ? fri_part_words(C) : C->proof_words)) return P2G_E_BADARG;
+    if (!fr && C->d.num_public_inputs > 0 && !public_inputs) { ctx->err = "public_inputs is NULL"; return P2G_E_BADARG; }
     CU(cudaSetDevice(ctx->device));
     const p2g_circuit_desc& d = C->d;
     const CircuitDev& cd = C->cd;
@@ -512,11 +527,29 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     const bool dbg = getenv("P2G_DEBUG") != nullptr;
 #define DBG(msg) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[p2g] %s (%s)\n", msg, cudaGetErrorString(e_)); } } while (0)
 
+    gl_t* d_wires = nullptr;
+    p2g_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
+    std::vector<gl_t> wcap, zcap, qcap;
+    Challenger ch;
+    ProofConsts* pc_host = (ProofConsts*)(ctx->pinned + ctx->pinned_words / 2);   // upper half of the pinned staging buffer (the lower half receives D2H results)
+    static_assert(sizeof(ProofConsts) < 16384, "ProofConsts too large");
+    gl_t deltas_flat[16] = {0};
+    ProofConsts* d_pc = nullptr;
+    gl_t* d_lut_evals = nullptr;
+    ext_t zeta;
+    if (fr) {
+        // p2g_fri_prove: the commitments, the transcript up to the openings and zeta are the caller's
+        wb = const_cast<p2g_batch*>(fr->wires); zb = const_cast<p2g_batch*>(fr->zs); qb = const_cast<p2g_batch*>(fr->quotient);
+        memcpy(ch.state, fr->challenger_io, 12 * sizeof(gl_t));
+        memcpy(ch.in_buf, fr->challenger_io + 12, 8 * sizeof(gl_t));
+        memcpy(ch.out_buf, fr->challenger_io + 20, 8 * sizeof(gl_t));
+        ch.in_len = (int)fr->challenger_io[28]; ch.out_len = (int)fr->challenger_io[29];
+        zeta = fr->zeta;
+    } else {
     gl_t pi_hash[4];
     host_hash_no_pad(public_inputs, (size_t)d.num_public_inputs, pi_hash);
 
     // ---- stage A: wires ----
-    gl_t* d_wires = nullptr;
     const gl_t* wires = d_wires_in;
     if (wires_on_host) {
         if ((rc = S.alloc(&d_wires, (size_t)W * n))) return rc;
@@ -524,19 +557,13 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         wires = d_wires;
     }
     tm.mark();
-    p2g_batch *wb = nullptr, *zb = nullptr, *qb = nullptr;
-    std::vector<gl_t> wcap, zcap, qcap;
     if ((rc = commit(1, wires, W, true, &wb, wcap))) return rc;
     tm.mark();
 
     DBG("wires committed");
-    Challenger ch;
     ch.observe_many(d.circuit_digest, 4);
     ch.observe_many(pi_hash, 4);
     ch.observe_many(wcap.data(), capw);
-    ProofConsts* pc_host = (ProofConsts*)(ctx->pinned + ctx->pinned_words / 2);   // upper half of the pinned staging buffer (the lower half receives D2H results)
-    static_assert(sizeof(ProofConsts) < 16384, "ProofConsts too large");
-    gl_t deltas_flat[16] = {0};
     {
         gl_t betas[MAX_CH], gammas[MAX_CH];
         for (int i = 0; i < nch; i++) betas[i] = ch.get();
@@ -549,10 +576,8 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         }
         fill_consts(pc_host, C, betas, gammas, deltas_flat, pi_hash);
     }
-    ProofConsts* d_pc;
     CU(S.alloc_bytes((void**)&d_pc, sizeof(ProofConsts)));
     CU(cudaMemcpyAsync(d_pc, pc_host, sizeof(ProofConsts), cudaMemcpyHostToDevice, st));
-    gl_t* d_lut_evals;
     if ((rc = S.alloc(&d_lut_evals, MAX_CH * 8))) return rc;
     if (has_lookup) {
         P2G_COUNT_LAUNCH(1); lut_eval_kernel<<<dim3(cd.num_luts, nch), 1024, 0, st>>>(cd, d_pc, C->d_lut_data, C->d_lut_off, C->d_lut_len, d_lut_evals);
@@ -616,11 +641,12 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     S.free(d_qv); S.free(d_qa); S.free(d_qc);
     tm.mark();
     ch.observe_many(qcap.data(), capw);
-    const ext_t zeta = ch.get_ext();
+    zeta = ch.get_ext();
+    DBG("quotient committed");
+    }   // !fr
     const gl_t g = gl_root_of_unity(logn);
     const ext_t zeta_next = ext_mul_base(zeta, g);
 
-    DBG("quotient committed");
     // ---- openings ----
     const p2g_batch* oracles[4] = {C->cs, wb, zb, qb};
     const int tot0 = NC + R + W + zpp + nch * qdf + nlz, tot1 = nch + nlz;
@@ -655,10 +681,10 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     CU(ctx_wait(ctx));
     memcpy(open.data(), ctx->pinned, open.size() * sizeof(ext_t));
     tm.mark();
-    ch.observe_many((const gl_t*)open.data(), 2 * open.size());
-
-    // ---- proof assembly starts: caps + openings ----
+    // ---- proof assembly starts: caps + openings (p2g_fri_prove: the caller has them and has observed them) ----
     gl_t* w = proof_out;
+    if (!fr) {
+    ch.observe_many((const gl_t*)open.data(), 2 * open.size());
     memcpy(w, wcap.data(), capw * 8); w += capw;
     memcpy(w, zcap.data(), capw * 8); w += capw;
     memcpy(w, qcap.data(), capw * 8); w += capw;
@@ -676,6 +702,7 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
         put(o0 + off, nlz);                      // lookup_zs
         put(o1 + nch, nlz);                      // lookup_zs_next
     }
+    }   // !fr
 
     DBG("openings done");
     // ---- prove_openings: batch combination ----
@@ -875,12 +902,12 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     w += rec * nq;
     memcpy(w, fcoef.data(), final_len * sizeof(ext_t)); w += 2 * final_len;
     *w++ = pow_witness;
-    for (int i = 0; i < d.num_public_inputs; i++) *w++ = public_inputs[i];
+    if (!fr) for (int i = 0; i < d.num_public_inputs; i++) *w++ = public_inputs[i];
     tm.mark();
     tm.finish(&ctx->timings);
 
     // transcript for parity tests
-    {
+    if (!fr) {
         p2g_transcript& tr = ctx->transcript; memset(&tr, 0, sizeof(tr));
         for (int i = 0; i < nch; i++) { tr.betas[i] = pc_host->betas[i]; tr.gammas[i] = pc_host->gammas[i]; tr.alphas[i] = pc_host->alphas[i]; }
         memcpy(tr.deltas, deltas_flat, sizeof(gl_t) * 4 * nch);
@@ -895,9 +922,15 @@ static int32_t prove_impl(p2g_ctx* ctx, const p2g_circuit* C, const gl_t* d_wire
     S.free(d_vals); S.free(d_comp); S.free(d_comp_lde); S.free(d_zp); S.free(d_apow); S.free(d_open);
     S.free(d_lut_evals);
     S.free(d_plist); S.free(d_gt); S.free(d_qidx); S.free(d_q); S.free(d_pc);
-    S.free_batch(wb); S.free_batch(zb); S.free_batch(qb);
+    if (!fr) { S.free_batch(wb); S.free_batch(zb); S.free_batch(qb); }
     if (d_wires) S.free(d_wires);
-    if ((size_t)(w - proof_out) != C->proof_words) { ctx->err = "proof length mismatch"; return P2G_E_BADARG; }
+    if (fr) {
+        memcpy(fr->challenger_io, ch.state, 12 * sizeof(gl_t));
+        memcpy(fr->challenger_io + 12, ch.in_buf, 8 * sizeof(gl_t));
+        memcpy(fr->challenger_io + 20, ch.out_buf, 8 * sizeof(gl_t));
+        fr->challenger_io[28] = (uint64_t)ch.in_len; fr->challenger_io[29] = (uint64_t)ch.out_len;
+    }
+    if ((size_t)(w - proof_out) != (fr ? fri_part_words(C) : C->proof_words)) { ctx->err = "proof length mismatch"; return P2G_E_BADARG; }
     if (proof_words_out) *proof_words_out = (size_t)(w - proof_out);
     return P2G_OK;
 }
@@ -995,6 +1028,27 @@ extern "C" int32_t p2g_open(p2g_ctx* ctx, const p2g_batch* const* batches, uint3
     CU(cudaMemcpyAsync(openings_out, d_open, 2 * tot * sizeof(gl_t), cudaMemcpyDeviceToHost, ctx->st));
     CU(ctx_wait(ctx));               // the host vector of pointers dies with this frame
     return P2G_OK;
+}
+
+// PolynomialBatch::prove_openings + fri_proof on their own: batch combination at zeta and g zeta, LDE, commit phase,
+// proof of work (lowest nonce) and query rounds, with the caller's commitments and transcript
+extern "C" size_t p2g_fri_proof_words(const p2g_circuit* C) { return C ? fri_part_words(C) : 0; }
+extern "C" int32_t p2g_fri_prove(p2g_ctx* ctx, const p2g_circuit* C, const p2g_batch* wires, const p2g_batch* zs, const p2g_batch* quotient,
+                                 const uint64_t zeta[2], uint64_t* challenger_io, uint64_t* fri_out, size_t fri_cap_words,
+                                 size_t* fri_words_out) {
+    if (!ctx || !C || !wires || !zs || !quotient || !zeta || !challenger_io || !fri_out || zeta[0] >= GL_P || zeta[1] >= GL_P) return P2G_E_BADARG;
+    const CircuitDev& cd = C->cd;
+    const p2g_batch* bs[3] = {wires, zs, quotient};
+    const uint32_t cols[3] = {(uint32_t)cd.W, (uint32_t)cd.zs_cols, (uint32_t)(cd.nch * cd.qdf)};
+    for (int i = 0; i < 3; i++)
+        if (bs[i]->ncols != cols[i] || bs[i]->log_n != (uint32_t)cd.logn || bs[i]->rate_bits != (uint32_t)cd.rate_bits ||
+            bs[i]->blk_log != (uint32_t)cd.rate_bits || bs[i]->cap_height != (uint32_t)C->d.cap_height) {
+            ctx->err = "batches do not match the circuit (columns, degree, cap height, whole LDE domain)"; return P2G_E_BADARG;
+        }
+    if (challenger_io[28] > 7 || challenger_io[29] > 8) { ctx->err = "bad challenger buffer lengths"; return P2G_E_BADARG; }
+    for (int i = 0; i < 28; i++) if (challenger_io[i] >= GL_P) { ctx->err = "non-canonical challenger word"; return P2G_E_BADARG; }
+    FriResume fr = {wires, zs, quotient, ext_make(zeta[0], zeta[1]), challenger_io};
+    return prove_impl(ctx, C, nullptr, false, nullptr, fri_out, fri_cap_words, fri_words_out, nullptr, &fr);
 }
 
 // p2g_prove for a batch: proof i runs on context i mod n_ctx, one host thread per context, so the latency-bound

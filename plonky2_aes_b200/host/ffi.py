@@ -101,6 +101,8 @@ SIGNATURES = {
     "p2g_debug_canary": (C.c_int32, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "p2g_quotient": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp]),
     "p2g_open": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp]),
+    "p2g_fri_proof_words": (C.c_size_t, [_vp]),
+    "p2g_fri_prove": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2g_prove_batch": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp, C.c_size_t, _vp]),
     "p2g_prove_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2g_last_transcript": (C.c_int32, [_vp, C.POINTER(Transcript)]),

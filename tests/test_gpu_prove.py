@@ -543,4 +543,71 @@ def test_staged_quotient_and_openings(gpu_ctx, oracle):
         gpu_ctx.check(lib.p2g_open(gpu_ctx.handle, (C.c_void_p * 2)(wb.handle, qb.handle), 2, zeta.ctypes.data, out.ctypes.data))
         assert np.array_equal(out[:wb.ncols].ravel(), pr["openings.wires"])
         assert np.array_equal(out[wb.ncols:].ravel(), pr["openings.quotient_polys"])
+        # p2g_fri_prove: the transcript replayed on the host (Challenger of iop/challenger.rs over the oracle's
+        # permutation) up to the openings, then the FRI part of the proof from the staged entry point
+        ch = _Challenger(oracle)
+        pi_hash = oracle.hash_no_pad(pin) if pin is not None and len(pin) else np.zeros(4, dtype=np.uint64)
+        ch.observe(data.circuit_digest); ch.observe(pi_hash); ch.observe(pr["wires_cap"])
+        b_ = [ch.get() for _ in range(nch)]; g_ = [ch.get() for _ in range(nch)]
+        assert b_ == list(betas) and g_ == list(gammas)
+        if d.num_luts:
+            extra = [ch.get() for _ in range(2 * nch)]
+            assert b_ + g_ + extra == list(deltas)
+        ch.observe(pr["plonk_zs_partial_products_cap"])
+        assert [ch.get() for _ in range(nch)] == list(alphas)
+        ch.observe(pr["quotient_polys_cap"])
+        assert [ch.get(), ch.get()] == list(zeta)
+        for name in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys", "lookup_zs",
+                     "plonk_zs_next", "lookup_zs_next"):
+            ch.observe(pr["openings." + name])
+        io = ch.export()
+        fw = lib.p2g_fri_proof_words(data._gpu_circuit)
+        fri = np.empty(fw, dtype=np.uint64)
+        got = C.c_size_t()
+        gpu_ctx.check(lib.p2g_fri_prove(gpu_ctx.handle, data._gpu_circuit, wb.handle, zb.handle, qb.handle, zeta.ctypes.data,
+                                        io.ctypes.data, fri.ctypes.data, fw, C.byref(got)))
+        npi = 0 if pi is None else len(pi)
+        tail = proof[len(proof) - npi - fw:len(proof) - npi]
+        assert got.value == fw and np.array_equal(fri, tail), "FRI part of the proof"
+        assert int(io[28]) <= 7 and int(io[29]) <= 8
+        # refused: a non-canonical transcript word, a batch of the wrong shape
+        bad = io.copy(); bad[3] = P
+        assert lib.p2g_fri_prove(gpu_ctx.handle, data._gpu_circuit, wb.handle, zb.handle, qb.handle, zeta.ctypes.data,
+                                 bad.ctypes.data, fri.ctypes.data, fw, None) == -2
+        assert lib.p2g_fri_prove(gpu_ctx.handle, data._gpu_circuit, zb.handle, wb.handle, qb.handle, zeta.ctypes.data,
+                                 io.ctypes.data, fri.ctypes.data, fw, None) == -2
         wb.free(); zb.free(); qb.free()
+
+
+class _Challenger:
+    """Challenger<F, PoseidonHash> (iop/challenger.rs): duplex sponge of rate 8; get() pops the output buffer from its end"""
+
+    def __init__(self, oracle):
+        self.o, self.state, self.inb, self.outb = oracle, np.zeros(12, dtype=np.uint64), [], []
+
+    def _duplex(self):
+        for i, v in enumerate(self.inb):
+            self.state[i] = v
+        self.inb = []
+        self.state = self.o.poseidon(self.state)
+        self.outb = [int(v) for v in self.state[:8]]
+
+    def observe(self, xs):
+        for x in np.asarray(xs, dtype=np.uint64).ravel():
+            self.outb = []
+            self.inb.append(int(x))
+            if len(self.inb) == 8:
+                self._duplex()
+
+    def get(self):
+        if self.inb or not self.outb:
+            self._duplex()
+        return self.outb.pop()
+
+    def export(self):
+        io = np.zeros(30, dtype=np.uint64)
+        io[:12] = self.state
+        io[12:12 + len(self.inb)] = self.inb
+        io[20:20 + len(self.outb)] = self.outb
+        io[28], io[29] = len(self.inb), len(self.outb)
+        return io
