@@ -16,20 +16,21 @@ extern std::atomic<unsigned long long> g_p2g_launches;
 // ---- NTT (ntt.cu) -------------------------------------------------------------------------
 // A plan = device tables for one transform shape.  The transform of size n = R * M runs as
 // R * variants thread blocks per column: block (variant, q) folds the first log2(R) DIF stages,
-// the coset/inverse scaling and the variant shift into one table multiply
-//     y_q[t] = sum_k x[t + k*M] * T[variant][q][k][t]
+// the coset/inverse scaling and the variant shift into its load phase
+//     y_q[t] = sum_k x[t + k*M] * base_q^(t + kM)
 // and then runs a size-M decimation-in-frequency transform entirely in shared memory.
 enum { NTT_KIND_LDE = 0, NTT_KIND_INV = 1 };
-// Two shapes.  Direct (R <= 4): the table holds base^(t + kM) for every k, T = [variants][R][R][M], and a block
-// does R multiplications per point on load.  Pre-folded (R >= 8, prefold = 1): a first kernel (ntt_outer_kernel)
-// multiplies x[t + kM] by shift^(kM) (C, [variants][R]) and runs the R-point transform over k for every t, leaving
-// Z[q][t] where block q will read it; the table is base_q^t only, T = [variants][R][M] -- linear in n -- and the
+// Two shapes, one table T[variant][q][t] = base_q^t (t < M; times 1/n for the inverse) -- V n words, linear in n.
+// Direct (R <= 4): block (variant, q) computes y_q[t] = base_q^t * sum_k x[t + kM] * base_q^(kM) with the R per-block
+// constants base_q^(kM) from C ([variants][R][R]): R - 1 products summed unreduced + one table multiplication per point.
+// Pre-folded (R >= 8, prefold = 1): a first kernel (ntt_outer_kernel) multiplies x[t + kM] by shift^(kM) (C,
+// [variants][R]) and runs the R-point transform over k for every t, leaving Z[q][t] where block q will read it; the
 // size-M kernel does one multiplication per point on load.
 struct NttPlan {
     int kind, log_n, log_m, log_r, log_variants, prefold;
-    gl_t* T;    // direct: [variants][R][R][M]; pre-folded: [variants][R][M]
+    gl_t* T;    // [variants][R][M]
     gl_t* tw;   // per-pass compact twiddle tables (forward or inverse roots), tw_words entries
-    gl_t* C;    // pre-folded only: [variants][R] input scale factors, then R/2 twiddles of the R-point transform
+    gl_t* C;    // direct: [variants][R][R] constants base_q^(kM); pre-folded: [variants][R] input scale factors, then R/2 twiddles of the R-point transform
     int tw_words;
 };
 // largest transform: 2^21 points (R = 2^7 chunks of 2^14); the provers accept degree_bits <= 20

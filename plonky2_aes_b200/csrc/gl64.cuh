@@ -169,6 +169,26 @@ __device__ __forceinline__ gl_t gl_mul2_lazy(gl_t a, gl_t b, gl_t c, gl_t d) {
         : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "=r"(h2) : "r"(m0), "r"(m1), "r"(n0), "r"(n1));
     return gl_fold5(l0, l1, h0, h1, h2);
 }
+// a*b + c (all any u64) -> lazy residue
+__device__ __forceinline__ gl_t gl_mad_lazy(gl_t a, gl_t b, gl_t c) {
+    uint32_t l0, l1, h0, h1, c0, c1, h2;
+    pmul128(a, b, l0, l1, h0, h1); gl_unpack(c, c0, c1);
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, 0, 0;"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "=r"(h2) : "r"(c0), "r"(c1));
+    return gl_fold5(l0, l1, h0, h1, h2);
+}
+// a*b + c*d + e*f + g (all any u64) -> lazy residue: three 128-bit products and a word summed in 160 bits, one fold
+__device__ __forceinline__ gl_t gl_mad3_lazy(gl_t a, gl_t b, gl_t c, gl_t d, gl_t e, gl_t f, gl_t g) {
+    uint32_t l0, l1, h0, h1, m0, m1, n0, n1, p0, p1, q0, q1, g0, g1, h2;
+    pmul128(a, b, l0, l1, h0, h1); pmul128(c, d, m0, m1, n0, n1); pmul128(e, f, p0, p1, q0, q1); gl_unpack(g, g0, g1);
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, 0, 0;"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "=r"(h2) : "r"(m0), "r"(m1), "r"(n0), "r"(n1));
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\taddc.u32 %4, %4, 0;"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "+r"(h2) : "r"(p0), "r"(p1), "r"(q0), "r"(q1));
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, %4, 0;"
+        : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1), "+r"(h2) : "r"(g0), "r"(g1));
+    return gl_fold5(l0, l1, h0, h1, h2);
+}
 #else
 // any u64 * any u64 -> lazy residue
 GL_HD gl_t gl_mul_lazy(gl_t a, gl_t b) {
@@ -178,6 +198,10 @@ GL_HD gl_t gl_mul_lazy(gl_t a, gl_t b) {
 }
 GL_HD gl_t gl_mul2_lazy(gl_t a, gl_t b, gl_t c, gl_t d) {
     return gl_add_lazy(gl_mul_lazy(a, b), gl_canon(gl_mul_lazy(c, d)));
+}
+GL_HD gl_t gl_mad_lazy(gl_t a, gl_t b, gl_t c) { return gl_add_lazy(gl_mul_lazy(a, b), gl_canon(c)); }
+GL_HD gl_t gl_mad3_lazy(gl_t a, gl_t b, gl_t c, gl_t d, gl_t e, gl_t f, gl_t g) {
+    return gl_add_lazy(gl_add_lazy(gl_mul_lazy(a, b), gl_canon(gl_mul_lazy(c, d))), gl_canon(gl_add_lazy(gl_mul_lazy(e, f), gl_canon(g))));
 }
 #endif
 // any * any -> canonical

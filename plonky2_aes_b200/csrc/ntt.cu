@@ -138,7 +138,7 @@ ntt_outer_kernel(const gl_t* in, size_t in_stride, gl_t* z, size_t z_stride, con
 
 __global__ void __launch_bounds__(512, 1)
 ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__ out, size_t out_stride,
-               const gl_t* __restrict__ T, const gl_t* __restrict__ tw,
+               const gl_t* __restrict__ T, const gl_t* __restrict__ tw, const gl_t* __restrict__ D,
                int log_n, int log_m, int log_variants, int out_mode, uint32_t blk_first, int inverse, uint32_t tw_skip, int prefold) {
     extern __shared__ gl_t sm[];
     const int log_r = log_n - log_m;
@@ -152,7 +152,8 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
     // pre-folded plans: `in` holds Z[q][t] at blk_local * n + q * M + t (possibly the output buffer itself: the block
     // has read its M words before anyone writes) and the table is base_q^t only
     const gl_t* x = in + (size_t)col * in_stride + (prefold ? ((size_t)blk_local << log_n) + ((size_t)q << log_m) : 0);
-    const gl_t* Tq = T + ((size_t)(variant * R + q) << (prefold ? log_m : log_n));   // [k][t], or [t]
+    const gl_t* Tq = T + ((size_t)(variant * R + q) << log_m);       // base_q^t, t < M (times 1/n for the inverse)
+    const gl_t* Dq = D + ((size_t)(variant * R + q) << log_r);       // direct plans: base_q^(kM), k < R
     // per-pass twiddle tables live behind the data in shared memory (global/L2 twiddle loads were
     // the dominant stall of this kernel: long_scoreboard 3.0 per issue, profiles/)
     // tw_skip: leading table words left in global memory (the block-size-2^13 table of the two-blocks-
@@ -182,41 +183,56 @@ ntt_dif_kernel(const gl_t* __restrict__ in, size_t in_stride, gl_t* __restrict__
             for (uint32_t t = tid; t < M; t += nth) sm[smpad(t)] = gl_mul(x[t], __ldg(Tq + t));
         }
     } else if (R <= 2 && (M % (8 * nth)) == 0) {
+        // y[t] = base^t (x[t] + base^M x[t + M]): one table word per point, the per-block constant in a register
+        const gl_t c1 = R == 2 ? __ldg(Dq + 1) : 0;
         for (uint32_t t0 = tid; t0 < M; t0 += 8 * nth) {
-            gl_t xv[8][2], tv[8][2];
+            gl_t xv[8][2], tv[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const uint32_t t = t0 + u * nth;
-                xv[u][0] = __ldg(x + t); tv[u][0] = __ldg(Tq + t);
-                if (R == 2) { xv[u][1] = __ldg(x + t + M); tv[u][1] = __ldg(Tq + M + t); }
+                xv[u][0] = __ldg(x + t); tv[u] = __ldg(Tq + t);
+                if (R == 2) xv[u][1] = __ldg(x + t + M);
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                gl_t acc = gl_mul(xv[u][0], tv[u][0]);
-                if (R == 2) acc = gl_add(acc, gl_mul(xv[u][1], tv[u][1]));
-                sm[smpad(t0 + u * nth)] = acc;
+                gl_t acc = xv[u][0];
+                if (R == 2) acc = gl_mad_lazy(xv[u][1], c1, acc);
+                sm[smpad(t0 + u * nth)] = gl_mul(acc, tv[u]);
             }
         }
     } else if (R == 4 && (M % (4 * nth)) == 0) {
+        // y[t] = base^t (x[t] + c1 x[t + M] + c2 x[t + 2M] + c3 x[t + 3M]), c_k = base^(kM): the three products are
+        // summed unreduced (gl_mad3_lazy: one fold), then one multiplication by the table word -- 5 loads per point
+        // instead of 8 and a table of V R M words instead of V R n (the load phase was waiting on L2: 52 % of the
+        // kernel's samples for 32 % of its instructions)
+        const gl_t c1 = __ldg(Dq + 1), c2 = __ldg(Dq + 2), c3 = __ldg(Dq + 3);
+        // two half-batches of two points in flight: the loads of one are issued before the arithmetic of the other
+        gl_t xa[2][4], ta[2], xb[2][4], tb[2];
+#define NTT_LD4(XV, TV, T0) do {                                                          \
+            _Pragma("unroll") for (int u = 0; u < 2; u++) {                               \
+                const uint32_t t = (T0) + u * nth;                                        \
+                TV[u] = __ldg(Tq + t);                                                    \
+                _Pragma("unroll") for (int k = 0; k < 4; k++) XV[u][k] = __ldg(x + t + k * M); \
+            } } while (0)
+#define NTT_FOLD4(XV, TV, T0) do {                                                        \
+            _Pragma("unroll") for (int u = 0; u < 2; u++)                                 \
+                sm[smpad((T0) + u * nth)] = gl_mul(gl_mad3_lazy(XV[u][1], c1, XV[u][2], c2, XV[u][3], c3, XV[u][0]), TV[u]); \
+            } while (0)
+        NTT_LD4(xa, ta, tid);
         for (uint32_t t0 = tid; t0 < M; t0 += 4 * nth) {
-            gl_t xv[4][4], tv[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t t = t0 + u * nth;
-#pragma unroll
-                for (int k = 0; k < 4; k++) { xv[u][k] = __ldg(x + t + k * M); tv[u][k] = __ldg(Tq + (size_t)k * M + t); }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                sm[smpad(t0 + u * nth)] = gl_add(gl_canon(gl_mul2_lazy(xv[u][0], tv[u][0], xv[u][1], tv[u][1])),
-                                                 gl_canon(gl_mul2_lazy(xv[u][2], tv[u][2], xv[u][3], tv[u][3])));
+            NTT_LD4(xb, tb, t0 + 2 * nth);
+            NTT_FOLD4(xa, ta, t0);
+            if (t0 + 4 * nth < M) NTT_LD4(xa, ta, t0 + 4 * nth);
+            NTT_FOLD4(xb, tb, t0 + 2 * nth);
         }
+#undef NTT_LD4
+#undef NTT_FOLD4
     } else {
         for (uint32_t t = tid; t < M; t += nth) {
-            gl_t acc = gl_mul(__ldg(x + t), __ldg(Tq + t));
+            gl_t acc = __ldg(x + t);
             for (uint32_t k = 1; k < R; k++)
-                acc = gl_add(acc, gl_mul(__ldg(x + t + ((size_t)k << log_m)), __ldg(Tq + ((size_t)k << log_m) + t)));
-            sm[smpad(t)] = acc;
+                acc = gl_add(acc, gl_mul(__ldg(x + t + ((size_t)k << log_m)), __ldg(Dq + k)));
+            sm[smpad(t)] = gl_mul(acc, __ldg(Tq + t));
         }
     }
     __syncthreads();
@@ -286,7 +302,7 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
     plan->log_variants = kind == NTT_KIND_LDE ? rate_bits : 0;
     const size_t n = (size_t)1 << log_n, M = (size_t)1 << plan->log_m, R = (size_t)1 << plan->log_r;
     const size_t V = (size_t)1 << plan->log_variants;
-    std::vector<gl_t> T(plan->prefold ? V * R * M : V * R * n), tw(M / 2 ? M / 2 : 1), Cs;
+    std::vector<gl_t> T(V * R * M), tw(M / 2 ? M / 2 : 1), Cs;
     gl_t wn = gl_root_of_unity(log_n);
     gl_t wN = gl_root_of_unity(log_n + plan->log_variants);
     gl_t wm = gl_root_of_unity(plan->log_m);
@@ -297,9 +313,19 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
         for (size_t q = 0; q < R; q++) {
             gl_t base = gl_mul(shift, gl_pow(wn, gl_bitrev((uint32_t)q, plan->log_r)));
             gl_t x = kind == NTT_KIND_INV ? ninv : 1;
-            const size_t len = plan->prefold ? M : n;
-            gl_t* dst = T.data() + (v * R + q) * len;   // index j = t + k*M  == [k][t]; pre-folded: k = 0 only
-            for (size_t j = 0; j < len; j++) { dst[j] = x; x = gl_mul(x, base); }
+            gl_t* dst = T.data() + (v * R + q) * M;
+            for (size_t j = 0; j < M; j++) { dst[j] = x; x = gl_mul(x, base); }
+        }
+    }
+    if (!plan->prefold) {
+        // direct plans: D[v][q][k] = base_q^(kM), the per-block constants of the load phase
+        Cs.resize(V * R * R);
+        for (size_t v = 0; v < V; v++) {
+            gl_t shift = kind == NTT_KIND_LDE ? gl_mul(7, gl_pow(wN, v)) : 1;
+            for (size_t q = 0; q < R; q++) {
+                gl_t step = gl_pow(gl_mul(shift, gl_pow(wn, gl_bitrev((uint32_t)q, plan->log_r))), M), x = 1;
+                for (size_t k = 0; k < R; k++) { Cs[(v * R + q) * R + k] = x; x = gl_mul(x, step); }
+            }
         }
     }
     if (plan->prefold) {
@@ -330,7 +356,7 @@ int ntt_plan_build(NttPlan* plan, int kind, int log_n, int rate_bits, cudaStream
     }
     if (cudaMalloc(&plan->T, T.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); return -2; }
     if (cudaMalloc(&plan->tw, tw.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); ntt_plan_free(plan); return -2; }
-    if (plan->prefold) {
+    {
         if (cudaMalloc(&plan->C, Cs.size() * sizeof(gl_t)) != cudaSuccess) { cudaGetLastError(); ntt_plan_free(plan); return -2; }
         if (cudaMemcpyAsync(plan->C, Cs.data(), Cs.size() * sizeof(gl_t), cudaMemcpyHostToDevice, st) != cudaSuccess) { ntt_plan_free(plan); return -1; }
     }
@@ -384,7 +410,7 @@ int ntt_launch(const NttPlan* plan, const gl_t* in, size_t in_stride, gl_t* out,
             src = z; src_stride = z_stride;
         }
         ntt_dif_kernel<<<grid, threads, smem, st>>>(src, src_stride, out + (size_t)c0 * out_stride,
-                                                    out_stride, plan->T, plan->tw, plan->log_n, plan->log_m,
+                                                    out_stride, plan->T, plan->tw, plan->C, plan->log_n, plan->log_m,
                                                     plan->log_variants, out_mode, blk_first, plan->kind == NTT_KIND_INV ? 1 : 0, tw_skip, plan->prefold);
         P2G_COUNT_LAUNCH(1);
     }
