@@ -127,11 +127,12 @@ def test_poseidon_extreme_words(gpu_ctx, oracle):
     t.free()
 
 
-@pytest.mark.parametrize("ncols,log_n", [(20, 10), (3, 14)])
+@pytest.mark.parametrize("ncols,log_n", [(20, 10), (3, 14), (2, 17)])
 def test_coset_sharded_commit_matches_full(gpu_ctx, oracle, ncols, log_n):
     """multi-GPU coset split of one commitment, emulated on one GPU: every shard's LDE block and cap
     entries equal the corresponding slice of the full commitment (and of the oracle's).  log_n = 14
-    takes the 2^13-point / two-blocks-per-SM NTT configuration."""
+    takes the 2^13-point / two-blocks-per-SM NTT configuration, log_n = 17 the pre-folded one (outer kernel on a
+    subset of the cosets)."""
     import ctypes as C
     import torch
     from plonky2_aes_b200.host.sharding import sharded_commit
