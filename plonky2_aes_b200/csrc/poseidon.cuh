@@ -4,18 +4,22 @@
 // /root/reference/aes-gcm/src/circuit_gcm.rs:781 `data.prove(pw)` and directly from
 // /root/reference/feistel/src/lib.rs:106 `hash_n_to_hash_no_pad`).
 //
-// Device design (one permutation per thread, everything in registers):
-//  * the INT pipes are the roofline (profiles/r1_int_pipes_microbench.jsonl: IMAD.WIDE.U32 and
-//    IADD3 both issue every 2nd/1st cycle per SM sub-partition, 64-bit mul.hi is 13 cycles), so
-//    the field multiply is written on 32-bit halves: 4 IMAD.WIDE + a carry chain, then the
-//    Goldilocks fold  hi*2^64 = hi_lo*(2^32-1) - hi_hi  with ONE more IMAD.WIDE;
-//  * the MDS layer uses the small circulant coefficients (<= 41): 32-bit halves of the state
-//    are accumulated with IMAD.WIDE chains (12 * 41 * 2^32 < 2^42, no carries) and the NEXT
-//    round's constants are the initial value of those accumulators, so adding round constants
-//    costs nothing;
+// Device design (one permutation per thread, everything in registers; DESIGN.md section 3 has the measurements):
+//  * the permutation is bound by instruction issue: on B200 an FP64 instruction and an IMAD.WIDE hold the issue port
+//    of a sub-partition for two cycles, IMAD.WIDE occupies the fmaheavy pipe for four
+//    (profiles/r2_issue_rate_microbench.jsonl), so the design minimises issue slots;
+//  * S-box: x^2 and x^4 as three-product squarings, x^3 and x^7 on the compiler's 128-bit product (four IMAD.WIDE
+//    whose 64-bit addend and carry absorb the partial-product additions), each followed by the Goldilocks fold
+//    hi*2^64 = hi_lo*(2^32-1) - hi_hi  as a 12-instruction carry chain;
+//  * linear layers on the otherwise idle FP64 pipe: the 32-bit halves of the state are exact doubles, the circulant
+//    coefficients are small, every partial sum stays below 2^53, and the accumulators start at 2^52 + round
+//    constant so the integer result is read straight from the mantissa words.  The circulant splits twice
+//    (12 -> 6 + 6 -> 3 + 3 + 6): 184 FP64 instructions per full round instead of 290;
+//  * the 22 partial rounds run as 11 merged pairs: u = circ(C*C) s' + cc (8 y0 + z - t0) + 8 (z - cA0) e0 + K, the same
+//    split product plus one rank-one term, 236 FP64 instructions and 13 accumulator read-outs per TWO rounds;
 //  * intermediate values are lazy residues (any u64); only outputs are canonicalised;
-//  * the 4+4 full rounds share one loop body and the 22 partial rounds another, keeping the hot
-//    code inside the 32 KB instruction cache.
+//  * the 4+4 full rounds share one loop body and the 11 pairs another, keeping the hot code inside the
+//    instruction cache.
 #pragma once
 #include "gl64.cuh"
 
@@ -120,10 +124,9 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
 // which IMAD.WIDE does not (profiles/r1_int_pipes_microbench.jsonl: dfma+iadd3 2.08 cyc/pair,
 // imad.wide+iadd3 5.3).  Accumulators start at 2^52 + round constant, so the integer result can
 // be read straight out of the mantissa with no conversion instruction.
-// SBOX_ALL: apply the S-box to every word right before it enters the accumulation (full rounds),
-// so the IMAD/IADD3 work of word i+1 overlaps the DFMAs of word i inside one warp.
-// Otherwise (partial rounds) only word 0 goes through the S-box and it is accumulated LAST, so
-// the 264 DFMAs of the other words hide the latency of that dependent multiply chain.
+// SBOX_ALL: every word goes through the S-box before it enters the accumulation (full rounds).
+// Otherwise (single partial rounds, used only when P2G_PARTIAL_PAIRS is 0) only word 0 does and its group is
+// accumulated LAST, so the DFMAs of the other words hide the latency of that dependent multiply chain.
 // accumulators start at 2^52 + constant: the integer sits in the low mantissa bits (an F2I readout
 // from plain-constant accumulators was measured slower: 0.96 vs 0.99 G perm/s)
 // Raw words of the double, exponent bits included: the offset they add to the state word
