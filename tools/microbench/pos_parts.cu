@@ -12,9 +12,15 @@
 #define TAG "base"
 #endif
 #define ITERS 512
+#ifndef TPB
+#define TPB 256
+#endif
+#ifndef MINB
+#define MINB 3
+#endif
 
 template <int OP>
-__global__ void __launch_bounds__(256, 3) k(gl_t* out, uint32_t iters) {
+__global__ void __launch_bounds__(TPB, MINB) k(gl_t* out, uint32_t iters) {
 #if defined(__CUDA_ARCH__)
     gl_t s[12];
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,25 +106,25 @@ __global__ void __launch_bounds__(256, 3) k(gl_t* out, uint32_t iters) {
 }
 template <int OP> void run(const char* name, double units, gl_t* d, int sms, uint32_t iters) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int blocks = sms * 3 * 4;
-    k<OP><<<blocks, 256>>>(d, iters);
+    const int blocks = sms * MINB * 4;
+    k<OP><<<blocks, TPB>>>(d, iters);
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
-        cudaEventRecord(e0); k<OP><<<blocks, 256>>>(d, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventRecord(e0); k<OP><<<blocks, TPB>>>(d, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
-    const double warp_units = (double)blocks * 8 * iters * units;
+    const double warp_units = (double)blocks * (TPB / 32) * iters * units;
     const double cyc = best * 1e-3 * 1.965e9 * sms * 4 / warp_units;
     printf("{\"tag\": \"%s\", \"op\": \"%s\", \"ms\": %.3f, \"cycles_per_unit_per_smsp\": %.1f}\n", TAG, name, best, cyc);
 }
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); const int sms = p.multiProcessorCount;
-    gl_t* d; cudaMalloc(&d, (size_t)sms * 12 * 256 * 8);
+    gl_t* d; cudaMalloc(&d, (size_t)sms * MINB * 4 * TPB * 8);
     run<0>("sbox", 12, d, sms, ITERS); run<1>("square+fold", 12, d, sms, ITERS * 4); run<2>("product only", 12, d, sms, ITERS * 4);
     run<3>("readout+2 i2f+2 dadd", 12, d, sms, ITERS * 4); run<4>("i2f+lop3", 24, d, sms, ITERS * 4); run<5>("lop3", 24, d, sms, ITERS * 4);
     run<6>("full round", 1, d, sms, ITERS); run<7>("partial pair", 1, d, sms, ITERS); run<8>("permutation", 1, d, sms, 64);
     // digest of the permutation run: equal for every arithmetic variant
-    const size_t n = (size_t)sms * 12 * 256; gl_t* h = (gl_t*)malloc(n * 8);
+    const size_t n = (size_t)sms * MINB * 4 * TPB; gl_t* h = (gl_t*)malloc(n * 8);
     cudaMemcpy(h, d, n * 8, cudaMemcpyDeviceToHost);
     gl_t dig = 0; for (size_t i = 0; i < n; i++) dig = dig * 0x100000001B3ull ^ h[i];
     printf("{\"tag\": \"%s\", \"perm_digest\": \"%016llx\"}\n", TAG, (unsigned long long)dig);
