@@ -117,6 +117,25 @@ __device__ __forceinline__ gl_t poseidon_sbox(gl_t x) {
     return pmul(x3, x4);
 #endif
 }
+// x^7 with the last product left unfolded: (h1:h0:l1:l0) = x^3 * x^4, value = (l0 - h0 - h1) + 2^32 (l1 + h0) (mod p).
+// P2G_SBOX_UNFOLDED=1 lets the full rounds hand these two limbs to the FP64 layer directly (four I2F and three FP64
+// additions instead of the 12-instruction fold and two I2F).  Measured: the full-round loop alone 1893 -> 1860 cycles
+// per warp, but the whole permutation 1.516 -> 1.497 G/s (register pressure: spills in the round loop), so it is off;
+// the bias tables carry the offset that makes it exact either way (tools/gen_poseidon_f64.py).
+#ifndef P2G_SBOX_UNFOLDED
+#define P2G_SBOX_UNFOLDED 0
+#endif
+__device__ __forceinline__ void poseidon_sbox_limbs(gl_t x, double& xl, double& xh) {
+#if P2G_SBOX_UNFOLDED && !defined(P2G_DIAG_NO_SBOX)
+    const gl_t x2 = psqr(x), x4 = psqr(x2), x3 = pmul_v1(x, x2);
+    uint32_t l0, l1, h0, h1; pmul128(x3, x4, l0, l1, h0, h1);
+    xl = __dsub_rn(__dsub_rn((double)l0, (double)h0), (double)h1);
+    xh = __dadd_rn((double)l1, (double)h0);
+#else
+    const gl_t v = poseidon_sbox(x);
+    xl = (double)(uint32_t)v; xh = (double)(uint32_t)(v >> 32);
+#endif
+}
 // s <- MDS * s + RC[next_row]   (lazy in, lazy out) on the FP64 pipe.
 // The circulant coefficients are <= 41, so every partial sum of  c_i * (32-bit half)  plus a 32-bit
 // constant stays below 2^43: DFMA on integer-valued doubles is exact, and the FP64 pipe (16
@@ -191,15 +210,13 @@ __device__ __forceinline__ void poseidon_round(gl_t s[12], int next_row) {
 #pragma unroll
     for (int jj = 0; jj < 3; jj++) {
         const int j = SBOX_ALL ? jj : (jj + 1) % 3;             // words (0, 6, 3, 9) last in partial rounds
-        gl_t v[4];
+        double xl[4], xh[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int w = j + 6 * (u & 1) + 3 * (u >> 1);        // j, j + 6, j + 3, j + 9
-            v[u] = (SBOX_ALL || w == 0) ? poseidon_sbox(s[w]) : s[w];
+            if (SBOX_ALL || w == 0) poseidon_sbox_limbs(s[w], xl[u], xh[u]);
+            else { xl[u] = (double)(uint32_t)s[w]; xh[u] = (double)(uint32_t)(s[w] >> 32); }
         }
-        double xl[4], xh[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { xl[u] = (double)(uint32_t)v[u]; xh[u] = (double)(uint32_t)(v[u] >> 32); }
 #ifdef P2G_DIAG_NO_MDS
         L.am[j] = __dadd_rn(L.am[j], __dadd_rn(__dadd_rn(xl[0], xl[1]), __dadd_rn(xl[2], xl[3])));
         H.am[j] = __dadd_rn(H.am[j], __dadd_rn(__dadd_rn(xh[0], xh[1]), __dadd_rn(xh[2], xh[3])));

@@ -121,7 +121,10 @@ text = """/* generated by tools/gen_poseidon_f64.py from poseidon_rc.inc (consta
 """
 text += table("POSEIDON_RCD_LO", [2**52 + v for v in lo]) + "\n"
 text += table("POSEIDON_RCD_HI", [2**52 + v for v in hi]) + "\n"
-RCS_LO, RCS_HI = split2([lo[12 * r:12 * r + 12] for r in range(31)], [hi[12 * r:12 * r + 12] for r in range(31)])
+# + 2 (DL, DH) on every word: the full rounds feed the S-box outputs as UNFOLDED products (low limb l0 - h0 - h1 in
+# (-2^33, 2^32), high limb l1 + h0 < 2^33), so the variable part of an accumulator can be as low as -264 * 2^33
+RCS_LO, RCS_HI = split2([[v + 2 * DL for v in lo[12 * r:12 * r + 12]] for r in range(31)],
+                        [[v + 2 * DH for v in hi[12 * r:12 * r + 12]] for r in range(31)])
 text += table("POSEIDON_RCS_LO", RCS_LO) + "\n"
 text += table("POSEIDON_RCS_HI", RCS_HI) + "\n"
 open(os.path.join(csrc, "poseidon_rc_f64.inc"), "w").write(text)
@@ -290,11 +293,12 @@ for pat in ([U] * 12, [U] * 6 + [0] * 6, [0] * 6 + [U] * 6, [0] + [U] * 11, [U] 
 print("split pair tables ok")
 
 
-# exact emulation of the split full round (poseidon_round<true>): s <- M sbox(s) + rc[next_row]
-def full_round_emulated(s, next_row):
-    x = [sbox(v) for v in s]
+# exact emulation of the split full round (poseidon_round<true>): s <- M sbox(s) + rc[next_row].  The S-box outputs
+# arrive as limb pairs (X_lo, X_hi) with value X_lo + 2^32 X_hi (mod p): the unfolded 128-bit product x^3 * x^4 gives
+# X_lo = l0 - h0 - h1, X_hi = l1 + h0
+def full_round_emulated(limbs, next_row):
     halves = []
-    for xs, tab in (([Fraction(v & 0xFFFFFFFF) for v in x], RCS_LO), ([Fraction(v >> 32) for v in x], RCS_HI)):
+    for xs, tab in (([Fraction(a) for a, _ in limbs], RCS_LO), ([Fraction(b) for _, b in limbs], RCS_HI)):
         pp = [Fraction(tab[12 * next_row + r]) for r in range(3)]
         pm = [Fraction(tab[12 * next_row + 3 + r]) for r in range(3)]
         am = [Fraction(tab[12 * next_row + 6 + r]) for r in range(6)]
@@ -304,10 +308,14 @@ def full_round_emulated(s, next_row):
     return [readout(halves[0][r], halves[1][r]) for r in range(12)]
 
 
-for pat in ([random.randrange(P) for _ in range(12)], [P - 1] * 12, [0] * 12, [0xFFFFFFFF] * 12):
+LIM = 2**33 - 2
+pats = [[(random.randrange(-LIM, 2**32), random.randrange(0, LIM)) for _ in range(12)] for _ in range(4)]
+pats += [[(-LIM, LIM)] * 12, [(2**32 - 1, LIM)] * 12, [(-LIM, 0)] * 12, [(0, 0)] * 12,
+         [(-LIM, LIM) if j < 6 else (2**32 - 1, 0) for j in range(12)], [(2**32 - 1, 0) if j < 6 else (-LIM, LIM) for j in range(12)],
+         [(-LIM, LIM) if j % 2 else (2**32 - 1, 0) for j in range(12)], [(-LIM, LIM) if (j // 3) % 2 else (2**32 - 1, 0) for j in range(12)]]
+for pat in pats:
+    vals = [(a + (b << 32)) % P for a, b in pat]
     for row in range(1, 31):
-        ref = [(a + b) % P for a, b in zip(mds([sbox(v) for v in pat]), rc_true[12 * row:12 * row + 12])]
+        ref = [(a + b) % P for a, b in zip(mds(vals), rc_true[12 * row:12 * row + 12])]
         assert full_round_emulated(pat, row) == ref, row
-# extreme S-box outputs (lazy residues up to 2^64 - 1) cannot be produced through sbox(); bound the accumulators directly
-assert 2**52 + 4 * DL + 2**34 + 264 * 2**33 < 2**53
 print("split full round ok")
