@@ -137,6 +137,25 @@ impl GpuCircuit {
         let words = self.prove(ctx, wires, public_inputs)?;
         self.desc.proof_words_to_bytes(&words)
     }
+    /// The FRI phase on its own (`PolynomialBatch::prove_openings` + `fri_proof`): `wires` / `zs` / `quotient` are raw
+    /// batch handles of this circuit (`p2g_commit_from_values*`, `p2g_quotient`), `zeta` the evaluation point and
+    /// `challenger` the caller's `Challenger` state after it observed the openings, 30 words
+    /// (12 sponge, 8 input buffer, 8 output buffer, input length, output length); it is updated in place.
+    /// Returns the FriProof part of the flat proof words.
+    pub fn fri_prove(&self, ctx: &GpuContext, wires: *const p2g_batch, zs: *const p2g_batch, quotient: *const p2g_batch,
+                     zeta: [u64; 2], challenger: &mut [u64; 30]) -> Result<Vec<u64>, GpuError> {
+        assert!(ctx.raw == self.ctx, "a circuit is bound to the context it was loaded on");
+        unsafe {
+            let cap = p2g_fri_proof_words(self.raw);
+            let mut out = vec![0u64; cap];
+            let mut n = 0usize;
+            let rc = p2g_fri_prove(ctx.raw, self.raw, wires, zs, quotient, zeta.as_ptr(), challenger.as_mut_ptr(),
+                                   out.as_mut_ptr(), cap, &mut n);
+            if rc != P2G_OK { return Err(ctx.err(rc)); }
+            out.truncate(n);
+            Ok(out)
+        }
+    }
     pub fn raw(&self) -> *mut p2g_circuit { self.raw }
 }
 impl Drop for GpuCircuit { fn drop(&mut self) { unsafe { p2g_circuit_free(self.ctx, self.raw); } } }
