@@ -420,6 +420,124 @@ __device__ __forceinline__ void poseidon_partial_pair(gl_t s[12], int pair, int 
     for (int r = 0; r < 12; r++) s[r] = pos_readout(al[r], ah[r]);
 }
 #endif  // P2G_PAIR_SPLIT
+// P2G_PAIR_BASIS=1: experiment, off.  Measured (profiles/r2_poseidon_pair_basis_experiment.txt): chained permutations
+// 1.512 -> 1.553 G/s with the basis entered in FP64 under a `first` flag (but 68 bytes of spills in the Merkle leaf
+// kernel: its time unchanged, 3.40 ms), 1.520 G/s in this form (integer entry, no spills: leaf kernel 3.40 ms as well),
+// 1.447 G/s with the last pair as a second instantiation of the body (instruction fetch).  The proof rate did not move.
+#ifndef P2G_PAIR_BASIS
+#define P2G_PAIR_BASIS 0
+#endif
+#if P2G_PAIR_BASIS && P2G_PAIR_SPLIT
+// The pair with its state kept in the (E, F) basis between pairs: E_j = u_j + u_{j+6}, F_j = u_j - u_{j+6} (j < 6).
+// The split accumulators of a pair are exactly E / 2 and F / 2 of its output, so with all coefficients doubled
+// (free) a pair reads (E, F) and writes (E', F'): neither the recombination acc+ +- acc- at the end of a pair nor the
+// X+- formation at the start of the next is needed -- 198 instead of 236 FP64 instructions.  Word 0, the only one that
+// meets an S-box, is (E'_0 + F'_0) / 2, exact on the accumulators (every bias is even); inside a pair it becomes
+// E_0 = y0 + x6, F_0 = y0 - x6 with x6 = E_0 - x0.  Between pairs s[] holds [e_0..e_5, x0, f_1..f_5]
+// (poseidon_to_pair_basis converts the natural state once, in integer arithmetic); the last pair writes the natural
+// state (a uniform branch: two instantiations of this body measured 1.45 instead of 1.55 G perm/s, instruction fetch).  Tables and an exact emulation of this function: tools/gen_poseidon_f64.py (POSEIDON_PAIRB_*).
+// natural state -> [e_0..e_5, x0, f_1..f_5], e_j = x_j + x_{j+6}, f_j = x_j - x_{j+6} (lazy residues)
+__device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c);
+__device__ __forceinline__ void poseidon_to_pair_basis(gl_t s[12]) {
+    const gl_t x0 = s[0];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const gl_t b = gl_canon(s[j + 6]);
+        const gl_t e = gl_add_lazy_dev(s[j], b), f = gl_sub(s[j], b);
+        s[j] = e; s[j + 6] = f;
+    }
+    s[6] = x0;
+}
+__device__ __forceinline__ void poseidon_partial_pair_basis(gl_t s[12], int pair, int zero, bool last) {
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    const double C2[12] = POSEIDON_C2_INIT;
+    const double BIAS = 4503599627370496.0;               // 2^52
+    double ppl[3], pml[3], fal[6], pph[3], pmh[3], fah[6];
+    const int pz = 12 * pair + zero;                      // per-thread looking index: LDC instead of LDCU + moves
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        ppl[r] = POSEIDON_PAIRB_LO[pz + r]; pml[r] = POSEIDON_PAIRB_LO[pz + 3 + r];
+        pph[r] = POSEIDON_PAIRB_HI[pz + r]; pmh[r] = POSEIDON_PAIRB_HI[pz + 3 + r];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) { fal[r] = POSEIDON_PAIRB_LO[pz + 6 + r]; fah[r] = POSEIDON_PAIRB_HI[pz + 6 + r]; }
+    double tl = POSEIDON_PAIRB_T_LO[pair + zero], th = POSEIDON_PAIRB_T_HI[pair + zero];
+    const gl_t y0 = poseidon_sbox(s[6]);
+    const double y0l = (double)(uint32_t)y0, y0h = (double)(uint32_t)(y0 >> 32);
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) {
+        const int j = (jj + 1) % 3;                       // group (0, 3) last: the S-box chain of word 0 hides behind the others
+        // e_j, f_j (x0 for j = 0), e_{j+3}, f_{j+3}
+        double e0l = (double)(uint32_t)s[j], e0h = (double)(uint32_t)(s[j] >> 32);
+        double f0l = (double)(uint32_t)s[j + 6], f0h = (double)(uint32_t)(s[j + 6] >> 32);
+        const double e1l = (double)(uint32_t)s[j + 3], e1h = (double)(uint32_t)(s[j + 3] >> 32);
+        const double f1l = (double)(uint32_t)s[j + 9], f1h = (double)(uint32_t)(s[j + 9] >> 32);
+        if (j == 0) {                                      // e0 = e_0, f0 = x0: x6 = e_0 - x0, then E_0 = y0 + x6, F_0 = y0 - x6
+            const double x6l = __dsub_rn(e0l, f0l), x6h = __dsub_rn(e0h, f0h);
+            e0l = __dadd_rn(y0l, x6l); f0l = __dsub_rn(y0l, x6l); e0h = __dadd_rn(y0h, x6h); f0h = __dsub_rn(y0h, x6h);
+        }
+#ifdef P2G_DIAG_NO_MDS
+        fal[j] = __dadd_rn(fal[j], __dadd_rn(__dadd_rn(e0l, f0l), __dadd_rn(e1l, f1l)));
+        fah[j] = __dadd_rn(fah[j], __dadd_rn(__dadd_rn(e0h, f0h), __dadd_rn(e1h, f1h)));
+#else
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const double n0 = C2[(j - r + 12) % 12] - C2[(j + 6 - r + 12) % 12], n1 = C2[(j + 3 - r + 12) % 12] - C2[(j + 9 - r + 12) % 12];
+            fal[r] = __fma_rn(f0l, n0, fal[r]); fal[r] = __fma_rn(f1l, n1, fal[r]);
+            fah[r] = __fma_rn(f0h, n0, fah[r]); fah[r] = __fma_rn(f1h, n1, fah[r]);
+        }
+        const double upl = __dadd_rn(e0l, e1l), uml = __dsub_rn(e0l, e1l), uph = __dadd_rn(e0h, e1h), umh = __dsub_rn(e0h, e1h);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const double pa = 0.5 * (C2[(j - r + 12) % 12] + C2[(j + 6 - r + 12) % 12]);
+            const double pb = 0.5 * (C2[(j + 3 - r + 12) % 12] + C2[(j + 9 - r + 12) % 12]);
+            ppl[r] = __fma_rn(upl, pa + pb, ppl[r]); pml[r] = __fma_rn(uml, pa - pb, pml[r]);
+            pph[r] = __fma_rn(uph, pa + pb, pph[r]); pmh[r] = __fma_rn(umh, pa - pb, pmh[r]);
+        }
+#endif
+        // row 0 of M on the (E, F) inputs
+        const double m0a = C[j] + (j == 0 ? 8. : 0.), m0b = C[j + 6], m1a = C[j + 3], m1b = C[j + 9];
+        tl = __fma_rn(e0l, 0.5 * (m0a + m0b), tl); tl = __fma_rn(f0l, 0.5 * (m0a - m0b), tl);
+        tl = __fma_rn(e1l, 0.5 * (m1a + m1b), tl); tl = __fma_rn(f1l, 0.5 * (m1a - m1b), tl);
+        th = __fma_rn(e0h, 0.5 * (m0a + m0b), th); th = __fma_rn(f0h, 0.5 * (m0a - m0b), th);
+        th = __fma_rn(e1h, 0.5 * (m1a + m1b), th); th = __fma_rn(f1h, 0.5 * (m1a - m1b), th);
+    }
+    const gl_t z0 = poseidon_sbox(pos_readout(tl, th));
+    // while that S-box runs: E'_r = pp_r + pm_r, E'_{r+3} = pp_r - pm_r
+    double el[6], eh[6];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        el[r] = __dadd_rn(ppl[r], pml[r]); el[r + 3] = __dsub_rn(ppl[r], pml[r]);
+        eh[r] = __dadd_rn(pph[r], pmh[r]); eh[r + 3] = __dsub_rn(pph[r], pmh[r]);
+    }
+    const double mzl = __hiloint2double(0x43300000, (int)(uint32_t)z0), mzh = __hiloint2double(0x43300000, (int)(uint32_t)(z0 >> 32));
+    const double gl = __fma_rn(y0l, 8., __dsub_rn(mzl, tl)), gh = __fma_rn(y0h, 8., __dsub_rn(mzh, th));   // 8 y0 + z - t0 (+ E)
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        const double cp = C[(12 - r) % 12] + C[(6 - r) % 12], cn = C[(12 - r) % 12] - C[(6 - r) % 12];       // cc[r] +- cc[r + 6]
+        el[r] = __fma_rn(gl, cp, el[r]); fal[r] = __fma_rn(gl, cn, fal[r]);
+        eh[r] = __fma_rn(gh, cp, eh[r]); fah[r] = __fma_rn(gh, cn, fah[r]);
+    }
+    const double zpl = __dsub_rn(mzl, BIAS), zph = __dsub_rn(mzh, BIAS);
+    el[0] = __fma_rn(zpl, 8., el[0]); fal[0] = __fma_rn(zpl, 8., fal[0]);
+    eh[0] = __fma_rn(zph, 8., eh[0]); fah[0] = __fma_rn(zph, 8., fah[0]);
+    double ol[12], oh[12];
+    if (last) {                                           // natural state: u_r = (E'_r + F'_r) / 2, u_{r+6} = (E'_r - F'_r) / 2
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const double hl = 0.5 * el[r], hh = 0.5 * eh[r];
+            ol[r] = __fma_rn(fal[r], 0.5, hl); ol[r + 6] = __dadd_rn(__fma_rn(fal[r], -0.5, hl), POSEIDON_PAIRB_EXIT_LO);
+            oh[r] = __fma_rn(fah[r], 0.5, hh); oh[r + 6] = __dadd_rn(__fma_rn(fah[r], -0.5, hh), POSEIDON_PAIRB_EXIT_HI);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 6; r++) { ol[r] = el[r]; oh[r] = eh[r]; ol[r + 6] = fal[r]; oh[r + 6] = fah[r]; }
+        ol[6] = __fma_rn(fal[0], 0.5, 0.5 * el[0]); oh[6] = __fma_rn(fah[0], 0.5, 0.5 * eh[0]);   // word 0 for the next pair's S-box
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = pos_readout(ol[r], oh[r]);
+}
+#endif
 __device__ __forceinline__ gl_t gl_add_lazy_dev(gl_t a, gl_t c) {   // c canonical
     gl_t s = a + c;
     return s < a ? s + GL_EPS : s;
@@ -440,8 +558,14 @@ __device__ __forceinline__ void poseidon_permute_lazy(gl_t s[12]) {
         if (phase == 0) {
 #if P2G_PARTIAL_PAIRS
             const int zero = pos_lane_zero();
+#if P2G_PAIR_BASIS && P2G_PAIR_SPLIT
+            poseidon_to_pair_basis(s);
+#pragma unroll 1
+            for (int p = 0; p < 11; p++, k += 2) poseidon_partial_pair_basis(s, p, zero, p == 10);   // ONE copy of the body: a second one costs more in instruction fetch than the branch
+#else
 #pragma unroll 1
             for (int p = 0; p < 11; p++, k += 2) poseidon_partial_pair(s, p, zero);
+#endif
 #else
 #pragma unroll 1
             for (int r = 0; r < 22; r++, k++) {

@@ -319,3 +319,159 @@ for pat in pats:
         ref = [(a + b) % P for a, b in zip(mds(vals), rc_true[12 * row:12 * row + 12])]
         assert full_round_emulated(pat, row) == ref, row
 print("split full round ok")
+
+
+# ---- the pair in the (E, F) basis (csrc/poseidon.cuh, poseidon_partial_pair_basis) ---------------------------------
+# Between two pairs the state is kept as E_j = u_j + u_{j+6}, F_j = u_j - u_{j+6} (j < 6): a pair's split accumulators
+# give exactly these (acc+ = E / 2, acc- = F / 2; all coefficients doubled here, which is free), so neither the
+# recombination at the end of a pair nor the X+- formation at the start of the next one is needed -- 198 instead of 236
+# FP64 instructions per pair.  Word 0, the only one that meets an S-box, is (E_0 + F_0) / 2, exact on the accumulators.
+# Per pair and 32-bit half the table holds [KPP_0..2, KPM_0..2, KF_0..5]: E'_r = pp_r + pm_r, E'_{r+3} = pp_r - pm_r.
+# Every KE_r / KF_r is even, so (E'_0 + F'_0) / 2 and, in the last pair, (E'_r +- F'_r) / 2 are integers.
+def even_rep(v, mult):
+    """(lo, hi) of v (mod p) with both parts even and offset by mult * (DL, DH)"""
+    lo, hi = (v & 0xFFFFFFFF) + mult * DL, (v >> 32) + mult * DH
+    a, b = PARITY_FIX[(lo & 1, hi & 1)]
+    return lo + a, hi + b
+
+
+PB_LO, PB_HI = [], []
+for p in range(11):
+    kA = 4 + 2 * p
+    cA = rc_true[12 * (kA + 1):12 * (kA + 2)]
+    cB = rc_true[12 * (kA + 2):12 * (kA + 3)]
+    Kp = [(sum(M[r][k] * cA[k] for k in range(12)) + cB[r]) % P for r in range(12)]
+    KE, KF = [], []
+    for r in range(6):
+        e0 = -8 * cA[0] if r == 0 else 0
+        KE.append(even_rep((Kp[r] + Kp[r + 6] + e0 - (cc[r] + cc[r + 6]) * E_READ - E_READ) % P, 4))
+        KF.append(even_rep((Kp[r] - Kp[r + 6] + e0 - (cc[r] - cc[r + 6]) * E_READ - E_READ) % P, 4))
+    for half, out in ((0, PB_LO), (1, PB_HI)):
+        out += [(KE[r][half] + KE[r + 3][half]) // 2 for r in range(3)]
+        out += [(KE[r][half] - KE[r + 3][half]) // 2 for r in range(3)]
+        out += [2**52 + KF[r][half] for r in range(6)]
+        assert all((KE[r][half] + KE[r + 3][half]) % 2 == 0 for r in range(3))
+    # pp carries the 2^52 of E' (pp + pm and pp - pm are both 2^52 + ...)
+    for out in (PB_LO, PB_HI):
+        for r in range(3):
+            out[12 * p + r] += 2**52
+EXIT_LO, EXIT_HI = even_rep((-E_READ) % P, 4)
+# the t accumulator (row 0 of M on the (E, F) inputs) has negative coefficients on F: a small offset that is 0 mod p
+# (E_0 = y0 + x6 and F_0 = y0 - x6 can be as low as -2^32 per half, F_3 / F_4 meet -1 / -16: the sum is above -42 * 2^32)
+TOFF = (44 * 2**32 + 45, 45 * 2**32 - 89)
+assert (TOFF[0] + (TOFF[1] << 32)) % P == 0
+text = table("POSEIDON_PAIRB_LO", PB_LO) + "\n" + table("POSEIDON_PAIRB_HI", PB_HI) + "\n"
+text += "#define POSEIDON_PAIRB_EXIT_LO %s\n#define POSEIDON_PAIRB_EXIT_HI %s\n" % (fmt(2**52 + EXIT_LO), fmt(2**52 + EXIT_HI))
+PBT_LO = [2**52 + ((rc_true[12 * (5 + 2 * p)] - E_READ) % P & 0xFFFFFFFF) + TOFF[0] for p in range(11)] + [0]
+PBT_HI = [2**52 + ((rc_true[12 * (5 + 2 * p)] - E_READ) % P >> 32) + TOFF[1] for p in range(11)] + [0]
+text += table("POSEIDON_PAIRB_T_LO", PBT_LO) + "\n" + table("POSEIDON_PAIRB_T_HI", PBT_HI) + "\n"
+open(os.path.join(csrc, "poseidon_rc_f64.inc"), "a").write(text)
+
+
+def pair_basis_emulated(st, p, first, last, force_y0=None, force_z=None):
+    """st: natural state (first) or [e_0..e_5, x0, f_1..f_5] as field elements (any representative < 2^64);
+    force_y0 / force_z replace the two S-box outputs by given lazy words (range checks only)"""
+    kA = 4 + 2 * p
+    cA0e = (rc_true[12 * (kA + 1)] - E_READ) % P
+    halves = lambda v: (Fraction(v & 0xFFFFFFFF), Fraction(v >> 32))
+    x0 = st[0] if first else st[6]
+    y0 = sbox(x0) if force_y0 is None else force_y0
+    Eo, Fo, tb, y0h, x0h = [], [], [], halves(y0), halves(x0)
+    for h, (tabp, t_init) in enumerate(((PB_LO, 2**52 + (cA0e & 0xFFFFFFFF) + TOFF[0]), (PB_HI, 2**52 + (cA0e >> 32) + TOFF[1]))):
+        if first:
+            xs = [halves(v)[h] for v in st]
+            E = [dbl(xs[j] + xs[j + 6]) for j in range(6)]
+            F = [dbl(xs[j] - xs[j + 6]) for j in range(6)]
+            x6 = xs[6]
+        else:
+            E = [halves(st[j])[h] for j in range(6)]
+            F = [None] + [halves(st[6 + j])[h] for j in range(1, 6)]
+            x6 = dbl(E[0] - x0h[h])
+        E[0] = dbl(y0h[h] + x6); F[0] = dbl(y0h[h] - x6)
+        pp = [Fraction(tabp[12 * p + r]) for r in range(3)]
+        pm = [Fraction(tabp[12 * p + 3 + r]) for r in range(3)]
+        Fa = [Fraction(tabp[12 * p + 6 + r]) for r in range(6)]
+        t = Fraction(t_init)
+        for j in (1, 2, 0):
+            for jj in (j, j + 3):
+                for r in range(6):
+                    a, b = C2[(jj - r) % 12], C2[(jj + 6 - r) % 12]
+                    Fa[r] = dbl(Fa[r] + F[jj] * (a - b))
+                m0a = M[0][jj]; m0b = M[0][jj + 6]
+                assert (m0a + m0b) % 2 == 0
+                t = dbl(t + E[jj] * ((m0a + m0b) // 2)); t = dbl(t + F[jj] * ((m0a - m0b) // 2))
+            up, um = dbl(E[j] + E[j + 3]), dbl(E[j] - E[j + 3])
+            for r in range(3):
+                a = (C2[(j - r) % 12] + C2[(j + 6 - r) % 12]) // 2
+                b = (C2[(j + 3 - r) % 12] + C2[(j + 9 - r) % 12]) // 2
+                pp[r] = dbl(pp[r] + up * (a + b)); pm[r] = dbl(pm[r] + um * (a - b))
+        Eo.append([dbl(pp[r] + pm[r]) for r in range(3)] + [dbl(pp[r] - pm[r]) for r in range(3)])
+        Fo.append(Fa); tb.append(t)
+    t0 = readout(tb[0], tb[1])
+    xs_true = [y0] + ([v % P for v in st[1:]] if first else None or [])
+    z = sbox(t0) if force_z is None else force_z
+    zh = halves(z)
+    for h in range(2):
+        mz = Fraction(2**52 + zh[h])
+        gg = dbl(dbl(mz - tb[h]) + 8 * y0h[h])
+        for r in range(6):
+            Eo[h][r] = dbl(Eo[h][r] + gg * (cc[r] + cc[r + 6]))
+            Fo[h][r] = dbl(Fo[h][r] + gg * (cc[r] - cc[r + 6]))
+        z8 = dbl(8 * dbl(mz - 2**52))
+        Eo[h][0] = dbl(Eo[h][0] + z8); Fo[h][0] = dbl(Fo[h][0] + z8)
+    if last:
+        ex = (2**52 + EXIT_LO, 2**52 + EXIT_HI)
+        nat = [[None] * 12 for _ in range(2)]
+        for h in range(2):
+            for r in range(6):
+                he = dbl(Eo[h][r] / 2)
+                nat[h][r] = dbl(he + Fo[h][r] / 2)
+                nat[h][r + 6] = dbl(dbl(he - Fo[h][r] / 2) + ex[h])
+        return [readout(nat[0][r], nat[1][r]) for r in range(12)]
+    y0acc = [dbl(dbl(Eo[h][0] / 2) + Fo[h][0] / 2) for h in range(2)]
+    return ([readout(Eo[0][r], Eo[1][r]) for r in range(6)] + [readout(y0acc[0], y0acc[1])] +
+            [readout(Fo[0][r], Fo[1][r]) for r in range(1, 6)])
+
+
+for trial in range(12):
+    if trial == 0: s = [P - 1] * 12
+    elif trial == 1: s = [0] * 12
+    elif trial == 2: s = [0xFFFFFFFFFFFFFFFF] * 6 + [0] * 6
+    elif trial == 3: s = [0] * 6 + [0xFFFFFFFFFFFFFFFF] * 6
+    elif trial == 4: s = [0xFFFFFFFF] * 12
+    else: s = [random.randrange(P) for _ in range(12)]
+    ref = [v % P for v in s]
+    # poseidon_to_pair_basis: the natural state enters the basis once, in integer arithmetic
+    st = [(s[j] + s[j + 6]) % P for j in range(6)] + [s[0] % P] + [(s[j] - s[j + 6]) % P for j in range(1, 6)]
+    for p in range(11):
+        kA = 4 + 2 * p
+        for k in (kA, kA + 1):
+            ref[0] = sbox(ref[0])
+            ref = [(a + b) % P for a, b in zip(mds(ref), rc_true[12 * (k + 1):12 * (k + 2)])]
+        st = pair_basis_emulated(st, p, False, p == 10)
+        if p < 10:
+            e, x0, f = st[:6], st[6], [None] + st[7:]
+            assert x0 % P == ref[0] and all(e[j] % P == (ref[j] + ref[j + 6]) % P for j in range(6))
+            assert all(f[j] % P == (ref[j] - ref[j + 6]) % P for j in range(1, 6)), (trial, p)
+    assert [v % P for v in st] == ref, trial
+# worst-case magnitudes inside the chain: basis words forced to extreme representatives
+U = 0xFFFFFFFFFFFFFFFF
+for pat in ([U] * 12, [0] * 12, [U] * 6 + [0] * 6, [0] * 7 + [U] * 5, [U if j % 2 else 0 for j in range(12)], [U, 0, 0, U, 0, 0, U] + [0, U, 0, U, 0]):
+    for p in range(1, 10):
+        pair_basis_emulated(list(pat), p, False, False)
+    pair_basis_emulated(list(pat), 10, False, True)
+    pair_basis_emulated(list(pat), 0, False, False)
+print("basis pair tables ok")
+# random extreme representatives (each basis word 0, 2^64 - 1, low half only, high half only) through every pair
+EXT = [0, U, 0xFFFFFFFF, 0xFFFFFFFF00000000]
+for trial in range(int(os.environ.get("P2G_GEN_TRIALS", "3000"))):
+    pat = [random.choice(EXT) for _ in range(12)]
+    p = random.randrange(0, 11)
+    try:
+        pair_basis_emulated(list(pat), p, False, p == 10, random.choice(EXT + [None]), random.choice(EXT + [None]))
+        if 0 < p < 10:
+            pair_basis_emulated(list(pat), p, False, False, random.choice(EXT), random.choice(EXT))
+    except AssertionError:
+        print("range violation", p, [hex(v) for v in pat])
+        raise
+print("basis pair extremes ok")
