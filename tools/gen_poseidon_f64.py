@@ -408,7 +408,6 @@ def pair_basis_emulated(st, p, first, last, force_y0=None, force_z=None):
         Eo.append([dbl(pp[r] + pm[r]) for r in range(3)] + [dbl(pp[r] - pm[r]) for r in range(3)])
         Fo.append(Fa); tb.append(t)
     t0 = readout(tb[0], tb[1])
-    xs_true = [y0] + ([v % P for v in st[1:]] if first else None or [])
     z = sbox(t0) if force_z is None else force_z
     zh = halves(z)
     for h in range(2):
